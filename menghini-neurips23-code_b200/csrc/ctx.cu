@@ -1,0 +1,77 @@
+// Context management + TMA descriptor encoding for libgripb200.
+#include "ctx.h"
+
+extern "C" const char* gb_version(void) { return "gripb200 0.1 (sm_100a)"; }
+
+extern "C" int gb_create(gb_ctx** out, int device) {
+  if (!out) return GB_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+    cudaGetLastError();
+    return GB_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return GB_ERR_CUDA;
+  if (prop.major != 10) return GB_ERR_NO_DEVICE;  // tcgen05 kernels are sm_100a-only
+  if (cudaSetDevice(device) != cudaSuccess) return GB_ERR_CUDA;
+  cudaFree(0);
+  gb_ctx* c = new gb_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) !=
+          cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || fn == nullptr) {
+    delete c;
+    return GB_ERR_CUDA;
+  }
+  c->encode_tiled = reinterpret_cast<PFN_encodeTiled>(fn);
+  *out = c;
+  return GB_OK;
+}
+
+void gb_tower_free(gb_tower* t);
+
+extern "C" int gb_destroy(gb_ctx* c) {
+  if (!c) return GB_ERR_ARG;
+  cudaSetDevice(c->device);
+  if (c->ws) cudaFree(c->ws);
+  gb_tower_free(c->vit);
+  gb_tower_free(c->text);
+  delete c;
+  return GB_OK;
+}
+
+extern "C" const char* gb_last_error(gb_ctx* c) { return c ? c->err.c_str() : "null ctx"; }
+extern "C" uint64_t gb_launch_count(gb_ctx* c) { return c ? c->launches : 0; }
+
+int gb_ws_reserve(gb_ctx* c, size_t bytes) {
+  if (bytes <= c->ws_bytes) return GB_OK;
+  GB_CUDA(c, cudaDeviceSynchronize());
+  if (c->ws) GB_CUDA(c, cudaFree(c->ws));
+  c->ws = nullptr;
+  c->ws_bytes = 0;
+  GB_CUDA(c, cudaMalloc(&c->ws, bytes));
+  c->ws_bytes = bytes;
+  return GB_OK;
+}
+
+int gb_make_tmap_2d_f16(gb_ctx* c, CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols,
+                        uint64_t ld_elems, uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = c->encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims,
+                               strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return gb_fail(c, GB_ERR_CUDA,
+                   "cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%llu cols=%llu ld=%llu box=%u",
+                   (int)r, ptr, (unsigned long long)rows, (unsigned long long)cols,
+                   (unsigned long long)ld_elems, box_rows);
+  return GB_OK;
+}

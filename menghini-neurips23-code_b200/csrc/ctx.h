@@ -1,0 +1,69 @@
+// Host-side context shared by all C-ABI entry points of libgripb200.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gripb200.h"
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct gb_tower;  // tower.cu
+
+struct gb_ctx {
+  int device = 0;
+  int num_sms = 148;
+  std::string err;
+  PFN_encodeTiled encode_tiled = nullptr;
+  uint64_t launches = 0;  // kernels launched through this ctx (bench.py reports it)
+  // workspace owned by the ctx (grown on demand, never inside a timed region after warm-up)
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  gb_tower* vit = nullptr;
+  gb_tower* text = nullptr;
+};
+
+inline int gb_fail(gb_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+#define GB_CUDA(c, expr)                                                                  \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess)                                                                \
+      return gb_fail((c), GB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                     __FILE__, __LINE__);                                                 \
+  } while (0)
+
+#define GB_LAUNCH_CHECK(c)                                                               \
+  do {                                                                                   \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess)                                                               \
+      return gb_fail((c), GB_ERR_CUDA, "kernel launch failed: %s (%s:%d)",               \
+                     cudaGetErrorString(_e), __FILE__, __LINE__);                        \
+    (c)->launches++;                                                                     \
+  } while (0)
+
+// 2-D fp16 row-major tensor map with 128 B swizzle: box = {64 elements, box_rows}.
+int gb_make_tmap_2d_f16(gb_ctx* c, CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols,
+                        uint64_t ld_elems, uint32_t box_rows);
+
+// internal launchers shared between op-level and tower-level entry points
+int gb_launch_gemm(gb_ctx* c, const void* A, int lda, const void* W, int ldw, const float* bias,
+                   const void* resid, int ldr, void* out, int ldo, int M, int N, int K, int act,
+                   int out_f32, cudaStream_t st);
+int gb_ws_reserve(gb_ctx* c, size_t bytes);

@@ -1,0 +1,62 @@
+// Host launcher + C-ABI entry for the tcgen05 GEMM.
+#include "ctx.h"
+#include "gemm_tcgen05.cuh"
+
+using namespace gb;
+
+template <int BN>
+static int launch_gemm_bn(gb_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                          const GemmParams& p, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set[16] = {false};
+  if (!attr_set[c->device & 15]) {
+    GB_CUDA(c, cudaFuncSetAttribute(gemm_f16_tcgen05_kernel<BN>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set[c->device & 15] = true;
+  }
+  const int m_tiles = (p.M + kBM - 1) / kBM;
+  const int tiles = m_tiles * (p.N / BN);
+  const int grid = tiles < c->num_sms ? tiles : c->num_sms;
+  gemm_f16_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+  GB_LAUNCH_CHECK(c);
+  return GB_OK;
+}
+
+int gb_launch_gemm(gb_ctx* c, const void* A, int lda, const void* W, int ldw, const float* bias,
+                   const void* resid, int ldr, void* out, int ldo, int M, int N, int K, int act,
+                   int out_f32, cudaStream_t st) {
+  if (!A || !W || !out) return gb_fail(c, GB_ERR_ARG, "gemm: null pointer");
+  if (M <= 0) return GB_OK;
+  if (K % kBK != 0 || N % 128 != 0 || lda % 8 != 0 || ldw % 8 != 0 || ldo % 8 != 0 ||
+      (resid && ldr % 8 != 0))
+    return gb_fail(c, GB_ERR_ARG, "gemm: unsupported shape M=%d N=%d K=%d lda=%d ldw=%d ldo=%d", M,
+                   N, K, lda, ldw, ldo);
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) |
+       reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(resid) |
+       reinterpret_cast<uintptr_t>(bias)) & 15)
+    return gb_fail(c, GB_ERR_ARG, "gemm: pointers must be 16-byte aligned");
+  // 256-wide tiles halve the per-FLOP shared-memory traffic; use them when they still fill the GPU.
+  const int m_tiles = (M + kBM - 1) / kBM;
+  const bool wide = (N % 256 == 0) && (m_tiles * (N / 256) >= c->num_sms);
+  const int BN = wide ? 256 : 128;
+  CUtensorMap tmA, tmB;
+  int rc = gb_make_tmap_2d_f16(c, &tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM);
+  if (rc) return rc;
+  rc = gb_make_tmap_2d_f16(c, &tmB, W, (uint64_t)N, (uint64_t)K, (uint64_t)ldw, BN);
+  if (rc) return rc;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.out = out; p.ldo = ldo;
+  p.bias = bias;
+  p.resid = reinterpret_cast<const __half*>(resid); p.ldr = ldr;
+  p.act = act; p.out_f32 = out_f32;
+  return wide ? launch_gemm_bn<256>(c, tmA, tmB, p, st) : launch_gemm_bn<128>(c, tmA, tmB, p, st);
+}
+
+extern "C" int gb_gemm_f16(gb_ctx* c, const void* A, int lda, const void* W, int ldw,
+                           const float* bias, const void* resid, int ldr, void* out, int ldo, int M,
+                           int N, int K, int act, int out_f32, void* stream) {
+  if (!c) return GB_ERR_ARG;
+  return gb_launch_gemm(c, A, lda, W, ldw, bias, resid, ldr, out, ldo, M, N, K, act, out_f32,
+                        reinterpret_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,350 @@
+// Row-wise kernels around the GEMMs: LayerNorm (CLIP's fp32-internal LayerNorm), im2col of the
+// 32×32/stride-32 patch conv, token assembly (+ln_pre) for both towers, L2 row normalisation.
+// All are single-pass, HBM-streaming kernels: one warp per row, 16-byte vector accesses.
+#include "ctx.h"
+#include "common.cuh"
+
+using namespace gb;
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm over D ∈ {512, 768} (D % 256 == 0).  y = (x-mean)/sqrt(var+eps)*g + b, fp32 math,
+// two-pass variance like torch.native_layer_norm.  in_row = row_idx ? row_idx[r] : r*in_row_mul.
+// Reference: clip.model.LayerNorm (x.float() → layer_norm → .type(orig)) used by ln_pre, ln_1,
+// ln_2, ln_post (models/clip_encoders.py:157,189) and ln_final (:85).
+// ---------------------------------------------------------------------------------------------
+template <int D, typename OutT>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const __half* __restrict__ x, int ldx, const int32_t* __restrict__ row_idx,
+                 int in_row_mul, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 OutT* __restrict__ y, int ldy, int rows, float eps) {
+  constexpr int V = D / 256;  // 16-byte chunks per lane
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const size_t in_row = row_idx ? (size_t)row_idx[warp] : (size_t)warp * in_row_mul;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + in_row * ldx);
+  float f[V * 8];
+  float s = 0.f;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const uint4 u = xr[v * 32 + lane];
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 a = __half22float2(h[t]);
+      f[v * 8 + 2 * t] = a.x;
+      f[v * 8 + 2 * t + 1] = a.y;
+      s += a.x + a.y;
+    }
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V * 8; ++i) {
+    const float d = f[i] - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const int col = (v * 32 + lane) * 8;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + col));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
+    float o[8];
+    o[0] = (f[v * 8 + 0] - mean) * rstd * g0.x + b0.x;
+    o[1] = (f[v * 8 + 1] - mean) * rstd * g0.y + b0.y;
+    o[2] = (f[v * 8 + 2] - mean) * rstd * g0.z + b0.z;
+    o[3] = (f[v * 8 + 3] - mean) * rstd * g0.w + b0.w;
+    o[4] = (f[v * 8 + 4] - mean) * rstd * g1.x + b1.x;
+    o[5] = (f[v * 8 + 5] - mean) * rstd * g1.y + b1.y;
+    o[6] = (f[v * 8 + 6] - mean) * rstd * g1.z + b1.z;
+    o[7] = (f[v * 8 + 7] - mean) * rstd * g1.w + b1.w;
+    if constexpr (sizeof(OutT) == 2) {
+      uint4 u;
+      __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(o[2 * t], o[2 * t + 1]);
+      reinterpret_cast<uint4*>(y + (size_t)warp * ldy)[v * 32 + lane] = u;
+    } else {
+      float4* yo = reinterpret_cast<float4*>(y + (size_t)warp * ldy + col);
+      yo[0] = make_float4(o[0], o[1], o[2], o[3]);
+      yo[1] = make_float4(o[4], o[5], o[6], o[7]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// im2col for conv1 (kernel = stride = 32, no bias): out[(b*49 + py*7 + px), c*1024 + ky*32 + kx]
+//   = img[b, c, py*32 + ky, px*32 + kx]   (fp32 or fp16 NCHW in → fp16 out).
+// Because stride == kernel the re-index is a permutation: every input element is read once.
+// Reference: self.conv1(x) + reshape/permute, models/clip_encoders.py:131-133.
+// ---------------------------------------------------------------------------------------------
+template <typename InT>
+__global__ void __launch_bounds__(256)
+im2col_patch32_kernel(const InT* __restrict__ img, __half* __restrict__ out, int B) {
+  // one thread per 8 consecutive kx: total = B*3*224*28 groups
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)B * 3 * 224 * 28;
+  if (gid >= total) return;
+  const int x8 = gid % 28;
+  const int y = (gid / 28) % 224;
+  const int c = (gid / (28 * 224)) % 3;
+  const int b = gid / (28 * 224 * 3);
+  const InT* src = img + (((size_t)b * 3 + c) * 224 + y) * 224 + x8 * 8;
+  float v[8];
+  if constexpr (sizeof(InT) == 4) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+    const float4 d = __ldg(reinterpret_cast<const float4*>(src) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = d.x; v[5] = d.y; v[6] = d.z; v[7] = d.w;
+  } else {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src));
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 a = __half22float2(h[t]);
+      v[2 * t] = a.x; v[2 * t + 1] = a.y;
+    }
+  }
+  const int py = y >> 5, ky = y & 31, px = (x8 * 8) >> 5, kx = (x8 * 8) & 31;
+  uint4 o;
+  __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(v[2 * t], v[2 * t + 1]);
+  __half* dst = out + ((size_t)b * 49 + py * 7 + px) * 3072 + c * 1024 + ky * 32 + kx;
+  *reinterpret_cast<uint4*>(dst) = o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Vision token assembly fused with ln_pre (D = 768):
+//   row l of image b:  l == 0      → class_embedding + pos[0]
+//                      1 ≤ l ≤ P   → prefix[l-1]            (no positional embedding!)
+//                      l > P       → patch[b, l-1-P] + pos[l-P]
+//   x[b*L + l] = ln_pre(row)            (fp16 residual stream)
+// Reference: models/clip_encoders.py:135-157 (prefix inserted after pos-emb, before ln_pre).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+vit_assemble_lnpre_kernel(const __half* __restrict__ patch, const float* __restrict__ cls,
+                          const float* __restrict__ pos, const float* __restrict__ prefix, int P,
+                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                          __half* __restrict__ x, int B, float eps) {
+  constexpr int D = 768, V = 3;
+  const int L = 50 + P;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * L) return;
+  const int b = warp / L, l = warp % L;
+  float f[V * 8];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const int col = (v * 32 + lane) * 8;
+    float a[8];
+    if (l >= 1 && l <= P) {
+      const float4 p0 = __ldg(reinterpret_cast<const float4*>(prefix + (size_t)(l - 1) * D + col));
+      const float4 p1 = __ldg(reinterpret_cast<const float4*>(prefix + (size_t)(l - 1) * D + col + 4));
+      a[0] = p0.x; a[1] = p0.y; a[2] = p0.z; a[3] = p0.w; a[4] = p1.x; a[5] = p1.y; a[6] = p1.z; a[7] = p1.w;
+    } else {
+      const int pl = (l == 0) ? 0 : l - P;  // positional row
+      const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos + (size_t)pl * D + col));
+      const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos + (size_t)pl * D + col + 4));
+      a[0] = p0.x; a[1] = p0.y; a[2] = p0.z; a[3] = p0.w; a[4] = p1.x; a[5] = p1.y; a[6] = p1.z; a[7] = p1.w;
+      if (l == 0) {
+        const float4 c0 = __ldg(reinterpret_cast<const float4*>(cls + col));
+        const float4 c1 = __ldg(reinterpret_cast<const float4*>(cls + col + 4));
+        a[0] += c0.x; a[1] += c0.y; a[2] += c0.z; a[3] += c0.w; a[4] += c1.x; a[5] += c1.y; a[6] += c1.z; a[7] += c1.w;
+      } else {
+        const uint4 u = *reinterpret_cast<const uint4*>(patch + ((size_t)b * 49 + (l - 1 - P)) * D + col);
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 e = __half22float2(h[t]);
+          a[2 * t] += e.x; a[2 * t + 1] += e.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[v * 8 + i] = a[i];
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V * 8; ++i) s += f[i];
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V * 8; ++i) { const float d = f[i] - mean; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const int col = (v * 32 + lane) * 8;
+    uint4 u;
+    __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int c0 = col + 2 * t;
+      const float o0 = (f[v * 8 + 2 * t] - mean) * rstd * __ldg(gamma + c0) + __ldg(beta + c0);
+      const float o1 = (f[v * 8 + 2 * t + 1] - mean) * rstd * __ldg(gamma + c0 + 1) + __ldg(beta + c0 + 1);
+      h[t] = __floats2half2_rn(o0, o1);
+    }
+    *reinterpret_cast<uint4*>(x + (size_t)warp * D + col) = u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Text token assembly (D = 512, ctx = 77):
+//   x[c*77 + l] = (1 ≤ l ≤ P ? prefix[l-1] : token_embedding[ids[c,l]]) + pos[l]
+// Reference: models/clip_encoders.py:63-74 (rows 1..P of the embedded prompt are overwritten by the
+// learnable prefix, then the positional embedding is added to every row).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+text_assemble_kernel(const int32_t* __restrict__ ids, const __half* __restrict__ tok_emb,
+                     const float* __restrict__ pos, const float* __restrict__ prefix, int P,
+                     __half* __restrict__ x, int C, int ctx_len) {
+  constexpr int D = 512, V = 2;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= C * ctx_len) return;
+  const int l = warp % ctx_len;
+  const bool is_prefix = (l >= 1 && l <= P);
+  const int id = ids[warp];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const int col = (v * 32 + lane) * 8;
+    float a[8];
+    if (is_prefix) {
+      const float4 p0 = __ldg(reinterpret_cast<const float4*>(prefix + (size_t)(l - 1) * D + col));
+      const float4 p1 = __ldg(reinterpret_cast<const float4*>(prefix + (size_t)(l - 1) * D + col + 4));
+      a[0] = p0.x; a[1] = p0.y; a[2] = p0.z; a[3] = p0.w; a[4] = p1.x; a[5] = p1.y; a[6] = p1.z; a[7] = p1.w;
+    } else {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(tok_emb + (size_t)id * D + col));
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 e = __half22float2(h[t]);
+        a[2 * t] = e.x; a[2 * t + 1] = e.y;
+      }
+    }
+    const float4 q0 = __ldg(reinterpret_cast<const float4*>(pos + (size_t)l * D + col));
+    const float4 q1 = __ldg(reinterpret_cast<const float4*>(pos + (size_t)l * D + col + 4));
+    a[0] += q0.x; a[1] += q0.y; a[2] += q0.z; a[3] += q0.w; a[4] += q1.x; a[5] += q1.y; a[6] += q1.z; a[7] += q1.w;
+    uint4 o;
+    __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(a[2 * t], a[2 * t + 1]);
+    *reinterpret_cast<uint4*>(x + (size_t)warp * D + col) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row L2 normalisation of [rows, 512] fp32 features → fp16 (and/or fp32) unit rows.
+// Reference: `x / x.norm(dim=-1, keepdim=True)` at every logits site, e.g.
+// methods/semi_supervised_learning/textual_prompt.py:98-103 and CLIP.forward.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+l2norm512_kernel(const float* __restrict__ x, __half* __restrict__ y16, float* __restrict__ y32,
+                 int rows) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * 512);
+  float4 v[4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i] = xr[i * 32 + lane];
+    s += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+  }
+  const float inv = 1.0f / sqrtf(warp_sum(s));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 o = make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
+    if (y32) reinterpret_cast<float4*>(y32 + (size_t)warp * 512)[i * 32 + lane] = o;
+    if (y16) {
+      uint2 u;
+      __half2* h = reinterpret_cast<__half2*>(&u);
+      h[0] = __floats2half2_rn(o.x, o.y);
+      h[1] = __floats2half2_rn(o.z, o.w);
+      reinterpret_cast<uint2*>(y16 + (size_t)warp * 512)[i * 32 + lane] = u;
+    }
+  }
+}
+
+inline int warps_grid(long long rows) { return (int)((rows * 32 + 255) / 256); }
+
+}  // namespace
+
+// ---- internal launchers (used by tower.cu) ------------------------------------------------------
+int gb_launch_layernorm(gb_ctx* c, const void* x, int ldx, const int32_t* row_idx, int in_row_mul,
+                        const float* gamma, const float* beta, void* y, int ldy, int rows, int D,
+                        int out_f32, cudaStream_t st) {
+  if (rows <= 0) return GB_OK;
+  if (D != 512 && D != 768) return gb_fail(c, GB_ERR_ARG, "layernorm: D must be 512 or 768");
+  const int grid = warps_grid(rows);
+  const __half* xi = reinterpret_cast<const __half*>(x);
+  if (D == 768) {
+    if (out_f32) layernorm_kernel<768, float><<<grid, 256, 0, st>>>(xi, ldx, row_idx, in_row_mul, gamma, beta, (float*)y, ldy, rows, 1e-5f);
+    else layernorm_kernel<768, __half><<<grid, 256, 0, st>>>(xi, ldx, row_idx, in_row_mul, gamma, beta, (__half*)y, ldy, rows, 1e-5f);
+  } else {
+    if (out_f32) layernorm_kernel<512, float><<<grid, 256, 0, st>>>(xi, ldx, row_idx, in_row_mul, gamma, beta, (float*)y, ldy, rows, 1e-5f);
+    else layernorm_kernel<512, __half><<<grid, 256, 0, st>>>(xi, ldx, row_idx, in_row_mul, gamma, beta, (__half*)y, ldy, rows, 1e-5f);
+  }
+  GB_LAUNCH_CHECK(c);
+  return GB_OK;
+}
+
+int gb_launch_im2col(gb_ctx* c, const void* img, int img_f32, void* out, int B, cudaStream_t st) {
+  if (B <= 0) return GB_OK;
+  const size_t total = (size_t)B * 3 * 224 * 28;
+  const int grid = (int)((total + 255) / 256);
+  if (img_f32) im2col_patch32_kernel<float><<<grid, 256, 0, st>>>((const float*)img, (__half*)out, B);
+  else im2col_patch32_kernel<__half><<<grid, 256, 0, st>>>((const __half*)img, (__half*)out, B);
+  GB_LAUNCH_CHECK(c);
+  return GB_OK;
+}
+
+int gb_launch_vit_assemble(gb_ctx* c, const void* patch, const float* cls, const float* pos,
+                           const float* prefix, int P, const float* gamma, const float* beta,
+                           void* x, int B, cudaStream_t st) {
+  if (B <= 0) return GB_OK;
+  vit_assemble_lnpre_kernel<<<warps_grid((long long)B * (50 + P)), 256, 0, st>>>(
+      (const __half*)patch, cls, pos, prefix, P, gamma, beta, (__half*)x, B, 1e-5f);
+  GB_LAUNCH_CHECK(c);
+  return GB_OK;
+}
+
+int gb_launch_text_assemble(gb_ctx* c, const int32_t* ids, const void* tok_emb, const float* pos,
+                            const float* prefix, int P, void* x, int C, int ctx_len,
+                            cudaStream_t st) {
+  if (C <= 0) return GB_OK;
+  text_assemble_kernel<<<warps_grid((long long)C * ctx_len), 256, 0, st>>>(
+      ids, (const __half*)tok_emb, pos, prefix, P, (__half*)x, C, ctx_len);
+  GB_LAUNCH_CHECK(c);
+  return GB_OK;
+}
+
+int gb_launch_l2norm512(gb_ctx* c, const float* x, void* y16, float* y32, int rows,
+                        cudaStream_t st) {
+  if (rows <= 0) return GB_OK;
+  l2norm512_kernel<<<warps_grid(rows), 256, 0, st>>>(x, (__half*)y16, y32, rows);
+  GB_LAUNCH_CHECK(c);
+  return GB_OK;
+}
+
+// ---- C ABI ----------------------------------------------------------------------------------------
+extern "C" int gb_layernorm_f16(gb_ctx* c, const void* x, int ldx, const int32_t* row_idx,
+                                int in_row_mul, const float* gamma, const float* beta, void* y,
+                                int ldy, int rows, int D, int out_f32, void* stream) {
+  if (!c) return GB_ERR_ARG;
+  if (!x || !gamma || !beta || !y) return gb_fail(c, GB_ERR_ARG, "layernorm: null pointer");
+  return gb_launch_layernorm(c, x, ldx, row_idx, in_row_mul, gamma, beta, y, ldy, rows, D, out_f32,
+                             (cudaStream_t)stream);
+}
+
+extern "C" int gb_l2norm512(gb_ctx* c, const float* x, void* y16, float* y32, int rows,
+                            void* stream) {
+  if (!c) return GB_ERR_ARG;
+  if (!x || (!y16 && !y32)) return gb_fail(c, GB_ERR_ARG, "l2norm: null pointer");
+  return gb_launch_l2norm512(c, x, y16, y32, rows, (cudaStream_t)stream);
+}
