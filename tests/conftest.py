@@ -1,0 +1,25 @@
+import importlib
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu under gpurun)")
+
+
+@pytest.fixture(scope="session")
+def pkg():
+    """The product package (its directory name has hyphens, so it is imported by string)."""
+    return importlib.import_module("menghini-neurips23-code_b200")
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
