@@ -16,6 +16,7 @@
 #ifndef GRIPB200_H_
 #define GRIPB200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -53,6 +54,133 @@ const char* gb_version(void);
 int gb_gemm_f16(gb_ctx* ctx, const void* A, int lda, const void* W, int ldw, const float* bias,
                 const void* resid, int ldr, void* out, int ldo, int M, int N, int K, int act,
                 int out_f32, void* stream);
+
+/* y = LayerNorm(x) with fp32 statistics (clip.model.LayerNorm: ln_pre/ln_1/ln_2/ln_post/ln_final,
+ * models/clip_encoders.py:85,157,189).  x fp16 [*,ldx]; input row r = row_idx ? row_idx[r] :
+ * r*in_row_mul (gathers the CLS / EOT rows); D in {512,768}; y fp16 or fp32 [rows,ldy]. */
+int gb_layernorm_f16(gb_ctx* ctx, const void* x, int ldx, const int32_t* row_idx, int in_row_mul,
+                     const float* gamma, const float* beta, void* y, int ldy, int rows, int D,
+                     int out_f32, void* stream);
+
+/* Row L2 normalisation `x / x.norm(dim=-1, keepdim=True)` of fp32 [rows,512] features
+ * (methods/semi_supervised_learning/textual_prompt.py:98-103) → fp16 and/or fp32 unit rows. */
+int gb_l2norm512(gb_ctx* ctx, const float* x, void* y16, float* y32, int rows, void* stream);
+
+/* softmax(Q K^T / 8 [+ causal mask]) V per (sample, head) on the packed in-proj output
+ * qkv fp16 [B*L, 3D] → out fp16 [B*L, D]; head dim 64, L <= 96.  nn.MultiheadAttention core of
+ * clip.model.ResidualAttentionBlock.  _bwd: data gradient dqkv from dout (weights are frozen). */
+int gb_attention_fwd(gb_ctx* ctx, const void* qkv, void* out, int B, int L, int D, int causal,
+                     void* stream);
+int gb_attention_bwd(gb_ctx* ctx, const void* qkv, const void* dout, void* dqkv, int B, int L,
+                     int D, int causal, void* stream);
+
+/* ---- towers ------------------------------------------------------------------------------- */
+
+/* One ResidualAttentionBlock.  Weights fp16 in nn.Linear layout [out,in]; biases and LayerNorm
+ * parameters fp32.  *_t are [in,out] transposed copies used by the prompt-gradient pass
+ * (may be NULL when only forward is needed). */
+typedef struct gb_block_weights {
+  const float* ln1_g; const float* ln1_b;
+  const void* w_qkv;  const float* b_qkv;   /* [3D,D], [3D] */
+  const void* w_o;    const float* b_o;     /* [D,D],  [D]  */
+  const float* ln2_g; const float* ln2_b;
+  const void* w_fc;   const float* b_fc;    /* [4D,D], [4D] */
+  const void* w_proj; const float* b_proj;  /* [D,4D], [D]  */
+  const void* w_qkv_t; const void* w_o_t; const void* w_fc_t; const void* w_proj_t;
+} gb_block_weights;
+
+/* Frozen CLIP ViT-B/32 image tower (clip.model.VisionTransformer as re-wired by
+ * models/clip_encoders.py:105-194).  The table is copied; the device buffers stay caller-owned. */
+typedef struct gb_vit_weights {
+  int width, layers, heads, out_dim;        /* 768, 12, 12, 512 */
+  const void* conv_w;                        /* fp16 [768, 3*32*32] (conv1.weight flattened) */
+  const float* cls;                          /* [768] class_embedding */
+  const float* pos;                          /* [50,768] positional_embedding */
+  const float* ln_pre_g;  const float* ln_pre_b;
+  const float* ln_post_g; const float* ln_post_b;
+  const void* proj_t;                        /* fp16 [512,768] = proj^T */
+  const void* proj;                          /* fp16 [768,512] = proj (gradient pass) or NULL */
+  const gb_block_weights* blocks;            /* [layers] */
+} gb_vit_weights;
+
+/* Frozen CLIP text tower (token_embedding, positional_embedding, transformer, ln_final,
+ * text_projection: models/clip_encoders.py:29-37). */
+typedef struct gb_text_weights {
+  int width, layers, heads, out_dim, ctx_len, vocab; /* 512, 12, 8, 512, 77, 49408 */
+  const void* tok_emb;                       /* fp16 [vocab,512] */
+  const float* pos;                          /* [77,512] */
+  const float* ln_final_g; const float* ln_final_b;
+  const void* proj_t;                        /* fp16 [512,512] = text_projection^T */
+  const void* proj;                          /* fp16 [512,512] = text_projection or NULL */
+  const gb_block_weights* blocks;
+} gb_text_weights;
+
+int gb_vit_set_weights(gb_ctx* ctx, const gb_vit_weights* w);
+int gb_text_set_weights(gb_ctx* ctx, const gb_text_weights* w);
+
+/* Bytes of the activation tape a forward must fill for a later prompt-gradient pass over
+ * `samples` sequences of `L` tokens of width D (0 on bad arguments). */
+size_t gb_tape_bytes(int samples, int L, int D, int layers);
+
+/* CustomVisionTransformer.forward (models/clip_encoders.py:123-194) / encode_image when P == 0:
+ * conv1 patch embed, CLS + positional embedding, P prefix rows inserted after CLS (no positional
+ * embedding), ln_pre, 12 blocks, ln_post(CLS) @ proj.
+ *   img    : [B,3,224,224] NCHW, fp32 (img_f32 != 0) or fp16          prefix : fp32 [P,768] or NULL
+ *   feat   : fp32 [B,512] un-normalised (what the reference modules return) or NULL
+ *   featn  : fp16 [B,512] L2-normalised rows (input of gb_sim_softmax_argmax) or NULL
+ *   tape   : gb_tape_bytes(B, 50+P, 768, 12) bytes or NULL (inference) */
+int gb_vit_forward(gb_ctx* ctx, const void* img, int img_f32, const float* prefix, int B, int P,
+                   float* feat, void* featn, void* tape, void* stream);
+/* dprefix fp32 [P,768] = d loss / d prefix given dfeat fp32 [B,512] (autograd through
+ * CustomImageEncoder w.r.t. ImagePrefixModel.prefix, models/prompts_models.py:52-61). */
+int gb_vit_backward_prefix(gb_ctx* ctx, const float* dfeat, const float* prefix, int B, int P,
+                           const void* tape, float* dprefix, void* stream);
+
+/* CustomTextEncoder.forward after tokenisation (models/clip_encoders.py:63-89) / encode_text when
+ * P == 0: token embedding, rows 1..P overwritten by the prefix, + positional embedding, 12 causal
+ * blocks, ln_final, EOT-row gather, @ text_projection.
+ *   ids : int32 [C, ld_ids] token ids; eot : int32 [C] = ids.argmax(-1)
+ *   Lt  : positions processed, max(eot)+1 <= Lt <= 77.  Causality makes positions after EOT
+ *         irrelevant to the EOT row, so Lt < 77 is exact, not an approximation. */
+int gb_text_forward(gb_ctx* ctx, const int32_t* ids, int ld_ids, const int32_t* eot,
+                    const float* prefix, int C, int P, int Lt, float* feat, void* featn, void* tape,
+                    void* stream);
+int gb_text_backward_prefix(gb_ctx* ctx, const float* dfeat, const int32_t* eot, int C, int P,
+                            int Lt, const void* tape, float* dprefix, void* stream);
+
+/* ---- pool scan: similarity + softmax + argmax + leaderboard ------------------------------- */
+
+/* logits = scale * F T^T, probs = softmax(logits), pred = argmax: CLIP.forward + softmax + argmax of
+ * utils/clip_pseudolabels.py:59-65 for all N images in one HBM pass.
+ *   F fp16 [N,512], T fp16 [C,512], both with unit rows; C <= 128.
+ *   mode 0: pred = argmax(probs) (clip_pseudolabels.py:63); 1: argmax(logits) (textual_fpl.py:228)
+ *   pred int32 [N]; p_pred fp32 [N] = probs[i,pred[i]]; probs fp32 [N,C] or NULL. */
+int gb_sim_softmax_argmax(gb_ctx* ctx, const void* F, const void* T, float scale, int N, int C,
+                          int mode, int32_t* pred, float* p_pred, float* probs, void* stream);
+
+/* The sequential per-class leaderboard of utils/clip_pseudolabels.py:46-101 (and the 9
+ * assign_pseudo_labels copies), exactly: arrival-order fill, strict `<` against the LAST entry,
+ * sort-and-truncate on admission, spill of rejected images into every other board.
+ * `state` is caller-owned device memory of gb_leaderboard_state_bytes(C,k) bytes; it is
+ * relocatable, so a shard can hand it to the shard that owns the next index range.
+ * rank[i] orders images like their path strings (ties in sorted()); NULL = index order.
+ * _update feeds rows [row_begin,row_end) of probs/pred (local row r = global image idx0 + r). */
+size_t gb_leaderboard_state_bytes(int C, int k);
+int gb_leaderboard_init(gb_ctx* ctx, void* state, int C, int k, void* stream);
+int gb_leaderboard_update(gb_ctx* ctx, void* state, int C, int k, const float* probs,
+                          const int32_t* pred, const int32_t* rank, int row_begin, int row_end,
+                          int idx0, int prefilter, void* stream);
+/* out_idx int32 [C,k] (list order, -1 padded), out_len int32 [C], out_p fp32 [C,k] or NULL. */
+int gb_leaderboard_export(gb_ctx* ctx, const void* state, int C, int k, int32_t* out_idx,
+                          int32_t* out_len, float* out_p, void* stream);
+/* Fused scan of rows [0,N): gb_sim_softmax_argmax with the leaderboard pre-filter in its epilogue,
+ * exact replay of the surviving rows between chunks.  Replaces the loop
+ * utils/clip_pseudolabels.py:55-101.  Local row i is global image idx0 + i: boards store global
+ * indices and rank[] is indexed globally, F/pred/p_pred/probs locally — a shard continues on the
+ * state handed over by the owner of the preceding index range. */
+int gb_pseudolabel_scan(gb_ctx* ctx, void* state, const void* F, const void* T, float scale, int N,
+                        int C, int k, int mode, int idx0, const int32_t* rank, int32_t* pred,
+                        float* p_pred, float* probs, void* stream);
 
 #ifdef __cplusplus
 }

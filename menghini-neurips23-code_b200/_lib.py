@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes
 import os
 import re
-from ctypes import c_char_p, c_float, c_int, c_int64, c_uint64, c_void_p
+from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_size_t, c_uint64, c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgripb200.so")
@@ -18,6 +18,57 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "gripb200.h")
 class GripB200Error(RuntimeError):
     pass
 
+
+P = c_void_p
+
+
+class BlockWeights(Structure):
+    _fields_ = [(n, P) for n in (
+        "ln1_g", "ln1_b", "w_qkv", "b_qkv", "w_o", "b_o", "ln2_g", "ln2_b", "w_fc", "b_fc",
+        "w_proj", "b_proj", "w_qkv_t", "w_o_t", "w_fc_t", "w_proj_t")]
+
+
+class VitWeights(Structure):
+    _fields_ = [("width", c_int), ("layers", c_int), ("heads", c_int), ("out_dim", c_int),
+                ("conv_w", P), ("cls", P), ("pos", P), ("ln_pre_g", P), ("ln_pre_b", P),
+                ("ln_post_g", P), ("ln_post_b", P), ("proj_t", P), ("proj", P),
+                ("blocks", POINTER(BlockWeights))]
+
+
+class TextWeights(Structure):
+    _fields_ = [("width", c_int), ("layers", c_int), ("heads", c_int), ("out_dim", c_int),
+                ("ctx_len", c_int), ("vocab", c_int),
+                ("tok_emb", P), ("pos", P), ("ln_final_g", P), ("ln_final_b", P), ("proj_t", P),
+                ("proj", P), ("blocks", POINTER(BlockWeights))]
+
+
+_SIGNATURES = {
+    "gb_create": (c_int, [POINTER(P), c_int]),
+    "gb_destroy": (c_int, [P]),
+    "gb_last_error": (c_char_p, [P]),
+    "gb_launch_count": (c_uint64, [P]),
+    "gb_version": (c_char_p, []),
+    "gb_gemm_f16": (c_int, [P, P, c_int, P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int,
+                            c_int, c_int, P]),
+    "gb_layernorm_f16": (c_int, [P, P, c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, P]),
+    "gb_l2norm512": (c_int, [P, P, P, P, c_int, P]),
+    "gb_attention_fwd": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
+    "gb_attention_bwd": (c_int, [P, P, P, P, c_int, c_int, c_int, c_int, P]),
+    "gb_vit_set_weights": (c_int, [P, POINTER(VitWeights)]),
+    "gb_text_set_weights": (c_int, [P, POINTER(TextWeights)]),
+    "gb_tape_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "gb_vit_forward": (c_int, [P, P, c_int, P, c_int, c_int, P, P, P, P]),
+    "gb_vit_backward_prefix": (c_int, [P, P, P, c_int, c_int, P, P, P]),
+    "gb_text_forward": (c_int, [P, P, c_int, P, P, c_int, c_int, c_int, P, P, P, P]),
+    "gb_text_backward_prefix": (c_int, [P, P, P, c_int, c_int, c_int, P, P, P]),
+    "gb_sim_softmax_argmax": (c_int, [P, P, P, c_float, c_int, c_int, c_int, P, P, P, P]),
+    "gb_leaderboard_state_bytes": (c_size_t, [c_int, c_int]),
+    "gb_leaderboard_init": (c_int, [P, P, c_int, c_int, P]),
+    "gb_leaderboard_update": (c_int, [P, P, c_int, c_int, P, P, P, c_int, c_int, c_int, c_int, P]),
+    "gb_leaderboard_export": (c_int, [P, P, c_int, c_int, P, P, P, P]),
+    "gb_pseudolabel_scan": (c_int, [P, P, P, P, c_float, c_int, c_int, c_int, c_int, c_int, P, P,
+                                    P, P, P]),
+}
 
 _lib = None
 
@@ -36,20 +87,9 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise GripB200Error(
             f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-            "(there is no CPU fallback)"
-        )
+            "(there is no CPU fallback)")
     lib = ctypes.CDLL(LIB_PATH)
-    P = c_void_p
-    sig = {
-        "gb_create": (c_int, [ctypes.POINTER(P), c_int]),
-        "gb_destroy": (c_int, [P]),
-        "gb_last_error": (c_char_p, [P]),
-        "gb_launch_count": (c_uint64, [P]),
-        "gb_version": (c_char_p, []),
-        "gb_gemm_f16": (c_int, [P, P, c_int, P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int,
-                                c_int, c_int, P]),
-    }
-    for name, (res, args) in sig.items():
+    for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
@@ -80,8 +120,7 @@ class Context:
         if rc != 0:
             raise GripB200Error(
                 f"gb_create(device={device}) failed with status {rc}: libgripb200 needs an sm_100 "
-                "(B200) GPU; there is no CPU fallback"
-            )
+                "(B200) GPU; there is no CPU fallback")
         self.h = h
         self.device = int(device)
 
@@ -116,3 +155,41 @@ class Context:
             int(bool(out_f32)), stream_ptr())
         self.check(rc, "gb_gemm_f16")
         return out
+
+    def layernorm(self, x, gamma, beta, row_idx=None, in_row_mul=1, rows=None, out_f32=False):
+        import torch
+
+        D = x.shape[-1]
+        rows = (x.shape[0] if row_idx is None else row_idx.numel()) if rows is None else rows
+        y = torch.empty(rows, D, device=x.device, dtype=torch.float32 if out_f32 else torch.float16)
+        rc = self.lib.gb_layernorm_f16(self.h, ptr(x), x.stride(0), ptr(row_idx), in_row_mul,
+                                       ptr(gamma), ptr(beta), ptr(y), D, rows, D, int(out_f32),
+                                       stream_ptr())
+        self.check(rc, "gb_layernorm_f16")
+        return y
+
+    def l2norm512(self, x, want16=True, want32=False):
+        import torch
+
+        rows = x.shape[0]
+        y16 = torch.empty(rows, 512, device=x.device, dtype=torch.float16) if want16 else None
+        y32 = torch.empty(rows, 512, device=x.device, dtype=torch.float32) if want32 else None
+        self.check(self.lib.gb_l2norm512(self.h, ptr(x), ptr(y16), ptr(y32), rows, stream_ptr()),
+                   "gb_l2norm512")
+        return y16, y32
+
+    def attention_fwd(self, qkv, B, L, D, causal):
+        import torch
+
+        out = torch.empty(B * L, D, device=qkv.device, dtype=torch.float16)
+        self.check(self.lib.gb_attention_fwd(self.h, ptr(qkv), ptr(out), B, L, D, int(causal),
+                                             stream_ptr()), "gb_attention_fwd")
+        return out
+
+    def attention_bwd(self, qkv, dout, B, L, D, causal):
+        import torch
+
+        dqkv = torch.empty_like(qkv)
+        self.check(self.lib.gb_attention_bwd(self.h, ptr(qkv), ptr(dout), ptr(dqkv), B, L, D,
+                                             int(causal), stream_ptr()), "gb_attention_bwd")
+        return dqkv

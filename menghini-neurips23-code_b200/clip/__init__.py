@@ -1,0 +1,106 @@
+"""Stand-in for the third-party `clip` package on the reference's import seam (`import clip`,
+`from clip import clip`, `clip.model.Transformer`): same entry points, B200 engine underneath.
+
+    clip.load("ViT-B/32", device)  → (model, preprocess)     methods/clip_baseline.py:39-41
+    clip.tokenize(list[str])       → LongTensor [n, 77]       models/clip_encoders.py:41,60
+
+Weights: there is no network in this environment, so `load` takes them from (in this order) the
+`state_dict=` argument, the file named by $GRIPB200_CLIP_WEIGHTS (a torch-saved state_dict in
+openai/CLIP layout, e.g. `torch.jit.load('ViT-B-32.pt').state_dict()`), or — when
+$GRIPB200_SYNTHETIC_SEED is set — seeded random-init weights of the ViT-B/32 architecture.
+Tokeniser: the BPE vocabulary file is third-party data that is not redistributable here; when
+$GRIPB200_BPE_VOCAB is absent a deterministic word-hash tokenizer with the same framing
+([SOT] … [EOT], zero padded, EOT = arg-max id) is used and says so once.
+"""
+from __future__ import annotations
+
+import os
+import warnings
+
+import torch
+
+from . import model  # noqa: F401  (clip.model.Transformer)
+from .model import CLIP, Transformer, build_model  # noqa: F401
+from .._lib import GripB200Error
+from ..synthetic import synthetic_state_dict
+
+SOT, EOT = 49406, 49407
+_warned = False
+
+
+def available_models():
+    return ["ViT-B/32"]
+
+
+def _preprocess():
+    """CLIP's transform: Resize(224, bicubic) → CenterCrop → RGB → ToTensor → Normalize."""
+    import numpy as np
+    from PIL import Image
+
+    mean = torch.tensor((0.48145466, 0.4578275, 0.40821073)).view(3, 1, 1)
+    std = torch.tensor((0.26862954, 0.26130258, 0.27577711)).view(3, 1, 1)
+
+    def transform(img):
+        w, h = img.size
+        s = 224 / min(w, h)
+        img = img.resize((max(224, round(w * s)), max(224, round(h * s))), Image.BICUBIC)
+        w, h = img.size
+        l, t = (w - 224) // 2, (h - 224) // 2
+        img = img.crop((l, t, l + 224, t + 224)).convert("RGB")
+        x = torch.from_numpy(np.asarray(img, dtype=np.uint8).copy()).permute(2, 0, 1).float() / 255.0
+        return (x - mean) / std
+
+    return transform
+
+
+def load(name="ViT-B/32", device="cuda", jit=False, state_dict=None, download_root=None):
+    if name.replace("/", "").replace("-", "").lower() != "vitb32":
+        raise GripB200Error(f"only ViT-B/32 is built for B200 (got {name})")
+    if state_dict is None:
+        path = os.environ.get("GRIPB200_CLIP_WEIGHTS")
+        seed = os.environ.get("GRIPB200_SYNTHETIC_SEED")
+        if path:
+            state_dict = torch.load(path, map_location="cpu")
+        elif seed is not None:
+            state_dict = synthetic_state_dict(int(seed))
+        else:
+            raise GripB200Error(
+                "no CLIP weights: pass state_dict=, or set GRIPB200_CLIP_WEIGHTS to a saved "
+                "state_dict, or GRIPB200_SYNTHETIC_SEED for random-init weights")
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise GripB200Error("the B200 CLIP runs on CUDA devices only; there is no CPU fallback")
+    return build_model(state_dict, dev), _preprocess()
+
+
+def _word_id(word: str) -> int:
+    h = 2166136261
+    for ch in word.encode("utf-8"):
+        h = ((h ^ ch) * 16777619) & 0xFFFFFFFF
+    return 1000 + h % 39000
+
+
+def tokenize(texts, context_length: int = 77, truncate: bool = False):
+    global _warned
+    if isinstance(texts, str):
+        texts = [texts]
+    if os.environ.get("GRIPB200_BPE_VOCAB"):
+        raise GripB200Error("BPE vocabulary loading is not wired in this build")
+    if not _warned:
+        warnings.warn("clip.tokenize: BPE vocabulary unavailable offline, using the word-hash tokenizer")
+        _warned = True
+    out = torch.zeros(len(texts), context_length, dtype=torch.long)
+    for i, text in enumerate(texts):
+        toks = [SOT] + [_word_id(w) for w in text.lower().split()] + [EOT]
+        if len(toks) > context_length:
+            if not truncate:
+                raise RuntimeError(f"Input {text} is too long for context length {context_length}")
+            toks = toks[:context_length]
+            toks[-1] = EOT
+        out[i, :len(toks)] = torch.tensor(toks)
+    return out
+
+
+# `from clip import clip` (models/clip_encoders.py:7) expects a sub-module with load/tokenize
+import sys as _sys
+clip = _sys.modules[__name__]

@@ -1,0 +1,460 @@
+// Multi-head self-attention core for the short CLIP sequences (vision L = 50+P ≤ 96, text L ≤ 77,
+// head dim 64):   O = softmax(Q·Kᵀ / 8 [+ causal mask]) · V    per (sample, head).
+//
+// Reference: nn.MultiheadAttention inside clip.model.ResidualAttentionBlock (need_weights=False,
+// text tower: additive −inf upper-triangular mask) reached from models/clip_encoders.py:75-84,186.
+// ≈1 % of the tower FLOPs: one CTA per (sample, head) keeps Q, K and Vᵀ of the
+// whole sequence in shared memory and runs both contractions on mma.sync m16n8k16 register
+// fragments (a 128-row tcgen05 tile would be >50 % padding at these lengths); the probabilities
+// never leave registers.  Input is the packed in-proj output qkv[B·L, 3·D]; output a[B·L, D].
+#include "ctx.h"
+#include "common.cuh"
+
+using namespace gb;
+
+namespace {
+
+constexpr int kDh = 64;
+constexpr int kQKld = kDh + 8;  // padded row (halves) → conflict-free 32-bit fragment loads
+
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float x, float y) {
+  const __half2 h = __floats2half2_rn(x, y);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t lds32(const __half* p) {
+  return *reinterpret_cast<const uint32_t*>(p);
+}
+
+// Stage Q, K (row-major, padded) and Vᵀ of one (sample, head) in shared memory; rows ≥ L are zero.
+template <int NT>
+__device__ __forceinline__ void stage_qkv(const __half* __restrict__ qkv, int L, int D, int b,
+                                          int h, __half* Qs, __half* Ks, __half* Vt) {
+  constexpr int Lp = NT * 8;
+  constexpr int ldv = Lp + 8;
+  const size_t ld = (size_t)3 * D;
+  for (int i = threadIdx.x; i < Lp * 8; i += blockDim.x) {
+    const int r = i >> 3, ch = i & 7;
+    uint4 q = make_uint4(0, 0, 0, 0), k = q, v = q;
+    if (r < L) {
+      const __half* src = qkv + ((size_t)b * L + r) * ld + h * kDh + ch * 8;
+      q = *reinterpret_cast<const uint4*>(src);
+      k = *reinterpret_cast<const uint4*>(src + D);
+      v = *reinterpret_cast<const uint4*>(src + 2 * D);
+    }
+    *reinterpret_cast<uint4*>(Qs + r * kQKld + ch * 8) = q;
+    *reinterpret_cast<uint4*>(Ks + r * kQKld + ch * 8) = k;
+    const __half* vh = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) Vt[(ch * 8 + e) * ldv + r] = vh[e];
+  }
+}
+
+// S = scale·Q·Kᵀ with masking, then row soft-max, all in the m16n8 accumulator layout:
+// thread (g = lane/4, t = lane%4) owns rows r0+g (s[..][0,1]) and r0+g+8 (s[..][2,3]),
+// columns nt*8 + 2t, +1.  Returns the row sums' inverses; s holds exp(x − max).
+template <int NT>
+__device__ __forceinline__ void scores_softmax(const __half* Qs, const __half* Ks, int r0, int L,
+                                               bool causal, int lane, float (&s)[NT][4],
+                                               float& inv0, float& inv1) {
+  const int g = lane >> 2, t = lane & 3;
+  uint32_t a[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    a[ks][0] = lds32(Qs + (r0 + g) * kQKld + ks * 16 + 2 * t);
+    a[ks][1] = lds32(Qs + (r0 + g + 8) * kQKld + ks * 16 + 2 * t);
+    a[ks][2] = lds32(Qs + (r0 + g) * kQKld + ks * 16 + 8 + 2 * t);
+    a[ks][3] = lds32(Qs + (r0 + g + 8) * kQKld + ks * 16 + 8 + 2 * t);
+  }
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint32_t b0 = lds32(Ks + (nt * 8 + g) * kQKld + ks * 16 + 2 * t);
+      const uint32_t b1 = lds32(Ks + (nt * 8 + g) * kQKld + ks * 16 + 8 + 2 * t);
+      mma16816(s[nt], a[ks], b0, b1);
+    }
+    const int c0 = nt * 8 + 2 * t;
+    const int ra = r0 + g, rb = r0 + g + 8;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int col = c0 + e;
+      const bool oka = col < L && !(causal && col > ra);
+      const bool okb = col < L && !(causal && col > rb);
+      s[nt][e] = oka ? s[nt][e] * 0.125f : -INFINITY;
+      s[nt][2 + e] = okb ? s[nt][2 + e] * 0.125f : -INFINITY;
+      m0 = fmaxf(m0, s[nt][e]);
+      m1 = fmaxf(m1, s[nt][2 + e]);
+    }
+  }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      s[nt][e] = __expf(s[nt][e] - m0);       // col 0 is never masked → m finite
+      s[nt][2 + e] = __expf(s[nt][2 + e] - m1);
+      l0 += s[nt][e];
+      l1 += s[nt][2 + e];
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  inv0 = 1.0f / l0;
+  inv1 = 1.0f / l1;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(128)
+attn_fwd_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int L, int D,
+                int causal) {
+  constexpr int Lp = NT * 8;  // multiple of 16
+  constexpr int ldv = Lp + 8;
+  extern __shared__ __align__(16) uint8_t attn_smem[];
+  __half* Qs = reinterpret_cast<__half*>(attn_smem);
+  __half* Ks = Qs + Lp * kQKld;
+  __half* Vt = Ks + Lp * kQKld;
+  const int h = blockIdx.x, b = blockIdx.y;
+  stage_qkv<NT>(qkv, L, D, b, h, Qs, Ks, Vt);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  for (int mt = warp; mt * 16 < L; mt += 4) {
+    const int r0 = mt * 16;
+    float s[NT][4];
+    float inv0, inv1;
+    scores_softmax<NT>(Qs, Ks, r0, L, causal != 0, lane, s, inv0, inv1);
+    float o[8][4];
+#pragma unroll
+    for (int dn = 0; dn < 8; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < NT / 2; ++kt) {
+      uint32_t a[4];
+      a[0] = pack_h2(s[2 * kt][0] * inv0, s[2 * kt][1] * inv0);
+      a[1] = pack_h2(s[2 * kt][2] * inv1, s[2 * kt][3] * inv1);
+      a[2] = pack_h2(s[2 * kt + 1][0] * inv0, s[2 * kt + 1][1] * inv0);
+      a[3] = pack_h2(s[2 * kt + 1][2] * inv1, s[2 * kt + 1][3] * inv1);
+#pragma unroll
+      for (int dn = 0; dn < 8; ++dn) {
+        const uint32_t b0 = lds32(Vt + (dn * 8 + g) * ldv + kt * 16 + 2 * t);
+        const uint32_t b1 = lds32(Vt + (dn * 8 + g) * ldv + kt * 16 + 8 + 2 * t);
+        mma16816(o[dn], a, b0, b1);
+      }
+    }
+    const int ra = r0 + g, rb = r0 + g + 8;
+#pragma unroll
+    for (int dn = 0; dn < 8; ++dn) {
+      const int col = h * kDh + dn * 8 + 2 * t;
+      if (ra < L)
+        *reinterpret_cast<__half2*>(out + ((size_t)b * L + ra) * D + col) =
+            __floats2half2_rn(o[dn][0], o[dn][1]);
+      if (rb < L)
+        *reinterpret_cast<__half2*>(out + ((size_t)b * L + rb) * D + col) =
+            __floats2half2_rn(o[dn][2], o[dn][3]);
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Backward w.r.t. the packed qkv (frozen weights: only data gradients exist).
+//   P = softmax(S),  dV = Pᵀ·dO,  dP = dO·Vᵀ,  dS = P ∘ (dP − rowsum(dP∘P)),  dQ = dS·K/8,  dK = dSᵀ·Q/8
+// Same one-CTA-per-(sample, head) layout; P is recomputed from the saved qkv.  dS is staged through
+// shared memory so the transposed products can re-use the m16n8k16 fragments.
+// -------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(128)
+attn_bwd_kernel(const __half* __restrict__ qkv, const __half* __restrict__ dout,
+                __half* __restrict__ dqkv, int L, int D, int causal) {
+  constexpr int Lp = NT * 8;
+  constexpr int ldv = Lp + 8;   // row stride of the [64, Lp] transposed tiles
+  constexpr int ldp = Lp + 8;   // row stride of the [Lp, Lp] P / dS tiles
+  extern __shared__ __align__(16) uint8_t attn_smem[];
+  __half* Qs = reinterpret_cast<__half*>(attn_smem);   // [Lp, 72]
+  __half* Ks = Qs + Lp * kQKld;                        // [Lp, 72]
+  __half* Vs = Ks + Lp * kQKld;                        // [Lp, 72]   V row-major (B operand of dO·Vᵀ)
+  __half* dOs = Vs + Lp * kQKld;                       // [Lp, 72]
+  __half* Qt = dOs + Lp * kQKld;                       // [64, ldv]  Qᵀ  (B operand of dSᵀ·Q)
+  __half* Kt = Qt + kDh * ldv;                         // [64, ldv]  Kᵀ  (B operand of dS·K)
+  __half* dOt = Kt + kDh * ldv;                        // [64, ldv]  dOᵀ (B operand of Pᵀ·dO)
+  __half* Ps = dOt + kDh * ldv;                        // [Lp, ldp]  P   (row-major: A of … transposed use)
+  __half* dSs = Ps + Lp * ldp;                         // [Lp, ldp]  dS
+  const int h = blockIdx.x, b = blockIdx.y;
+  const size_t ld = (size_t)3 * D;
+  for (int i = threadIdx.x; i < Lp * 8; i += blockDim.x) {
+    const int r = i >> 3, ch = i & 7;
+    uint4 q = make_uint4(0, 0, 0, 0), k = q, v = q, d = q;
+    if (r < L) {
+      const __half* src = qkv + ((size_t)b * L + r) * ld + h * kDh + ch * 8;
+      q = *reinterpret_cast<const uint4*>(src);
+      k = *reinterpret_cast<const uint4*>(src + D);
+      v = *reinterpret_cast<const uint4*>(src + 2 * D);
+      d = *reinterpret_cast<const uint4*>(dout + ((size_t)b * L + r) * D + h * kDh + ch * 8);
+    }
+    *reinterpret_cast<uint4*>(Qs + r * kQKld + ch * 8) = q;
+    *reinterpret_cast<uint4*>(Ks + r * kQKld + ch * 8) = k;
+    *reinterpret_cast<uint4*>(Vs + r * kQKld + ch * 8) = v;
+    *reinterpret_cast<uint4*>(dOs + r * kQKld + ch * 8) = d;
+    const __half* qh = reinterpret_cast<const __half*>(&q);
+    const __half* kh = reinterpret_cast<const __half*>(&k);
+    const __half* dh = reinterpret_cast<const __half*>(&d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      Qt[(ch * 8 + e) * ldv + r] = qh[e];
+      Kt[(ch * 8 + e) * ldv + r] = kh[e];
+      dOt[(ch * 8 + e) * ldv + r] = dh[e];
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  // ---- phase 1: per query-row tile: P, dP, dS (→ smem), dQ (→ global) ---------------------------
+  for (int mt = warp; mt * 16 < Lp; mt += 4) {
+    const int r0 = mt * 16;
+    float s[NT][4];
+    float inv0, inv1;
+    scores_softmax<NT>(Qs, Ks, r0, L, causal != 0, lane, s, inv0, inv1);
+    // dP = dO · Vᵀ   (A = dO rows, B[k=dh][n=key] = V[key][dh] → V row-major)
+    uint32_t a[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      a[ks][0] = lds32(dOs + (r0 + g) * kQKld + ks * 16 + 2 * t);
+      a[ks][1] = lds32(dOs + (r0 + g + 8) * kQKld + ks * 16 + 2 * t);
+      a[ks][2] = lds32(dOs + (r0 + g) * kQKld + ks * 16 + 8 + 2 * t);
+      a[ks][3] = lds32(dOs + (r0 + g + 8) * kQKld + ks * 16 + 8 + 2 * t);
+    }
+    float dsum0 = 0.f, dsum1 = 0.f;
+    float dp[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t b0 = lds32(Vs + (nt * 8 + g) * kQKld + ks * 16 + 2 * t);
+        const uint32_t b1 = lds32(Vs + (nt * 8 + g) * kQKld + ks * 16 + 8 + 2 * t);
+        mma16816(dp[nt], a[ks], b0, b1);
+      }
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        s[nt][e] *= inv0;          // P
+        s[nt][2 + e] *= inv1;
+        dsum0 += dp[nt][e] * s[nt][e];
+        dsum1 += dp[nt][2 + e] * s[nt][2 + e];
+      }
+    }
+    dsum0 += __shfl_xor_sync(0xffffffffu, dsum0, 1);
+    dsum0 += __shfl_xor_sync(0xffffffffu, dsum0, 2);
+    dsum1 += __shfl_xor_sync(0xffffffffu, dsum1, 1);
+    dsum1 += __shfl_xor_sync(0xffffffffu, dsum1, 2);
+    const bool va = r0 + g < L, vb = r0 + g + 8 < L;  // padded query rows contribute nothing
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int c0 = nt * 8 + 2 * t;
+      const float p0 = va ? s[nt][0] : 0.f, p1 = va ? s[nt][1] : 0.f;
+      const float p2 = vb ? s[nt][2] : 0.f, p3 = vb ? s[nt][3] : 0.f;
+      const float d0 = p0 * (dp[nt][0] - dsum0), d1 = p1 * (dp[nt][1] - dsum0);
+      const float d2 = p2 * (dp[nt][2] - dsum1), d3 = p3 * (dp[nt][3] - dsum1);
+      *reinterpret_cast<uint32_t*>(Ps + (r0 + g) * ldp + c0) = pack_h2(p0, p1);
+      *reinterpret_cast<uint32_t*>(Ps + (r0 + g + 8) * ldp + c0) = pack_h2(p2, p3);
+      *reinterpret_cast<uint32_t*>(dSs + (r0 + g) * ldp + c0) = pack_h2(d0, d1);
+      *reinterpret_cast<uint32_t*>(dSs + (r0 + g + 8) * ldp + c0) = pack_h2(d2, d3);
+      s[nt][0] = d0; s[nt][1] = d1; s[nt][2] = d2; s[nt][3] = d3;
+    }
+    // dQ = dS · K / 8   (A = dS from registers, B[k=key][n=dh] = K[key][dh] → Kᵀ tile)
+    float o[8][4];
+#pragma unroll
+    for (int dn = 0; dn < 8; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < NT / 2; ++kt) {
+      uint32_t af[4];
+      af[0] = pack_h2(s[2 * kt][0], s[2 * kt][1]);
+      af[1] = pack_h2(s[2 * kt][2], s[2 * kt][3]);
+      af[2] = pack_h2(s[2 * kt + 1][0], s[2 * kt + 1][1]);
+      af[3] = pack_h2(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+#pragma unroll
+      for (int dn = 0; dn < 8; ++dn) {
+        const uint32_t b0 = lds32(Kt + (dn * 8 + g) * ldv + kt * 16 + 2 * t);
+        const uint32_t b1 = lds32(Kt + (dn * 8 + g) * ldv + kt * 16 + 8 + 2 * t);
+        mma16816(o[dn], af, b0, b1);
+      }
+    }
+#pragma unroll
+    for (int dn = 0; dn < 8; ++dn) {
+      const int col = h * kDh + dn * 8 + 2 * t;
+      if (va)
+        *reinterpret_cast<__half2*>(dqkv + ((size_t)b * L + r0 + g) * ld + col) =
+            __floats2half2_rn(o[dn][0] * 0.125f, o[dn][1] * 0.125f);
+      if (vb)
+        *reinterpret_cast<__half2*>(dqkv + ((size_t)b * L + r0 + g + 8) * ld + col) =
+            __floats2half2_rn(o[dn][2] * 0.125f, o[dn][3] * 0.125f);
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: per key-row tile: dK = dSᵀ·Q/8, dV = Pᵀ·dO -------------------------------------
+  // A[m=key][k=query] = dS[query][key] → transposed read of the row-major smem tile (16-bit loads).
+  for (int mt = warp; mt * 16 < L; mt += 4) {
+    const int r0 = mt * 16;  // key rows
+    float ok[8][4], ov[8][4];
+#pragma unroll
+    for (int dn = 0; dn < 8; ++dn) {
+      ok[dn][0] = ok[dn][1] = ok[dn][2] = ok[dn][3] = 0.f;
+      ov[dn][0] = ov[dn][1] = ov[dn][2] = ov[dn][3] = 0.f;
+    }
+#pragma unroll
+    for (int kt = 0; kt < NT / 2; ++kt) {
+      const int q0 = kt * 16;  // query block
+      uint32_t as[4], ap[4];
+      {
+        auto ldT = [&](const __half* M, int key, int qq) -> uint32_t {
+          const __half x = M[(qq)*ldp + key];
+          const __half y = M[(qq + 1) * ldp + key];
+          const __half2 v2 = __halves2half2(x, y);
+          return *reinterpret_cast<const uint32_t*>(&v2);
+        };
+        as[0] = ldT(dSs, r0 + g, q0 + 2 * t);
+        as[1] = ldT(dSs, r0 + g + 8, q0 + 2 * t);
+        as[2] = ldT(dSs, r0 + g, q0 + 8 + 2 * t);
+        as[3] = ldT(dSs, r0 + g + 8, q0 + 8 + 2 * t);
+        ap[0] = ldT(Ps, r0 + g, q0 + 2 * t);
+        ap[1] = ldT(Ps, r0 + g + 8, q0 + 2 * t);
+        ap[2] = ldT(Ps, r0 + g, q0 + 8 + 2 * t);
+        ap[3] = ldT(Ps, r0 + g + 8, q0 + 8 + 2 * t);
+      }
+#pragma unroll
+      for (int dn = 0; dn < 8; ++dn) {
+        // B[k=query][n=dh] = Q[query][dh] / dO[query][dh] → transposed tiles Qt / dOt
+        const uint32_t bq0 = lds32(Qt + (dn * 8 + g) * ldv + q0 + 2 * t);
+        const uint32_t bq1 = lds32(Qt + (dn * 8 + g) * ldv + q0 + 8 + 2 * t);
+        mma16816(ok[dn], as, bq0, bq1);
+        const uint32_t bd0 = lds32(dOt + (dn * 8 + g) * ldv + q0 + 2 * t);
+        const uint32_t bd1 = lds32(dOt + (dn * 8 + g) * ldv + q0 + 8 + 2 * t);
+        mma16816(ov[dn], ap, bd0, bd1);
+      }
+    }
+    const int ra = r0 + g, rb = r0 + g + 8;
+#pragma unroll
+    for (int dn = 0; dn < 8; ++dn) {
+      const int col = h * kDh + dn * 8 + 2 * t;
+      if (ra < L) {
+        *reinterpret_cast<__half2*>(dqkv + ((size_t)b * L + ra) * ld + D + col) =
+            __floats2half2_rn(ok[dn][0] * 0.125f, ok[dn][1] * 0.125f);
+        *reinterpret_cast<__half2*>(dqkv + ((size_t)b * L + ra) * ld + 2 * D + col) =
+            __floats2half2_rn(ov[dn][0], ov[dn][1]);
+      }
+      if (rb < L) {
+        *reinterpret_cast<__half2*>(dqkv + ((size_t)b * L + rb) * ld + D + col) =
+            __floats2half2_rn(ok[dn][2] * 0.125f, ok[dn][3] * 0.125f);
+        *reinterpret_cast<__half2*>(dqkv + ((size_t)b * L + rb) * ld + 2 * D + col) =
+            __floats2half2_rn(ov[dn][2], ov[dn][3]);
+      }
+    }
+  }
+}
+
+template <int NT>
+size_t fwd_smem() {
+  constexpr int Lp = NT * 8;
+  return (size_t)(2 * Lp * kQKld + kDh * (Lp + 8)) * 2;
+}
+template <int NT>
+size_t bwd_smem() {
+  constexpr int Lp = NT * 8;
+  return (size_t)(4 * Lp * kQKld + 3 * kDh * (Lp + 8) + 2 * Lp * (Lp + 8)) * 2;
+}
+
+template <int NT>
+int launch_fwd(gb_ctx* c, const void* qkv, void* out, int B, int L, int D, int causal,
+               cudaStream_t st) {
+  const size_t smem = fwd_smem<NT>();
+  if (smem > 48 * 1024) {
+    static bool done[16] = {false};
+    if (!done[c->device & 15]) {
+      GB_CUDA(c, cudaFuncSetAttribute(attn_fwd_kernel<NT>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      done[c->device & 15] = true;
+    }
+  }
+  attn_fwd_kernel<NT><<<dim3(D / kDh, B), 128, smem, st>>>((const __half*)qkv, (__half*)out, L, D,
+                                                          causal);
+  GB_LAUNCH_CHECK(c);
+  return GB_OK;
+}
+template <int NT>
+int launch_bwd(gb_ctx* c, const void* qkv, const void* dout, void* dqkv, int B, int L, int D,
+               int causal, cudaStream_t st) {
+  const size_t smem = bwd_smem<NT>();
+  if (smem > 48 * 1024) {
+    static bool done[16] = {false};
+    if (!done[c->device & 15]) {
+      GB_CUDA(c, cudaFuncSetAttribute(attn_bwd_kernel<NT>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      done[c->device & 15] = true;
+    }
+  }
+  attn_bwd_kernel<NT><<<dim3(D / kDh, B), 128, smem, st>>>((const __half*)qkv, (const __half*)dout,
+                                                          (__half*)dqkv, L, D, causal);
+  GB_LAUNCH_CHECK(c);
+  return GB_OK;
+}
+
+}  // namespace
+
+int gb_launch_attn_fwd(gb_ctx* c, const void* qkv, void* out, int B, int L, int D, int causal,
+                       cudaStream_t st) {
+  if (B <= 0) return GB_OK;
+  if (L < 1 || L > 96 || D % kDh != 0)
+    return gb_fail(c, GB_ERR_ARG, "attention: L=%d (1..96) D=%d (multiple of 64) unsupported", L, D);
+  const int lp = (L + 15) / 16;
+  switch (lp) {
+    case 1: return launch_fwd<2>(c, qkv, out, B, L, D, causal, st);
+    case 2: return launch_fwd<4>(c, qkv, out, B, L, D, causal, st);
+    case 3: return launch_fwd<6>(c, qkv, out, B, L, D, causal, st);
+    case 4: return launch_fwd<8>(c, qkv, out, B, L, D, causal, st);
+    case 5: return launch_fwd<10>(c, qkv, out, B, L, D, causal, st);
+    default: return launch_fwd<12>(c, qkv, out, B, L, D, causal, st);
+  }
+}
+
+int gb_launch_attn_bwd(gb_ctx* c, const void* qkv, const void* dout, void* dqkv, int B, int L,
+                       int D, int causal, cudaStream_t st) {
+  if (B <= 0) return GB_OK;
+  if (L < 1 || L > 96 || D % kDh != 0)
+    return gb_fail(c, GB_ERR_ARG, "attention: L=%d (1..96) D=%d (multiple of 64) unsupported", L, D);
+  const int lp = (L + 15) / 16;
+  switch (lp) {
+    case 1: return launch_bwd<2>(c, qkv, dout, dqkv, B, L, D, causal, st);
+    case 2: return launch_bwd<4>(c, qkv, dout, dqkv, B, L, D, causal, st);
+    case 3: return launch_bwd<6>(c, qkv, dout, dqkv, B, L, D, causal, st);
+    case 4: return launch_bwd<8>(c, qkv, dout, dqkv, B, L, D, causal, st);
+    case 5: return launch_bwd<10>(c, qkv, dout, dqkv, B, L, D, causal, st);
+    default: return launch_bwd<12>(c, qkv, dout, dqkv, B, L, D, causal, st);
+  }
+}
+
+extern "C" int gb_attention_fwd(gb_ctx* c, const void* qkv, void* out, int B, int L, int D,
+                                int causal, void* stream) {
+  if (!c) return GB_ERR_ARG;
+  if (!qkv || !out) return gb_fail(c, GB_ERR_ARG, "attention: null pointer");
+  return gb_launch_attn_fwd(c, qkv, out, B, L, D, causal, (cudaStream_t)stream);
+}
+
+extern "C" int gb_attention_bwd(gb_ctx* c, const void* qkv, const void* dout, void* dqkv, int B,
+                                int L, int D, int causal, void* stream) {
+  if (!c) return GB_ERR_ARG;
+  if (!qkv || !dout || !dqkv) return gb_fail(c, GB_ERR_ARG, "attention: null pointer");
+  return gb_launch_attn_bwd(c, qkv, dout, dqkv, B, L, D, causal, (cudaStream_t)stream);
+}

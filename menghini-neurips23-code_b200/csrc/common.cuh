@@ -194,4 +194,10 @@ __device__ __forceinline__ float quick_gelu(float x) {
   return x / (1.0f + __expf(-1.702f * x));
 }
 
+__device__ __forceinline__ float quick_gelu_grad(float x) {
+  // d/dx [x·σ(1.702x)] = σ + 1.702·x·σ·(1−σ)
+  const float s = 1.0f / (1.0f + __expf(-1.702f * x));
+  return s + 1.702f * x * s * (1.0f - s);
+}
+
 }  // namespace gb

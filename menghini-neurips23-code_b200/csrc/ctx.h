@@ -65,5 +65,5 @@ int gb_make_tmap_2d_f16(gb_ctx* c, CUtensorMap* out, const void* ptr, uint64_t r
 // internal launchers shared between op-level and tower-level entry points
 int gb_launch_gemm(gb_ctx* c, const void* A, int lda, const void* W, int ldw, const float* bias,
                    const void* resid, int ldr, void* out, int ldo, int M, int N, int K, int act,
-                   int out_f32, cudaStream_t st);
+                   int out_f32, cudaStream_t st, void* aux = nullptr);
 int gb_ws_reserve(gb_ctx* c, size_t bytes);

@@ -24,7 +24,7 @@ static int launch_gemm_bn(gb_ctx* c, const CUtensorMap& tmA, const CUtensorMap& 
 
 int gb_launch_gemm(gb_ctx* c, const void* A, int lda, const void* W, int ldw, const float* bias,
                    const void* resid, int ldr, void* out, int ldo, int M, int N, int K, int act,
-                   int out_f32, cudaStream_t st) {
+                   int out_f32, cudaStream_t st, void* aux) {
   if (!A || !W || !out) return gb_fail(c, GB_ERR_ARG, "gemm: null pointer");
   if (M <= 0) return GB_OK;
   if (K % kBK != 0 || N % 128 != 0 || lda % 8 != 0 || ldw % 8 != 0 || ldo % 8 != 0 ||
@@ -50,6 +50,9 @@ int gb_launch_gemm(gb_ctx* c, const void* A, int lda, const void* W, int ldw, co
   p.bias = bias;
   p.resid = reinterpret_cast<const __half*>(resid); p.ldr = ldr;
   p.act = act; p.out_f32 = out_f32;
+  p.aux = reinterpret_cast<__half*>(aux);
+  if (act == 2 && !aux) return gb_fail(c, GB_ERR_ARG, "gemm: act 2 needs aux");
+  if (aux && (out_f32 || (reinterpret_cast<uintptr_t>(aux) & 15))) return gb_fail(c, GB_ERR_ARG, "gemm: aux needs fp16 output layout and 16-byte alignment");
   return wide ? launch_gemm_bn<256>(c, tmA, tmB, p, st) : launch_gemm_bn<128>(c, tmA, tmB, p, st);
 }
 
@@ -57,6 +60,7 @@ extern "C" int gb_gemm_f16(gb_ctx* c, const void* A, int lda, const void* W, int
                            const float* bias, const void* resid, int ldr, void* out, int ldo, int M,
                            int N, int K, int act, int out_f32, void* stream) {
   if (!c) return GB_ERR_ARG;
+  if (act < 0 || act > 1) return gb_fail(c, GB_ERR_ARG, "gemm: act must be 0 or 1");
   return gb_launch_gemm(c, A, lda, W, ldw, bias, resid, ldr, out, ldo, M, N, K, act, out_f32,
-                        reinterpret_cast<cudaStream_t>(stream));
+                        reinterpret_cast<cudaStream_t>(stream), nullptr);
 }

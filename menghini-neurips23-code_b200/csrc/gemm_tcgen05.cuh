@@ -29,8 +29,10 @@ struct GemmParams {
   const float* bias;    // [N] or nullptr
   const __half* resid;  // [M,ldr] or nullptr; may alias out
   int ldr;
-  int act;      // 0 none, 1 QuickGELU
+  int act;      // 0 none, 1 QuickGELU, 2 multiply by QuickGELU'(aux) (backward of act 1)
   int out_f32;  // 1 → fp32 store
+  __half* aux;  // [M,ldo] fp16 or nullptr.  act 1: receives the pre-activation (tape for backward);
+                // act 2: the saved pre-activation that is read.
 };
 
 template <int BN>
@@ -173,8 +175,33 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           }
         }
         if (p.act == 1) {
+          if (p.aux != nullptr && row_ok) {
+            uint4* a4 = reinterpret_cast<uint4*>(p.aux + (size_t)row * p.ldo + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+              for (int t = 0; t < 4; ++t)
+                h[t] = __floats2half2_rn(f[8 * j + 2 * t], f[8 * j + 2 * t + 1]);
+              a4[j] = o;
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
+        } else if (p.act == 2 && row_ok) {
+          const uint4* a4 = reinterpret_cast<const uint4*>(p.aux + (size_t)row * p.ldo + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 r = a4[j];
+            const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 x = __half22float2(h[t]);
+              f[8 * j + 2 * t] *= quick_gelu_grad(x.x);
+              f[8 * j + 2 * t + 1] *= quick_gelu_grad(x.y);
+            }
+          }
         }
         if (row_ok) {
           if (p.resid != nullptr) {

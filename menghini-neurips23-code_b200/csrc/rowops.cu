@@ -199,7 +199,7 @@ vit_assemble_lnpre_kernel(const __half* __restrict__ patch, const float* __restr
 // learnable prefix, then the positional embedding is added to every row).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-text_assemble_kernel(const int32_t* __restrict__ ids, const __half* __restrict__ tok_emb,
+text_assemble_kernel(const int32_t* __restrict__ ids, int ld_ids, const __half* __restrict__ tok_emb,
                      const float* __restrict__ pos, const float* __restrict__ prefix, int P,
                      __half* __restrict__ x, int C, int ctx_len) {
   constexpr int D = 512, V = 2;
@@ -208,7 +208,7 @@ text_assemble_kernel(const int32_t* __restrict__ ids, const __half* __restrict__
   if (warp >= C * ctx_len) return;
   const int l = warp % ctx_len;
   const bool is_prefix = (l >= 1 && l <= P);
-  const int id = ids[warp];
+  const int id = ids[(size_t)(warp / ctx_len) * ld_ids + l];
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     const int col = (v * 32 + lane) * 8;
@@ -271,6 +271,166 @@ l2norm512_kernel(const float* __restrict__ x, __half* __restrict__ y16, float* _
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// LayerNorm backward w.r.t. the input only (γ, β are frozen):
+//   x̂ = (x−μ)·rstd,  g = dy∘γ,  dx = rstd·(g − mean(g) − x̂·mean(g∘x̂))
+// dy row r pairs with x row xr = row_idx ? row_idx[r] : r*in_row_mul; the result is written (or, with
+// accumulate, added: the residual branch) to dx row xr.  fp16 streams, fp32 math.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const __half* __restrict__ dy, int lddy, const __half* __restrict__ x, int ldx,
+                     const int32_t* __restrict__ row_idx, int in_row_mul,
+                     const float* __restrict__ gamma, __half* __restrict__ dx, int lddx, int rows,
+                     int accumulate, float eps) {
+  constexpr int V = D / 256;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const size_t xr = row_idx ? (size_t)row_idx[warp] : (size_t)warp * in_row_mul;
+  const uint4* xp = reinterpret_cast<const uint4*>(x + xr * ldx);
+  const uint4* dp = reinterpret_cast<const uint4*>(dy + (size_t)warp * lddy);
+  float f[V * 8], g[V * 8];
+  float s = 0.f;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const uint4 u = xp[v * 32 + lane];
+    const uint4 w = dp[v * 32 + lane];
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+    const __half2* hd = reinterpret_cast<const __half2*>(&w);
+    const int col = (v * 32 + lane) * 8;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 a = __half22float2(h[t]);
+      const float2 d = __half22float2(hd[t]);
+      f[v * 8 + 2 * t] = a.x;
+      f[v * 8 + 2 * t + 1] = a.y;
+      g[v * 8 + 2 * t] = d.x * gm[2 * t];
+      g[v * 8 + 2 * t + 1] = d.y * gm[2 * t + 1];
+      s += a.x + a.y;
+    }
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V * 8; ++i) { const float d = f[i] - mean; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+  float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < V * 8; ++i) {
+    f[i] = (f[i] - mean) * rstd;  // x̂
+    m1 += g[i];
+    m2 += g[i] * f[i];
+  }
+  m1 = warp_sum(m1) * (1.0f / D);
+  m2 = warp_sum(m2) * (1.0f / D);
+  uint4* op = reinterpret_cast<uint4*>(dx + xr * lddx);
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = rstd * (g[v * 8 + i] - m1 - f[v * 8 + i] * m2);
+    if (accumulate) {
+      const uint4 u = op[v * 32 + lane];
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 a = __half22float2(h[t]);
+        o[2 * t] += a.x;
+        o[2 * t + 1] += a.y;
+      }
+    }
+    uint4 u;
+    __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(o[2 * t], o[2 * t + 1]);
+    op[v * 32 + lane] = u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gradient of the learnable prompt rows: dprefix[p,:] = inv_scale · Σ_s d(row 1+p of sample s).
+// Vision (ln_pre != 0): the rows went through ln_pre with input prefix[p] (models/clip_encoders.py:
+// 148-157), so each sample's row gradient is first pulled back through that LayerNorm.
+// Text: the prefix rows are the raw embeddings (+pos), gradient = plain sum over the C prompts
+// (models/clip_encoders.py:67).  One CTA per prompt row, warps stride over samples.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(256)
+prefix_grad_kernel(const __half* __restrict__ dx, int L, int S, const float* __restrict__ prefix,
+                   const float* __restrict__ gamma, int ln_pre, float inv_scale,
+                   float* __restrict__ dprefix, float eps) {
+  constexpr int V = D / 32;  // elements per lane, strided by 32
+  __shared__ float red[8][D];
+  const int p = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float xh[V], gm[V], acc[V];
+  float rstd = 1.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) { acc[i] = 0.f; xh[i] = 0.f; gm[i] = 1.f; }
+  if (ln_pre) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) { xh[i] = prefix[(size_t)p * D + i * 32 + lane]; s += xh[i]; }
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) { xh[i] -= mean; q += xh[i] * xh[i]; }
+    rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+#pragma unroll
+    for (int i = 0; i < V; ++i) { xh[i] *= rstd; gm[i] = gamma[i * 32 + lane]; }
+  }
+  for (int s = warp; s < S; s += 8) {
+    const __half* r = dx + ((size_t)s * L + 1 + p) * D;
+    float g[V];
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      g[i] = __half2float(r[i * 32 + lane]) * gm[i];
+      m1 += g[i];
+      m2 += g[i] * xh[i];
+    }
+    if (ln_pre) {
+      m1 = warp_sum(m1) * (1.0f / D);
+      m2 = warp_sum(m2) * (1.0f / D);
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] += rstd * (g[i] - m1 - xh[i] * m2);
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) acc[i] += g[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) red[warp][i * 32 + lane] = acc[i];
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][c];
+    dprefix[(size_t)p * D + c] = t * inv_scale;
+  }
+}
+
+// out16[r, :] = fp16(scale · in32[r, :])   (loss-scaled entry of the fp16 gradient stream)
+__global__ void __launch_bounds__(256)
+scale_f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t n,
+                        float scale) {
+  const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(in + i);
+    uint2 u;
+    __half2* h = reinterpret_cast<__half2*>(&u);
+    h[0] = __floats2half2_rn(v.x * scale, v.y * scale);
+    h[1] = __floats2half2_rn(v.z * scale, v.w * scale);
+    *reinterpret_cast<uint2*>(out + i) = u;
+  } else {
+    for (size_t j = i; j < n; ++j) out[j] = __float2half_rn(in[j] * scale);
+  }
+}
+
 inline int warps_grid(long long rows) { return (int)((rows * 32 + 255) / 256); }
 
 }  // namespace
@@ -314,12 +474,25 @@ int gb_launch_vit_assemble(gb_ctx* c, const void* patch, const float* cls, const
   return GB_OK;
 }
 
-int gb_launch_text_assemble(gb_ctx* c, const int32_t* ids, const void* tok_emb, const float* pos,
-                            const float* prefix, int P, void* x, int C, int ctx_len,
+__global__ void eot_rows_kernel(const int32_t* __restrict__ eot, int32_t* __restrict__ rows, int C,
+                                int Lt) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) rows[c] = c * Lt + min(eot[c], Lt - 1);
+}
+
+int gb_launch_eot_rows(gb_ctx* c, const int32_t* eot, int32_t* rows, int C, int Lt, cudaStream_t st) {
+  if (C <= 0) return GB_OK;
+  eot_rows_kernel<<<(C + 127) / 128, 128, 0, st>>>(eot, rows, C, Lt);
+  GB_LAUNCH_CHECK(c);
+  return GB_OK;
+}
+
+int gb_launch_text_assemble(gb_ctx* c, const int32_t* ids, int ld_ids, const void* tok_emb,
+                            const float* pos, const float* prefix, int P, void* x, int C, int ctx_len,
                             cudaStream_t st) {
   if (C <= 0) return GB_OK;
   text_assemble_kernel<<<warps_grid((long long)C * ctx_len), 256, 0, st>>>(
-      ids, (const __half*)tok_emb, pos, prefix, P, (__half*)x, C, ctx_len);
+      ids, ld_ids, (const __half*)tok_emb, pos, prefix, P, (__half*)x, C, ctx_len);
   GB_LAUNCH_CHECK(c);
   return GB_OK;
 }
@@ -328,6 +501,43 @@ int gb_launch_l2norm512(gb_ctx* c, const float* x, void* y16, float* y32, int ro
                         cudaStream_t st) {
   if (rows <= 0) return GB_OK;
   l2norm512_kernel<<<warps_grid(rows), 256, 0, st>>>(x, (__half*)y16, y32, rows);
+  GB_LAUNCH_CHECK(c);
+  return GB_OK;
+}
+
+int gb_launch_layernorm_bwd(gb_ctx* c, const void* dy, int lddy, const void* x, int ldx,
+                            const int32_t* row_idx, int in_row_mul, const float* gamma, void* dx,
+                            int lddx, int rows, int D, int accumulate, cudaStream_t st) {
+  if (rows <= 0) return GB_OK;
+  if (D != 512 && D != 768) return gb_fail(c, GB_ERR_ARG, "layernorm_bwd: D must be 512 or 768");
+  const int grid = warps_grid(rows);
+  if (D == 768)
+    layernorm_bwd_kernel<768><<<grid, 256, 0, st>>>((const __half*)dy, lddy, (const __half*)x, ldx, row_idx, in_row_mul, gamma, (__half*)dx, lddx, rows, accumulate, 1e-5f);
+  else
+    layernorm_bwd_kernel<512><<<grid, 256, 0, st>>>((const __half*)dy, lddy, (const __half*)x, ldx, row_idx, in_row_mul, gamma, (__half*)dx, lddx, rows, accumulate, 1e-5f);
+  GB_LAUNCH_CHECK(c);
+  return GB_OK;
+}
+
+int gb_launch_prefix_grad(gb_ctx* c, const void* dx, int L, int S, int P, int D, const float* prefix,
+                          const float* gamma, int ln_pre, float inv_scale, float* dprefix,
+                          cudaStream_t st) {
+  if (P <= 0) return GB_OK;
+  if (D == 768)
+    prefix_grad_kernel<768><<<P, 256, 0, st>>>((const __half*)dx, L, S, prefix, gamma, ln_pre, inv_scale, dprefix, 1e-5f);
+  else if (D == 512)
+    prefix_grad_kernel<512><<<P, 256, 0, st>>>((const __half*)dx, L, S, prefix, gamma, ln_pre, inv_scale, dprefix, 1e-5f);
+  else
+    return gb_fail(c, GB_ERR_ARG, "prefix_grad: D must be 512 or 768");
+  GB_LAUNCH_CHECK(c);
+  return GB_OK;
+}
+
+int gb_launch_scale_f32_to_f16(gb_ctx* c, const float* in, void* out, size_t n, float scale,
+                               cudaStream_t st) {
+  if (n == 0) return GB_OK;
+  const size_t threads = (n + 3) / 4;
+  scale_f32_to_f16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(in, (__half*)out, n, scale);
   GB_LAUNCH_CHECK(c);
   return GB_OK;
 }

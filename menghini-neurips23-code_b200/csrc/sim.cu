@@ -1,0 +1,740 @@
+// Pool scan: cosine-similarity logits → softmax → arg-max (+ leaderboard pre-filter) in ONE streaming
+// pass over the feature matrix, plus the exact sequential leaderboard replay.
+//
+//   logits[i,j] = scale · F[i,:]·T[j,:]     F [N,512] fp16 unit rows, T [C,512] fp16 unit rows
+//   probs[i,:]  = softmax(logits[i,:])      pred[i] = argmax     p_pred[i] = probs[i,pred[i]]
+//
+// Reference: CLIP.forward + `.softmax(dim=-1)` + `torch.argmax` executed once PER IMAGE at
+// utils/clip_pseudolabels.py:59-65 (and methods/*/textual_fpl.py:219-230 and siblings), followed by
+// the Python leaderboard utils/clip_pseudolabels.py:72-101.
+//
+// Kernel shape: the contraction needs 2·512·C FLOP per 1 KB feature row (≈100 FLOP/B at C=100), so it
+// only stays HBM-bound on the tensor pipe: persistent CTAs stream 128-row tiles of F through a TMA
+// ring, the prototype matrix stays resident in shared memory, tcgen05.mma accumulates the
+// [128 × C] logits tile in TMEM and each epilogue thread owns one image row (tcgen05.ld 32x32b), so
+// soft-max / arg-max / filter need no cross-thread reduction at all.  Algorithmic HBM traffic:
+// 1024 B (fp16 row) + 8 B (pred, p_pred) per image; full prob rows are written only on request or for
+// rows that can still change a leaderboard.
+#include "ctx.h"
+#include "common.cuh"
+
+using namespace gb;
+
+namespace {
+
+constexpr int kSimBM = 128;
+constexpr int kSimK = 512;
+constexpr int kSimKBlocks = kSimK / 64;  // 8
+constexpr int kSimStages = 5;
+constexpr int kSimThreads = 256;
+constexpr int kSimABytes = kSimBM * 64 * 2;  // 16 KB per stage
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+struct SimParams {
+  int N;           // rows of F covered by the tensor map
+  int C;           // classes (≤ BN)
+  int BN;          // C rounded up to 16 (UMMA N)
+  int tile_begin;  // first 128-row tile of this launch
+  int tile_end;    // one past the last tile
+  float scale;     // logit_scale.exp()
+  int mode;        // 0: pred = argmax(probs) (clip_pseudolabels.py:63); 1: argmax(logits) (textual_fpl.py:228)
+  int32_t* pred;   // [N]
+  float* p_pred;   // [N]
+  float* probs;    // [N, C] or nullptr: every row written
+  const float* lb;    // [C] leaderboard lower bounds or nullptr (no filtering)
+  uint32_t* flags;    // bit i%32 of flags[i/32]: row i may still change a board (only with lb)
+  float* cand_rows;   // [(tile_end-tile_begin)*128, C]: prob rows of flagged rows (only with lb)
+};
+
+__global__ void __launch_bounds__(kSimThreads, 1)
+sim_softmax_argmax_kernel(const __grid_constant__ CUtensorMap tmF,
+                          const __grid_constant__ CUtensorMap tmT, const SimParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int tBytes = p.BN * 128;  // one 64-wide k-block of T
+  uint8_t* smem_t = smem;
+  uint8_t* smem_a = smem + kSimKBlocks * tBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + kSimStages * kSimABytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kSimStages;
+  uint64_t* tfull_bar = bars + 2 * kSimStages;
+  uint64_t* tempty_bar = bars + 2 * kSimStages + 2;
+  uint64_t* t_bar = bars + 2 * kSimStages + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kSimStages + 5);
+  float* s_lb = reinterpret_cast<float*>(bars + 2 * kSimStages + 6);  // [BN]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmF);
+    tma_prefetch_desc(&tmT);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kSimStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    mbar_init(t_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 256);  // two accumulator stages of ≤128 fp32 columns
+    tmem_relinquish();
+  }
+  if (p.lb != nullptr)
+    for (int j = threadIdx.x; j < p.BN; j += kSimThreads) s_lb[j] = j < p.C ? p.lb[j] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // prototypes: resident for the whole kernel (rows ≥ C are zero-filled by TMA)
+      mbar_expect_tx(t_bar, kSimKBlocks * tBytes);
+      for (int kb = 0; kb < kSimKBlocks; ++kb)
+        tma_load_2d_hint(smem_t + kb * tBytes, &tmT, t_bar, kb * 64, 0, kEvictLast);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = p.tile_begin + blockIdx.x; tile < p.tile_end; tile += gridDim.x) {
+        for (int kb = 0; kb < kSimKBlocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], kSimABytes);
+          tma_load_2d_hint(smem_a + stage * kSimABytes, &tmF, &full_bar[stage], kb * 64,
+                           tile * kSimBM, kEvictFirst);
+          if (++stage == kSimStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(kSimBM, p.BN);
+      mbar_wait(t_bar, 0);
+      tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = p.tile_begin + blockIdx.x; tile < p.tile_end; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * 128;
+        for (int kb = 0; kb < kSimKBlocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_k_sw128(smem_u32(smem_a + stage * kSimABytes));
+          const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem_t + kb * tBytes));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kSimStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int C = p.C;
+    const int chunks = p.BN >> 4;
+    int it = 0;
+    for (int tile = p.tile_begin + blockIdx.x; tile < p.tile_end; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const int row = tile * kSimBM + q * 32 + lane;
+      const bool row_ok = row < p.N;
+      mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 128;
+      // pass 1: row max / first arg-max of the logits
+      float mx = -INFINITY;
+      int am = 0;
+      for (int c = 0; c < chunks; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x16(taddr + c * 16, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int col = c * 16 + j;
+          const float x = __uint_as_float(v[j]) * p.scale;
+          if (col < C && x > mx) { mx = x; am = col; }
+        }
+      }
+      // pass 2: soft-max denominator
+      float sum = 0.f;
+      for (int c = 0; c < chunks; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x16(taddr + c * 16, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int col = c * 16 + j;
+          if (col < C) sum += __expf(__uint_as_float(v[j]) * p.scale - mx);
+        }
+      }
+      const float inv = 1.0f / sum;
+      const float pmax = inv;  // exp(0) · inv
+      int pred = am;
+      bool survive = false;
+      const bool want_rows = p.probs != nullptr;
+      const bool filt = p.lb != nullptr;
+      if (want_rows || filt || p.mode == 0) {
+        // pass 3: probabilities → optional row store, arg-max over probs, leaderboard pre-filter
+        int first_pmax = -1;
+        for (int c = 0; c < chunks; ++c) {
+          uint32_t v[16];
+          tmem_ld_32x16(taddr + c * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = c * 16 + j;
+            if (col < C) {
+              const float pj = __expf(__uint_as_float(v[j]) * p.scale - mx) * inv;
+              if (first_pmax < 0 && pj == pmax) first_pmax = col;
+              if (filt && pj > s_lb[col]) survive = true;
+              if (want_rows && row_ok) p.probs[(size_t)row * C + col] = pj;
+            }
+          }
+        }
+        if (p.mode == 0 && first_pmax >= 0) pred = first_pmax;
+      }
+      // the accumulator may be recycled only after the LAST read; the candidate-row pass below
+      // re-reads it, so release after that
+      survive = survive && row_ok;
+      if (filt) {
+        const uint32_t ballot = __ballot_sync(0xffffffffu, survive);
+        if (lane == 0) p.flags[(tile * kSimBM + q * 32) >> 5] = ballot;
+        // tcgen05.ld is warp-collective: every lane re-reads the accumulator, only the flagged
+        // rows store their probabilities
+        if (!want_rows && ballot != 0) {
+          float* dst = p.cand_rows + (size_t)(row - p.tile_begin * kSimBM) * C;
+          for (int c = 0; c < chunks; ++c) {
+            uint32_t v[16];
+            tmem_ld_32x16(taddr + c * 16, v);
+            tmem_ld_wait();
+            if (survive) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int col = c * 16 + j;
+                if (col < C) dst[col] = __expf(__uint_as_float(v[j]) * p.scale - mx) * inv;
+              }
+            }
+          }
+        }
+      }
+      if (row_ok) {
+        p.pred[row] = pred;
+        p.p_pred[row] = pmax;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// =================================================================================================
+// Leaderboard state (device memory, caller-owned, relocatable: it can be handed to the next rank).
+//   int32 hdr[8]   : C, k, reserved…
+//   int32 cnt[C]   : entries in board j
+//   int32 srt[C]   : 1 once board j has been sorted (first successful admission)
+//   float lb[C]    : lower bound for the pre-filter: min(board) when full, −inf otherwise
+//   float ep[C*k]  : probabilities, list order
+//   int32 ei[C*k]  : global image indices, list order
+//   float sp[k+1]; int32 si[k+1] : scratch for the one-time full sort of a board
+// =================================================================================================
+struct LbView {
+  int C, k;
+  int32_t* cnt;
+  int32_t* srt;
+  float* lb;
+  float* ep;
+  int32_t* ei;
+  float* sp;
+  int32_t* si;
+};
+
+__host__ __device__ inline size_t lb_bytes(int C, int k) {
+  size_t w = 8 + 3 * (size_t)C + 2 * (size_t)C * k + 2 * ((size_t)k + 1);
+  return w * 4;
+}
+__host__ __device__ inline LbView lb_view(void* base, int C, int k) {
+  int32_t* w = reinterpret_cast<int32_t*>(base);
+  LbView v;
+  v.C = C; v.k = k;
+  v.cnt = w + 8;
+  v.srt = v.cnt + C;
+  v.lb = reinterpret_cast<float*>(v.srt + C);
+  v.ep = v.lb + C;
+  v.ei = reinterpret_cast<int32_t*>(v.ep + (size_t)C * k);
+  v.sp = reinterpret_cast<float*>(v.ei + (size_t)C * k);
+  v.si = reinterpret_cast<int32_t*>(v.sp + k + 1);
+  return v;
+}
+
+__global__ void lb_init_kernel(void* base, int C, int k) {
+  int32_t* w = reinterpret_cast<int32_t*>(base);
+  LbView v = lb_view(base, C, k);
+  for (int j = threadIdx.x; j < C; j += blockDim.x) {
+    v.cnt[j] = 0;
+    v.srt[j] = 0;
+    v.lb[j] = -INFINITY;
+  }
+  if (threadIdx.x == 0) {
+    w[0] = C; w[1] = k;
+    for (int i = 2; i < 8; ++i) w[i] = 0;
+  }
+}
+
+// (p, rank) descending order of Python's sorted(..., reverse=True) on (prob, path) tuples.
+__device__ __forceinline__ bool lb_before(float pa, int64_t ra, float pb, int64_t rb) {
+  return pa > pb || (pa == pb && ra > rb);
+}
+
+// Standalone pre-filter over an existing prob matrix: one thread per row; a warp covers one flag word.
+__global__ void __launch_bounds__(256)
+lb_filter_kernel(const float* __restrict__ probs, int C, int row_begin, int row_end,
+                 const float* __restrict__ lb, uint32_t* __restrict__ flags) {
+  const int row = (row_begin & ~31) + blockIdx.x * blockDim.x + threadIdx.x;
+  bool s = false;
+  if (row >= row_begin && row < row_end) {
+    const float* r = probs + (size_t)row * C;
+    for (int j = 0; j < C; ++j) s |= r[j] > __ldg(lb + j);
+  }
+  const uint32_t b = __ballot_sync(0xffffffffu, s);
+  if ((threadIdx.x & 31) == 0 && row < row_end) flags[row >> 5] = b;
+}
+
+// Exact sequential replay (utils/clip_pseudolabels.py:72-101) of the flagged rows of
+// [row_begin,row_end), in index order.  One CTA: warp 0 owns the state machine (lane l handles
+// boards l, l+32, …), warps 1-7 stage the flagged rows' probabilities into a shared-memory ring.
+constexpr int kLbThreads = 256;
+constexpr int kLbBatch = 64;  // rows per ring slot
+
+struct LbReplayParams {
+  void* state;
+  int C, k;
+  const float* rows;      // prob rows; row i lives at rows[(i - rows_row0) * C]
+  int rows_row0;
+  const int32_t* pred;    // [N] global
+  const int32_t* rank;    // [N] global tie-break rank (path order); nullptr → index order
+  const uint32_t* flags;  // global bitmask (bit i%32 of word i/32) or nullptr (every row)
+  int row_begin, row_end;
+  int idx0;               // global image index of local row 0 (boards and rank[] use global indices)
+};
+
+__device__ void lb_admit(const LbView& v, int j, float pj, int idx, const int32_t* rank,
+                         float* s_last, int lane);
+
+__global__ void __launch_bounds__(kLbThreads, 1) lb_replay_kernel(const LbReplayParams p) {
+  extern __shared__ uint8_t lb_smem[];
+  const int C = p.C, k = p.k;
+  float* ring = reinterpret_cast<float*>(lb_smem);                          // [2][kLbBatch][C]
+  int32_t* ring_idx = reinterpret_cast<int32_t*>(ring + 2 * kLbBatch * C);  // [2][kLbBatch]
+  int32_t* ring_pred = ring_idx + 2 * kLbBatch;                             // [2][kLbBatch]
+  int32_t* ring_n = ring_pred + 2 * kLbBatch;                               // [2]
+  float* s_last = reinterpret_cast<float*>(ring_n + 2);                     // [C]
+  int32_t* s_cnt = reinterpret_cast<int32_t*>(s_last + C);                  // [C]
+
+  const LbView v = lb_view(p.state, C, k);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = threadIdx.x; j < C; j += kLbThreads) {
+    const int c = v.cnt[j];
+    s_cnt[j] = c;
+    s_last[j] = c > 0 ? v.ep[(size_t)j * k + c - 1] : 0.f;
+  }
+  __syncthreads();
+
+  const int word_end = (p.row_end + 31) >> 5;
+  int w = p.row_begin >> 5;  // flag-scan cursor (warp 1, uniform)
+  int slot = 0;
+  bool have_prev = false;
+  while (true) {
+    if (warp == 0) {
+      // ---- consumer: exact sequential replay of the slot staged during the previous round ----
+      if (have_prev) {
+        const int ps = slot ^ 1;
+        const int n = ring_n[ps];
+        for (int s = 0; s < n; ++s) {
+          const int idx = ring_idx[ps * kLbBatch + s] + p.idx0;
+          const int own = ring_pred[ps * kLbBatch + s];
+          const float* row = ring + (size_t)(ps * kLbBatch + s) * C;
+          const float p_own = row[own];
+          const int c_own = s_cnt[own];
+          bool accepted = true;
+          if (c_own < k) {                         // utils/clip_pseudolabels.py:73-74
+            __syncwarp();
+            if (lane == 0) {
+              v.ep[(size_t)own * k + c_own] = p_own;
+              v.ei[(size_t)own * k + c_own] = idx;
+              s_cnt[own] = c_own + 1;
+              s_last[own] = p_own;
+            }
+            __syncwarp();
+          } else if (s_last[own] < p_own) {        // :75-82
+            lb_admit(v, own, p_own, idx, p.rank, s_last, lane);
+          } else {
+            accepted = false;
+          }
+          if (!accepted) {                         // :83-101 — offered to every other board
+            for (int j0 = 0; j0 < C; j0 += 32) {
+              const int j = j0 + lane;
+              bool need = false;
+              if (j < C && j != own) {
+                const int cj = s_cnt[j];
+                const float pj = row[j];
+                if (cj < k) {
+                  v.ep[(size_t)j * k + cj] = pj;
+                  v.ei[(size_t)j * k + cj] = idx;
+                  s_cnt[j] = cj + 1;
+                  s_last[j] = pj;
+                } else if (s_last[j] < pj) {
+                  need = true;
+                }
+              }
+              uint32_t nm = __ballot_sync(0xffffffffu, need);
+              while (nm) {
+                const int l = __ffs(nm) - 1;
+                nm &= nm - 1;
+                lb_admit(v, j0 + l, row[j0 + l], idx, p.rank, s_last, lane);
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+    } else {
+      // ---- producers: warp 1 collects the next ≤ kLbBatch flagged rows in index order ---------
+      if (warp == 1) {
+        int n = 0;
+        while (w < word_end) {
+          const int ww = w + lane;
+          uint32_t f = 0;
+          if (ww < word_end) {
+            f = p.flags ? p.flags[ww] : 0xffffffffu;
+            const int base = ww << 5;
+            if (base < p.row_begin) f &= ~((1u << (p.row_begin - base)) - 1u);   // < 32 by construction
+            if (base + 32 > p.row_end) f &= (p.row_end - base) >= 32 ? 0xffffffffu
+                                          : ((1u << (p.row_end - base)) - 1u);
+          }
+          const uint32_t nz = __ballot_sync(0xffffffffu, f != 0);
+          if (nz == 0) { w += 32; continue; }
+          const int first = __ffs(nz) - 1;
+          const uint32_t m = __shfl_sync(0xffffffffu, f, first);
+          const int cm = __popc(m);
+          w += first;
+          if (n + cm > kLbBatch) break;  // resume at this word next round
+          const int base = w << 5;
+          if ((m >> lane) & 1u) {
+            const int pos = n + __popc(m & ((1u << lane) - 1u));
+            ring_idx[slot * kLbBatch + pos] = base + lane;
+            ring_pred[slot * kLbBatch + pos] = p.pred[base + lane];
+          }
+          n += cm;
+          w += 1;
+        }
+        if (lane == 0) ring_n[slot] = n;
+      }
+      // producers-only barrier (7 warps), then everybody copies rows into the ring
+      asm volatile("bar.sync 1, %0;" ::"n"(kLbThreads - 32) : "memory");
+      const int n = ring_n[slot];
+      for (int s = warp - 1; s < n; s += (kLbThreads / 32 - 1)) {
+        const int idx = ring_idx[slot * kLbBatch + s];
+        const float* src = p.rows + (size_t)(idx - p.rows_row0) * C;
+        float* dst = ring + (size_t)(slot * kLbBatch + s) * C;
+        for (int j = lane; j < C; j += 32) dst[j] = src[j];
+      }
+    }
+    __syncthreads();
+    if (ring_n[slot] == 0) break;  // nothing new staged; the previous slot has just been replayed
+    have_prev = true;
+    slot ^= 1;
+  }
+  __syncthreads();
+  // publish counters and the pre-filter lower bounds
+  for (int j = threadIdx.x; j < C; j += kLbThreads) {
+    const int c = s_cnt[j];
+    v.cnt[j] = c;
+    float lbv = -INFINITY;
+    if (c >= k) {
+      if (v.srt[j]) {
+        lbv = v.ep[(size_t)j * k + k - 1];
+      } else {
+        lbv = INFINITY;
+        for (int e = 0; e < k; ++e) lbv = fminf(lbv, v.ep[(size_t)j * k + e]);
+      }
+    }
+    v.lb[j] = lbv;
+  }
+}
+
+// Admission of (pj, idx) into FULL board j whose last entry is < pj:
+//   board = sorted(board + [new], reverse=True)[:k]         (utils/clip_pseudolabels.py:78-82)
+// Warp-cooperative.  Sorted boards take an insertion; the first admission of a board does the full
+// (stable) sort of the k arrival-ordered entries plus the new one by rank counting.
+__device__ void lb_admit(const LbView& v, int j, float pj, int idx, const int32_t* rank,
+                         float* s_last, int lane) {
+  const int k = v.k;
+  float* ep = v.ep + (size_t)j * k;
+  int32_t* ei = v.ei + (size_t)j * k;
+  const int64_t rnew = rank ? (int64_t)rank[idx] : (int64_t)idx;
+  __syncwarp();
+  if (v.srt[j]) {
+    // pos = number of entries that stay in front of the new one (entries ≥ new; equal keys keep
+    // the old entry first — Python's sort is stable)
+    int pos = 0;
+    for (int e0 = 0; e0 < k; e0 += 32) {
+      const int e = e0 + lane;
+      bool front = false;
+      if (e < k) {
+        const float pe = ep[e];
+        front = pe > pj || (pe == pj && (rank ? (int64_t)rank[ei[e]] : (int64_t)ei[e]) >= rnew);
+      }
+      pos += __popc(__ballot_sync(0xffffffffu, front));
+    }
+    // shift [pos, k-2] → [pos+1, k-1] from the back, 32 at a time
+    for (int hi = k - 1; hi > pos; hi -= 32) {
+      const int e = hi - lane;  // destination
+      float tp = 0.f;
+      int ti = 0;
+      const bool act = e > pos;
+      if (act) { tp = ep[e - 1]; ti = ei[e - 1]; }
+      __syncwarp();
+      if (act) { ep[e] = tp; ei[e] = ti; }
+      __syncwarp();
+    }
+    if (lane == 0) { ep[pos] = pj; ei[pos] = idx; }
+    __syncwarp();
+  } else {
+    // full stable sort of k+1 items by rank counting into scratch, keep the first k
+    for (int a0 = 0; a0 <= k; a0 += 32) {
+      const int a = a0 + lane;
+      if (a <= k) {
+        const float pa = a < k ? ep[a] : pj;
+        const int ia = a < k ? ei[a] : idx;
+        const int64_t ra = rank ? (int64_t)rank[ia] : (int64_t)ia;
+        int before = 0;
+        for (int b = 0; b <= k; ++b) {
+          if (b == a) continue;
+          const float pb = b < k ? ep[b] : pj;
+          const int ib = b < k ? ei[b] : idx;
+          const int64_t rb = rank ? (int64_t)rank[ib] : (int64_t)ib;
+          if (lb_before(pb, rb, pa, ra) || (pb == pa && rb == ra && b < a)) ++before;
+        }
+        v.sp[before] = pa;
+        v.si[before] = ia;
+      }
+    }
+    __syncwarp();
+    for (int e = lane; e < k; e += 32) { ep[e] = v.sp[e]; ei[e] = v.si[e]; }
+    if (lane == 0) v.srt[j] = 1;
+    __syncwarp();
+  }
+  if (lane == 0) s_last[j] = ep[k - 1];
+  __syncwarp();
+}
+
+__global__ void lb_export_kernel(void* base, int C, int k, int32_t* out_idx, int32_t* out_len,
+                                 float* out_p) {
+  const LbView v = lb_view(base, C, k);
+  for (int j = blockIdx.x; j < C; j += gridDim.x) {
+    const int c = v.cnt[j];
+    if (threadIdx.x == 0) out_len[j] = c;
+    for (int e = threadIdx.x; e < k; e += blockDim.x) {
+      out_idx[(size_t)j * k + e] = e < c ? v.ei[(size_t)j * k + e] : -1;
+      if (out_p) out_p[(size_t)j * k + e] = e < c ? v.ep[(size_t)j * k + e] : 0.f;
+    }
+  }
+}
+
+size_t sim_smem_bytes(int BN) {
+  return (size_t)kSimKBlocks * BN * 128 + (size_t)kSimStages * kSimABytes + 1024 + 256 +
+         (size_t)BN * 4;
+}
+constexpr int kLbMaxC = 256;
+size_t lb_replay_smem_bytes(int C) {
+  return (size_t)2 * kLbBatch * C * 4 + (size_t)(4 * kLbBatch + 2) * 4 + (size_t)2 * C * 4 + 16;
+}
+
+int launch_sim(gb_ctx* c, const void* F, const void* T, float scale, int N, int C, int mode,
+               int row_begin, int row_end, int32_t* pred, float* p_pred, float* probs,
+               const float* lb, uint32_t* flags, float* cand_rows, cudaStream_t st) {
+  const int BN = (C + 15) & ~15;
+  if (C < 1 || BN > 128)
+    return gb_fail(c, GB_ERR_ARG, "sim: C=%d unsupported (1..128 classes per launch)", C);
+  if ((reinterpret_cast<uintptr_t>(F) | reinterpret_cast<uintptr_t>(T)) & 15)
+    return gb_fail(c, GB_ERR_ARG, "sim: F/T must be 16-byte aligned");
+  if (row_begin % kSimBM) return gb_fail(c, GB_ERR_ARG, "sim: row_begin must be a multiple of 128");
+  CUtensorMap tmF, tmT;
+  int rc = gb_make_tmap_2d_f16(c, &tmF, F, (uint64_t)N, kSimK, kSimK, kSimBM);
+  if (rc) return rc;
+  rc = gb_make_tmap_2d_f16(c, &tmT, T, (uint64_t)C, kSimK, kSimK, BN);
+  if (rc) return rc;
+  const size_t smem = sim_smem_bytes(BN);
+  static bool attr_set[16] = {false};
+  if (!attr_set[c->device & 15]) {
+    GB_CUDA(c, cudaFuncSetAttribute(sim_softmax_argmax_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sim_smem_bytes(128)));
+    attr_set[c->device & 15] = true;
+  }
+  SimParams p;
+  p.N = row_end < N ? row_end : N;
+  p.C = C; p.BN = BN;
+  p.tile_begin = row_begin / kSimBM;
+  p.tile_end = (p.N + kSimBM - 1) / kSimBM;
+  p.scale = scale; p.mode = mode;
+  p.pred = pred; p.p_pred = p_pred; p.probs = probs;
+  p.lb = lb; p.flags = flags; p.cand_rows = cand_rows;
+  const int tiles = p.tile_end - p.tile_begin;
+  if (tiles <= 0) return GB_OK;
+  const int grid = tiles < c->num_sms ? tiles : c->num_sms;
+  sim_softmax_argmax_kernel<<<grid, kSimThreads, smem, st>>>(tmF, tmT, p);
+  GB_LAUNCH_CHECK(c);
+  return GB_OK;
+}
+
+int launch_replay(gb_ctx* c, void* state, int C, int k, const float* rows, int rows_row0,
+                  const int32_t* pred, const int32_t* rank, const uint32_t* flags, int row_begin,
+                  int row_end, int idx0, cudaStream_t st) {
+  if (row_end <= row_begin) return GB_OK;
+  const size_t smem = lb_replay_smem_bytes(C);
+  static bool attr_set[16] = {false};
+  if (!attr_set[c->device & 15]) {
+    GB_CUDA(c, cudaFuncSetAttribute(lb_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)lb_replay_smem_bytes(kLbMaxC)));
+    attr_set[c->device & 15] = true;
+  }
+  LbReplayParams p;
+  p.state = state; p.C = C; p.k = k;
+  p.rows = rows; p.rows_row0 = rows_row0;
+  p.pred = pred; p.rank = rank; p.flags = flags;
+  p.row_begin = row_begin; p.row_end = row_end; p.idx0 = idx0;
+  lb_replay_kernel<<<1, kLbThreads, smem, st>>>(p);
+  GB_LAUNCH_CHECK(c);
+  return GB_OK;
+}
+
+}  // namespace
+
+// ---- C ABI ----------------------------------------------------------------------------------------
+extern "C" int gb_sim_softmax_argmax(gb_ctx* c, const void* F, const void* T, float scale, int N,
+                                     int C, int mode, int32_t* pred, float* p_pred, float* probs,
+                                     void* stream) {
+  if (!c) return GB_ERR_ARG;
+  if (N <= 0) return GB_OK;
+  if (!F || !T || !pred || !p_pred) return gb_fail(c, GB_ERR_ARG, "sim: null pointer");
+  return launch_sim(c, F, T, scale, N, C, mode, 0, N, pred, p_pred, probs, nullptr, nullptr,
+                    nullptr, (cudaStream_t)stream);
+}
+
+extern "C" size_t gb_leaderboard_state_bytes(int C, int k) {
+  if (C <= 0 || k <= 0) return 0;
+  return lb_bytes(C, k);
+}
+
+extern "C" int gb_leaderboard_init(gb_ctx* c, void* state, int C, int k, void* stream) {
+  if (!c) return GB_ERR_ARG;
+  if (!state || C <= 0 || C > kLbMaxC || k <= 0)
+    return gb_fail(c, GB_ERR_ARG, "leaderboard_init: bad arguments (C=%d in 1..256, k=%d > 0)", C, k);
+  lb_init_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(state, C, k);
+  GB_LAUNCH_CHECK(c);
+  return GB_OK;
+}
+
+// Feed rows [row_begin,row_end) of an existing prob matrix (row i at probs[i*C]) through the boards.
+extern "C" int gb_leaderboard_update(gb_ctx* c, void* state, int C, int k, const float* probs,
+                                     const int32_t* pred, const int32_t* rank, int row_begin,
+                                     int row_end, int idx0, int prefilter, void* stream) {
+  if (!c) return GB_ERR_ARG;
+  if (!state || !probs || !pred || C <= 0 || C > kLbMaxC || k <= 0 || row_begin < 0)
+    return gb_fail(c, GB_ERR_ARG, "leaderboard_update: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (row_end <= row_begin) return GB_OK;
+  if (!prefilter)
+    return launch_replay(c, state, C, k, probs, 0, pred, rank, nullptr, row_begin, row_end, idx0, st);
+  // chunked: filter against the bounds left by the previous chunk, then replay the survivors
+  const LbView v = lb_view(state, C, k);
+  int rc = gb_ws_reserve(c, ((size_t)(row_end + 31) / 32) * 4 + 256);
+  if (rc) return rc;
+  uint32_t* flags = reinterpret_cast<uint32_t*>(c->ws);
+  int chunk = 4096;
+  for (int r0 = row_begin; r0 < row_end;) {
+    const int r1 = min(r0 + chunk, row_end);
+    lb_filter_kernel<<<(r1 - (r0 & ~31) + 255) / 256, 256, 0, st>>>(probs, C, r0, r1, v.lb, flags);
+    GB_LAUNCH_CHECK(c);
+    rc = launch_replay(c, state, C, k, probs, 0, pred, rank, flags, r0, r1, idx0, st);
+    if (rc) return rc;
+    r0 = r1;
+    if (chunk < (1 << 18)) chunk *= 2;
+  }
+  return GB_OK;
+}
+
+extern "C" int gb_leaderboard_export(gb_ctx* c, const void* state, int C, int k, int32_t* out_idx,
+                                     int32_t* out_len, float* out_p, void* stream) {
+  if (!c) return GB_ERR_ARG;
+  if (!state || !out_idx || !out_len) return gb_fail(c, GB_ERR_ARG, "leaderboard_export: null pointer");
+  lb_export_kernel<<<C < 64 ? C : 64, 128, 0, (cudaStream_t)stream>>>(const_cast<void*>(state), C, k,
+                                                                     out_idx, out_len, out_p);
+  GB_LAUNCH_CHECK(c);
+  return GB_OK;
+}
+
+// Fused pool scan: sim + softmax + argmax + pre-filter in one HBM pass per chunk, exact replay of the
+// surviving rows between chunks.  Replaces the whole per-image loop of
+// utils/clip_pseudolabels.py:55-101.  Local row i is global image idx0 + i (a later shard continues on
+// the state handed over by the shard that owns the preceding index range); rank[] is global.
+extern "C" int gb_pseudolabel_scan(gb_ctx* c, void* state, const void* F, const void* T,
+                                   float scale, int N, int C, int k, int mode, int idx0,
+                                   const int32_t* rank, int32_t* pred, float* p_pred, float* probs,
+                                   void* stream) {
+  if (!c) return GB_ERR_ARG;
+  if (N <= 0) return GB_OK;
+  if (!state || !F || !T || !pred || !p_pred || k <= 0)
+    return gb_fail(c, GB_ERR_ARG, "pseudolabel_scan: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const LbView v = lb_view(state, C, k);
+  const int chunk_cap = 1 << 18;
+  const size_t flag_bytes = (((size_t)N + 127) / 128) * 16 + 256;
+  const size_t cand_bytes = probs ? 0 : (size_t)(N < chunk_cap ? ((N + 127) & ~127) : chunk_cap) * C * 4;
+  int rc = gb_ws_reserve(c, flag_bytes + cand_bytes);
+  if (rc) return rc;
+  uint32_t* flags = reinterpret_cast<uint32_t*>(c->ws);
+  float* cand = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(c->ws) + flag_bytes);
+  int chunk = 4096;
+  for (int r0 = 0; r0 < N;) {
+    const int r1 = min(r0 + chunk, N);
+    rc = launch_sim(c, F, T, scale, N, C, mode, r0, r1, pred, p_pred, probs, v.lb, flags,
+                    probs ? nullptr : cand, st);
+    if (rc) return rc;
+    rc = launch_replay(c, state, C, k, probs ? probs : cand, probs ? 0 : r0, pred, rank, flags, r0,
+                       r1, idx0, st);
+    if (rc) return rc;
+    r0 = r1;
+    if (chunk < chunk_cap) chunk *= 2;
+  }
+  return GB_OK;
+}

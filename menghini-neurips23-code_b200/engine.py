@@ -1,0 +1,326 @@
+"""Host side of the B200 towers: packs a CLIP ViT-B/32 state_dict into the device layout the C ABI
+wants, owns the gb_ctx weight tables, and exposes tower forward / prompt-gradient and the pool scan
+as torch-level calls (tensors in, tensors out; torch is only memory + streams here).
+
+Reference seams served:  clip_model.encode_image / encode_text / __call__ (third-party `clip`,
+call sites utils/clip_pseudolabels.py:59-61, methods/*/textual_prompt.py:100), the prompt-injecting
+forwards of models/clip_encoders.py:43-90,123-194 and autograd w.r.t. the prompt parameters.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import BlockWeights, Context, GripB200Error, TextWeights, VitWeights, ptr, stream_ptr
+
+EMBED = 512
+V_WIDTH, V_LAYERS, V_HEADS = 768, 12, 12
+T_WIDTH, T_LAYERS, T_HEADS, CTX_LEN = 512, 12, 8, 77
+
+
+def _require_cuda(device) -> torch.device:
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise GripB200Error(
+            f"the B200 engine runs on CUDA devices only (got {dev}); there is no CPU fallback")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+class Engine:
+    """Frozen towers of one CLIP ViT-B/32 on one GPU."""
+
+    def __init__(self, state_dict, device="cuda:0", with_grad: bool = True):
+        self.device = _require_cuda(device)
+        self.ctx = Context.get(self.device.index)
+        self.lib = self.ctx.lib
+        self.with_grad = with_grad
+        self._keep = []  # device tensors referenced by the C-side tables
+        sd = state_dict
+        with torch.cuda.device(self.device):
+            self._pack_vit(sd)
+            self._pack_text(sd)
+        ls = sd["logit_scale"]
+        self.logit_scale_exp = float(torch.as_tensor(ls).float().exp().item())
+
+    # ---- packing ------------------------------------------------------------------------------
+    def _f16(self, t):
+        t = t.detach().to(self.device, torch.float16).contiguous()
+        self._keep.append(t)
+        return t
+
+    def _f32(self, t):
+        # biases / LayerNorm affine: fp32 on device (rounded through fp16 first where clip.load keeps
+        # them in fp16, so both paths see the same parameter values)
+        t = t.detach().to(self.device, torch.float32).contiguous()
+        self._keep.append(t)
+        return t
+
+    def _blocks(self, sd, prefix, layers):
+        arr = (BlockWeights * layers)()
+        for i in range(layers):
+            p = f"{prefix}resblocks.{i}."
+            b = arr[i]
+            w_qkv, w_o = self._f16(sd[p + "attn.in_proj_weight"]), self._f16(sd[p + "attn.out_proj.weight"])
+            w_fc, w_proj = self._f16(sd[p + "mlp.c_fc.weight"]), self._f16(sd[p + "mlp.c_proj.weight"])
+            b.ln1_g, b.ln1_b = ptr(self._f32(sd[p + "ln_1.weight"])), ptr(self._f32(sd[p + "ln_1.bias"]))
+            b.ln2_g, b.ln2_b = ptr(self._f32(sd[p + "ln_2.weight"])), ptr(self._f32(sd[p + "ln_2.bias"]))
+            b.w_qkv, b.w_o, b.w_fc, b.w_proj = ptr(w_qkv), ptr(w_o), ptr(w_fc), ptr(w_proj)
+            b.b_qkv = ptr(self._f32(sd[p + "attn.in_proj_bias"].half()))
+            b.b_o = ptr(self._f32(sd[p + "attn.out_proj.bias"].half()))
+            b.b_fc = ptr(self._f32(sd[p + "mlp.c_fc.bias"].half()))
+            b.b_proj = ptr(self._f32(sd[p + "mlp.c_proj.bias"].half()))
+            if self.with_grad:
+                b.w_qkv_t = ptr(self._f16(w_qkv.t()))
+                b.w_o_t = ptr(self._f16(w_o.t()))
+                b.w_fc_t = ptr(self._f16(w_fc.t()))
+                b.w_proj_t = ptr(self._f16(w_proj.t()))
+        self._keep.append(arr)
+        return arr
+
+    def _pack_vit(self, sd):
+        w = VitWeights()
+        w.width, w.layers, w.heads, w.out_dim = V_WIDTH, V_LAYERS, V_HEADS, EMBED
+        conv = sd["visual.conv1.weight"]
+        if tuple(conv.shape) != (V_WIDTH, 3, 32, 32):
+            raise GripB200Error(f"only ViT-B/32 is built (conv1.weight {tuple(conv.shape)})")
+        w.conv_w = ptr(self._f16(conv.reshape(V_WIDTH, 3072)))
+        w.cls = ptr(self._f32(sd["visual.class_embedding"]))
+        w.pos = ptr(self._f32(sd["visual.positional_embedding"]))
+        w.ln_pre_g, w.ln_pre_b = ptr(self._f32(sd["visual.ln_pre.weight"])), ptr(self._f32(sd["visual.ln_pre.bias"]))
+        w.ln_post_g, w.ln_post_b = ptr(self._f32(sd["visual.ln_post.weight"])), ptr(self._f32(sd["visual.ln_post.bias"]))
+        proj = self._f16(sd["visual.proj"])
+        w.proj_t = ptr(self._f16(proj.t()))
+        w.proj = ptr(proj)
+        blocks = self._blocks(sd, "visual.transformer.", V_LAYERS)
+        w.blocks = ctypes.cast(blocks, ctypes.POINTER(BlockWeights))
+        self.ctx.check(self.lib.gb_vit_set_weights(self.ctx.h, ctypes.byref(w)), "gb_vit_set_weights")
+
+    def _pack_text(self, sd):
+        w = TextWeights()
+        w.width, w.layers, w.heads, w.out_dim = T_WIDTH, T_LAYERS, T_HEADS, EMBED
+        w.ctx_len, w.vocab = CTX_LEN, int(sd["token_embedding.weight"].shape[0])
+        w.tok_emb = ptr(self._f16(sd["token_embedding.weight"]))
+        w.pos = ptr(self._f32(sd["positional_embedding"]))
+        w.ln_final_g, w.ln_final_b = ptr(self._f32(sd["ln_final.weight"])), ptr(self._f32(sd["ln_final.bias"]))
+        proj = self._f16(sd["text_projection"])
+        w.proj_t = ptr(self._f16(proj.t()))
+        w.proj = ptr(proj)
+        blocks = self._blocks(sd, "transformer.", T_LAYERS)
+        w.blocks = ctypes.cast(blocks, ctypes.POINTER(BlockWeights))
+        self.ctx.check(self.lib.gb_text_set_weights(self.ctx.h, ctypes.byref(w)), "gb_text_set_weights")
+
+    # ---- towers -------------------------------------------------------------------------------
+    def tape_bytes(self, samples, L, D, layers=12) -> int:
+        return int(self.lib.gb_tape_bytes(samples, L, D, layers))
+
+    def vit_forward(self, img: torch.Tensor, prefix: Optional[torch.Tensor] = None,
+                    want_feat=True, want_featn=False, tape: bool = False):
+        """img [B,3,224,224] fp32/fp16 on this device; prefix fp32 [P,768] or None.
+        Returns (feat fp32 [B,512] | None, featn fp16 [B,512] | None, tape | None)."""
+        if img.device != self.device:
+            raise GripB200Error(f"image batch is on {img.device}, engine on {self.device}")
+        if img.dim() != 4 or tuple(img.shape[1:]) != (3, 224, 224):
+            raise GripB200Error(f"expected [B,3,224,224] images, got {tuple(img.shape)}")
+        if img.dtype not in (torch.float32, torch.float16):
+            img = img.float()
+        img = img.contiguous()
+        B = img.shape[0]
+        P = 0
+        if prefix is not None:
+            prefix = prefix.detach().reshape(-1, V_WIDTH).to(self.device, torch.float32).contiguous()
+            P = prefix.shape[0]
+        feat = torch.empty(B, EMBED, device=self.device, dtype=torch.float32) if want_feat else None
+        featn = torch.empty(B, EMBED, device=self.device, dtype=torch.float16) if want_featn else None
+        tp = None
+        if tape:
+            tp = torch.empty(self.tape_bytes(B, 50 + P, V_WIDTH), device=self.device, dtype=torch.uint8)
+        rc = self.lib.gb_vit_forward(self.ctx.h, ptr(img), int(img.dtype == torch.float32),
+                                     ptr(prefix) if P else None, B, P, ptr(feat), ptr(featn), ptr(tp),
+                                     stream_ptr())
+        self.ctx.check(rc, "gb_vit_forward")
+        return feat, featn, tp
+
+    def vit_backward_prefix(self, dfeat, prefix, tape):
+        prefix = prefix.detach().reshape(-1, V_WIDTH).to(self.device, torch.float32).contiguous()
+        dfeat = dfeat.detach().to(self.device, torch.float32).contiguous()
+        B, P = dfeat.shape[0], prefix.shape[0]
+        dprefix = torch.empty(P, V_WIDTH, device=self.device, dtype=torch.float32)
+        rc = self.lib.gb_vit_backward_prefix(self.ctx.h, ptr(dfeat), ptr(prefix), B, P, ptr(tape),
+                                             ptr(dprefix), stream_ptr())
+        self.ctx.check(rc, "gb_vit_backward_prefix")
+        return dprefix
+
+    def text_forward(self, ids: torch.Tensor, prefix: Optional[torch.Tensor] = None,
+                     want_feat=True, want_featn=False, tape: bool = False, full_context=False):
+        """ids int [C,77] (host or device); prefix fp32 [P,512] or None.
+        Positions after the last EOT are skipped unless full_context (exact either way: the causal
+        mask keeps them from reaching any EOT row)."""
+        ids_h = ids.detach().cpu()
+        eot_h = ids_h.argmax(dim=-1)
+        Lt = CTX_LEN if full_context else int(eot_h.max().item()) + 1
+        ids_d = ids_h.to(self.device, torch.int32).contiguous()
+        eot_d = eot_h.to(self.device, torch.int32).contiguous()
+        C = ids_d.shape[0]
+        P = 0
+        if prefix is not None:
+            prefix = prefix.detach().reshape(-1, T_WIDTH).to(self.device, torch.float32).contiguous()
+            P = prefix.shape[0]
+        Lt = max(Lt, P + 2)
+        feat = torch.empty(C, EMBED, device=self.device, dtype=torch.float32) if want_feat else None
+        featn = torch.empty(C, EMBED, device=self.device, dtype=torch.float16) if want_featn else None
+        tp = None
+        if tape:
+            tp = torch.empty(self.tape_bytes(C, Lt, T_WIDTH), device=self.device, dtype=torch.uint8)
+        rc = self.lib.gb_text_forward(self.ctx.h, ptr(ids_d), ids_d.stride(0), ptr(eot_d),
+                                      ptr(prefix) if P else None, C, P, Lt, ptr(feat), ptr(featn),
+                                      ptr(tp), stream_ptr())
+        self.ctx.check(rc, "gb_text_forward")
+        return feat, featn, (tp, eot_d, Lt)
+
+    def text_backward_prefix(self, dfeat, P, saved):
+        tape, eot_d, Lt = saved
+        dfeat = dfeat.detach().to(self.device, torch.float32).contiguous()
+        C = dfeat.shape[0]
+        dprefix = torch.empty(P, T_WIDTH, device=self.device, dtype=torch.float32)
+        rc = self.lib.gb_text_backward_prefix(self.ctx.h, ptr(dfeat), ptr(eot_d), C, P, Lt, ptr(tape),
+                                              ptr(dprefix), stream_ptr())
+        self.ctx.check(rc, "gb_text_backward_prefix")
+        return dprefix
+
+    # ---- pool scan ----------------------------------------------------------------------------
+    def sim_softmax_argmax(self, F16, T16, scale=None, mode=0, want_probs=False):
+        """F16 [N,512], T16 [C,512] fp16 unit rows → (pred int32 [N], p_pred fp32 [N], probs|None)."""
+        N, C = F16.shape[0], T16.shape[0]
+        scale = self.logit_scale_exp if scale is None else float(scale)
+        pred = torch.empty(N, device=self.device, dtype=torch.int32)
+        p_pred = torch.empty(N, device=self.device, dtype=torch.float32)
+        probs = torch.empty(N, C, device=self.device, dtype=torch.float32) if want_probs else None
+        rc = self.lib.gb_sim_softmax_argmax(self.ctx.h, ptr(F16), ptr(T16), scale, N, C, mode,
+                                            ptr(pred), ptr(p_pred), ptr(probs), stream_ptr())
+        self.ctx.check(rc, "gb_sim_softmax_argmax")
+        return pred, p_pred, probs
+
+
+class Leaderboard:
+    """Device-resident state of the reference's per-class pseudolabel boards
+    (utils/clip_pseudolabels.py:46-112).  The state tensor is plain bytes: it can be sent to the rank
+    that owns the next index range (ordered hand-off) and resumed there."""
+
+    def __init__(self, C: int, k: int, device="cuda:0", state: Optional[torch.Tensor] = None):
+        self.device = _require_cuda(device)
+        self.ctx = Context.get(self.device.index)
+        self.lib = self.ctx.lib
+        self.C, self.k = int(C), int(k)
+        if self.k <= 0 or self.C <= 0:
+            raise GripB200Error(f"leaderboard needs C > 0 and k > 0 (got C={C}, k={k})")
+        nbytes = int(self.lib.gb_leaderboard_state_bytes(self.C, self.k))
+        if state is None:
+            self.state = torch.empty(nbytes, device=self.device, dtype=torch.uint8)
+            self.ctx.check(self.lib.gb_leaderboard_init(self.ctx.h, ptr(self.state), self.C, self.k,
+                                                        stream_ptr()), "gb_leaderboard_init")
+        else:
+            if state.numel() != nbytes or state.dtype != torch.uint8:
+                raise GripB200Error("leaderboard state has the wrong size for (C, k)")
+            self.state = state.to(self.device).contiguous()
+
+    def update(self, probs, pred, rank=None, row_begin=0, row_end=None, idx0=0, prefilter=True):
+        """Feed rows [row_begin,row_end) of probs fp32 [n,C] / pred int32 [n]."""
+        n = probs.shape[0]
+        row_end = n if row_end is None else row_end
+        rc = self.lib.gb_leaderboard_update(self.ctx.h, ptr(self.state), self.C, self.k, ptr(probs),
+                                            ptr(pred), ptr(rank), row_begin, row_end, idx0,
+                                            int(bool(prefilter)), stream_ptr())
+        self.ctx.check(rc, "gb_leaderboard_update")
+
+    def scan(self, F16, T16, scale, mode=0, idx0=0, rank=None, want_probs=False):
+        """Fused similarity + softmax + argmax + board update over the rows of F16."""
+        N = F16.shape[0]
+        pred = torch.empty(N, device=self.device, dtype=torch.int32)
+        p_pred = torch.empty(N, device=self.device, dtype=torch.float32)
+        probs = torch.empty(N, self.C, device=self.device, dtype=torch.float32) if want_probs else None
+        rc = self.lib.gb_pseudolabel_scan(self.ctx.h, ptr(self.state), ptr(F16), ptr(T16), float(scale),
+                                          N, self.C, self.k, mode, idx0, ptr(rank), ptr(pred),
+                                          ptr(p_pred), ptr(probs), stream_ptr())
+        self.ctx.check(rc, "gb_pseudolabel_scan")
+        return pred, p_pred, probs
+
+    def export(self, want_p=False):
+        """(idx int32 [C,k] −1-padded, len int32 [C], p fp32 [C,k] | None), all on device."""
+        idx = torch.empty(self.C, self.k, device=self.device, dtype=torch.int32)
+        ln = torch.empty(self.C, device=self.device, dtype=torch.int32)
+        p = torch.empty(self.C, self.k, device=self.device, dtype=torch.float32) if want_p else None
+        self.ctx.check(self.lib.gb_leaderboard_export(self.ctx.h, ptr(self.state), self.C, self.k,
+                                                      ptr(idx), ptr(ln), ptr(p), stream_ptr()),
+                       "gb_leaderboard_export")
+        return idx, ln, p
+
+    def result(self, class_ids=None):
+        """(image indices, labels) in the reference's output order (boards in class order, each in
+        list order): utils/clip_pseudolabels.py:103-109."""
+        idx, ln, _ = self.export()
+        idx, ln = idx.cpu(), ln.cpu()
+        out_idx, out_lab = [], []
+        for j in range(self.C):
+            n = int(ln[j])
+            out_idx += idx[j, :n].tolist()
+            out_lab += [j if class_ids is None else class_ids[j]] * n
+        return out_idx, out_lab
+
+
+# ---- autograd bridges: gradient flows only into the prompt rows (the backbone is frozen) ----------
+class _VitPrefixFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, prefix, img, engine):
+        need = ctx.needs_input_grad[0]
+        feat, _, tape = engine.vit_forward(img, prefix, tape=need)
+        ctx.engine, ctx.tape = engine, tape
+        ctx.save_for_backward(prefix)
+        ctx.pshape = prefix.shape
+        return feat
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        (prefix,) = ctx.saved_tensors
+        if ctx.tape is None:
+            raise GripB200Error("backward through the image tower without a recorded tape")
+        dp = ctx.engine.vit_backward_prefix(dfeat, prefix, ctx.tape)
+        ctx.tape = None
+        return dp.reshape(ctx.pshape).to(prefix.dtype), None, None
+
+
+class _TextPrefixFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, prefix, ids, engine):
+        need = ctx.needs_input_grad[0]
+        feat, _, saved = engine.text_forward(ids, prefix, tape=need)
+        ctx.engine, ctx.saved_state = engine, saved
+        ctx.pshape, ctx.pdtype = prefix.shape, prefix.dtype
+        ctx.P = prefix.reshape(-1, T_WIDTH).shape[0]
+        return feat
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        if ctx.saved_state[0] is None:
+            raise GripB200Error("backward through the text tower without a recorded tape")
+        dp = ctx.engine.text_backward_prefix(dfeat, ctx.P, ctx.saved_state)
+        ctx.saved_state = None
+        return dp.reshape(ctx.pshape).to(ctx.pdtype), None, None
+
+
+def vit_with_prefix(engine: Engine, img, prefix):
+    """Differentiable (w.r.t. prefix) CustomVisionTransformer.forward."""
+    if prefix.requires_grad and torch.is_grad_enabled():
+        return _VitPrefixFn.apply(prefix, img, engine)
+    return engine.vit_forward(img, prefix)[0]
+
+
+def text_with_prefix(engine: Engine, ids, prefix):
+    """Differentiable (w.r.t. prefix) CustomTextEncoder.forward after tokenisation."""
+    if prefix.requires_grad and torch.is_grad_enabled():
+        return _TextPrefixFn.apply(prefix, ids, engine)
+    return engine.text_forward(ids, prefix)[0]
