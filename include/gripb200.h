@@ -41,6 +41,13 @@ const char* gb_last_error(gb_ctx* ctx);
 uint64_t gb_launch_count(gb_ctx* ctx);
 const char* gb_version(void);
 
+/* Per-launch CUDA-event timing of the two roofline kernels, for bench.py: between _begin and _end
+ * every tcgen05 GEMM launch (kind 0, work = 2*M*N*K FLOP) and every similarity/softmax/argmax launch
+ * (kind 1, work = algorithmic HBM bytes) is bracketed by an event pair on its own stream. */
+typedef struct gb_profile_stats { uint64_t launches; double ms; double work; } gb_profile_stats;
+int gb_profile_begin(gb_ctx* ctx);
+int gb_profile_end(gb_ctx* ctx, gb_profile_stats* out, int kinds);
+
 /* ---- op level (unit-testable building blocks) -------------------------------------------- */
 
 /* out[M,N] = epi(A[M,K] · W[N,K]^T): fp16 operands, fp32 accumulate (tcgen05 + TMA + TMEM).

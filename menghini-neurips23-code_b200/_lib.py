@@ -22,6 +22,10 @@ class GripB200Error(RuntimeError):
 P = c_void_p
 
 
+class ProfileStats(Structure):
+    _fields_ = [("launches", c_uint64), ("ms", ctypes.c_double), ("work", ctypes.c_double)]
+
+
 class BlockWeights(Structure):
     _fields_ = [(n, P) for n in (
         "ln1_g", "ln1_b", "w_qkv", "b_qkv", "w_o", "b_o", "ln2_g", "ln2_b", "w_fc", "b_fc",
@@ -48,6 +52,8 @@ _SIGNATURES = {
     "gb_last_error": (c_char_p, [P]),
     "gb_launch_count": (c_uint64, [P]),
     "gb_version": (c_char_p, []),
+    "gb_profile_begin": (c_int, [P]),
+    "gb_profile_end": (c_int, [P, POINTER(ProfileStats), c_int]),
     "gb_gemm_f16": (c_int, [P, P, c_int, P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int,
                             c_int, c_int, P]),
     "gb_layernorm_f16": (c_int, [P, P, c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, P]),
@@ -139,6 +145,15 @@ class Context:
     @property
     def launches(self) -> int:
         return int(self.lib.gb_launch_count(self.h))
+
+    def profile_begin(self):
+        self.check(self.lib.gb_profile_begin(self.h), "gb_profile_begin")
+
+    def profile_end(self):
+        """[(launches, ms, work)] for kind 0 (GEMM, FLOPs) and kind 1 (sim kernel, bytes)."""
+        arr = (ProfileStats * 2)()
+        self.check(self.lib.gb_profile_end(self.h, arr, 2), "gb_profile_end")
+        return [(int(a.launches), float(a.ms), float(a.work)) for a in arr]
 
     # ---- op level -------------------------------------------------------------------------
     def gemm(self, A, W, bias=None, resid=None, out=None, act=0, out_f32=False):

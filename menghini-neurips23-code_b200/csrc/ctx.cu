@@ -75,3 +75,26 @@ int gb_make_tmap_2d_f16(gb_ctx* c, CUtensorMap* out, const void* ptr, uint64_t r
                    (unsigned long long)ld_elems, box_rows);
   return GB_OK;
 }
+
+extern "C" int gb_profile_begin(gb_ctx* c) {
+  if (!c) return GB_ERR_ARG;
+  for (auto& r : c->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  c->prof.clear();
+  c->prof_on = true;
+  return GB_OK;
+}
+
+extern "C" int gb_profile_end(gb_ctx* c, gb_profile_stats* out, int kinds) {
+  if (!c || !out || kinds <= 0) return GB_ERR_ARG;
+  c->prof_on = false;
+  GB_CUDA(c, cudaDeviceSynchronize());
+  for (int k = 0; k < kinds; ++k) { out[k].launches = 0; out[k].ms = 0; out[k].work = 0; }
+  for (auto& r : c->prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    if (r.kind < kinds) { out[r.kind].launches++; out[r.kind].ms += ms; out[r.kind].work += r.work; }
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+  }
+  c->prof.clear();
+  return GB_OK;
+}

@@ -17,7 +17,10 @@ static int launch_gemm_bn(gb_ctx* c, const CUtensorMap& tmA, const CUtensorMap& 
   const int m_tiles = (p.M + kBM - 1) / kBM;
   const int tiles = m_tiles * (p.N / BN);
   const int grid = tiles < c->num_sms ? tiles : c->num_sms;
-  gemm_f16_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+  {
+    gb_prof_scope prof(c, st, 0, 2.0 * p.M * p.N * p.K);
+    gemm_f16_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+  }
   GB_LAUNCH_CHECK(c);
   return GB_OK;
 }
@@ -35,9 +38,10 @@ int gb_launch_gemm(gb_ctx* c, const void* A, int lda, const void* W, int ldw, co
        reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(resid) |
        reinterpret_cast<uintptr_t>(bias)) & 15)
     return gb_fail(c, GB_ERR_ARG, "gemm: pointers must be 16-byte aligned");
-  // 256-wide tiles halve the per-FLOP shared-memory traffic; use them when they still fill the GPU.
-  const int m_tiles = (M + kBM - 1) / kBM;
-  const bool wide = (N % 256 == 0) && (m_tiles * (N / 256) >= c->num_sms);
+  // 256-wide tiles halve the per-FLOP shared-memory traffic.  The tile shape is a function of N only:
+  // a row's arithmetic must not depend on how many other rows are in the batch (pseudolabels have to
+  // be bit-identical however the pool is batched or sharded across GPUs).
+  const bool wide = (N % 256 == 0);
   const int BN = wide ? 256 : 128;
   CUtensorMap tmA, tmB;
   int rc = gb_make_tmap_2d_f16(c, &tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM);

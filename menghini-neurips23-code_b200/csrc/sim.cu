@@ -40,6 +40,15 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
       : "memory");
 }
 
+// logit and probability of one accumulator element — explicit rounding steps (no FMA contraction) so
+// that every pass of the epilogue, and every launch mode, produces identical bits.
+__device__ __forceinline__ float sim_logit(uint32_t acc, float scale) {
+  return __fmul_rn(__uint_as_float(acc), scale);
+}
+__device__ __forceinline__ float sim_exp(uint32_t acc, float scale, float mx) {
+  return __expf(__fsub_rn(sim_logit(acc, scale), mx));
+}
+
 struct SimParams {
   int N;           // rows of F covered by the tensor map
   int C;           // classes (≤ BN)
@@ -171,7 +180,7 @@ sim_softmax_argmax_kernel(const __grid_constant__ CUtensorMap tmF,
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int col = c * 16 + j;
-          const float x = __uint_as_float(v[j]) * p.scale;
+          const float x = sim_logit(v[j], p.scale);
           if (col < C && x > mx) { mx = x; am = col; }
         }
       }
@@ -184,10 +193,10 @@ sim_softmax_argmax_kernel(const __grid_constant__ CUtensorMap tmF,
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int col = c * 16 + j;
-          if (col < C) sum += __expf(__uint_as_float(v[j]) * p.scale - mx);
+          if (col < C) sum += sim_exp(v[j], p.scale, mx);
         }
       }
-      const float inv = 1.0f / sum;
+      const float inv = __frcp_rn(sum);
       const float pmax = inv;  // exp(0) · inv
       int pred = am;
       bool survive = false;
@@ -204,7 +213,7 @@ sim_softmax_argmax_kernel(const __grid_constant__ CUtensorMap tmF,
           for (int j = 0; j < 16; ++j) {
             const int col = c * 16 + j;
             if (col < C) {
-              const float pj = __expf(__uint_as_float(v[j]) * p.scale - mx) * inv;
+              const float pj = __fmul_rn(sim_exp(v[j], p.scale, mx), inv);
               if (first_pmax < 0 && pj == pmax) first_pmax = col;
               if (filt && pj > s_lb[col]) survive = true;
               if (want_rows && row_ok) p.probs[(size_t)row * C + col] = pj;
@@ -231,7 +240,7 @@ sim_softmax_argmax_kernel(const __grid_constant__ CUtensorMap tmF,
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const int col = c * 16 + j;
-                if (col < C) dst[col] = __expf(__uint_as_float(v[j]) * p.scale - mx) * inv;
+                if (col < C) dst[col] = __fmul_rn(sim_exp(v[j], p.scale, mx), inv);
               }
             }
           }
@@ -611,7 +620,12 @@ int launch_sim(gb_ctx* c, const void* F, const void* T, float scale, int N, int 
   const int tiles = p.tile_end - p.tile_begin;
   if (tiles <= 0) return GB_OK;
   const int grid = tiles < c->num_sms ? tiles : c->num_sms;
-  sim_softmax_argmax_kernel<<<grid, kSimThreads, smem, st>>>(tmF, tmT, p);
+  {
+    // algorithmic bytes: one fp16 feature row in, (pred, p_pred) out per image (+ the prob row on request)
+    const double rows = (double)(p.N - row_begin);
+    gb_prof_scope prof(c, st, 1, rows * (kSimK * 2 + 8 + (probs ? 4.0 * C : 0.0)));
+    sim_softmax_argmax_kernel<<<grid, kSimThreads, smem, st>>>(tmF, tmT, p);
+  }
   GB_LAUNCH_CHECK(c);
   return GB_OK;
 }

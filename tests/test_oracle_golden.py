@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import clip_ref, leaderboard_ref, synth
+from oracle import clip_ref, leaderboard_ref, prompt_ref, synth
 
 
 def test_leaderboard_restatement_matches_reference_goldens(golden_dir):
@@ -78,3 +78,18 @@ def test_text_prompt_strings_follow_reference():
     assert ids.shape == (2, 77)
     assert ids[0, 1:5].unique().numel() == 1 and ids[0, 5] != ids[0, 1]
     assert ids.argmax(-1).tolist() == [8, 6]
+
+
+def test_prompt_forward_restatements_match_reference_goldens(golden_dir):
+    g = np.load(f"{golden_dir}/towers_vitb32_seed1234.npz")
+    model = clip_ref.build_model(seed=1234)
+    classes = [" ".join(c.split("_")) for c in synth.class_names(5, seed=1)]
+    with torch.no_grad():
+        t16 = prompt_ref.text_forward(model, synth.text_prefix(16), classes).numpy()
+        v4 = prompt_ref.image_forward(model, synth.images(2, seed=0), synth.image_prefix(4)).numpy()
+    assert np.abs(t16 - g["txt_feat_p16"]).max() < 1e-4
+    assert np.abs(v4 - g["img_feat_p4"]).max() < 1e-4
+    loss, grad, _ = prompt_ref.coop_step(model, synth.text_prefix(16), classes, synth.images(4, seed=0),
+                                         torch.tensor([0, 1, 2, 3]))
+    assert abs(float(loss) - float(g["coop_loss"])) < 1e-4
+    assert np.abs(grad.numpy() - g["coop_grad_prefix"]).max() < 1e-4
