@@ -54,6 +54,18 @@ def test_gemm_epilogues(ctx):
     _gemm_case(ctx, 333, 512, 768, out_f32=True)
 
 
+def test_gemm_rows_do_not_depend_on_batch(ctx):
+    """Bit-identical rows whatever M is (tile shape is a function of N only)."""
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for N, K in ((3072, 768), (768, 3072), (2304, 768), (512, 768), (1536, 512)):
+        A = (torch.randn(20000, K, device="cuda", generator=g) * 0.5).half()
+        W = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).half()
+        big = ctx.gemm(A, W, out_f32=True)
+        for m in (1, 50, 128, 1850):
+            small = ctx.gemm(A[:m].contiguous(), W, out_f32=True)
+            assert torch.equal(small, big[:m]), (N, K, m)
+
+
 def test_gemm_rejects_bad_shapes(ctx, pkg):
     A = torch.zeros(16, 100, device="cuda", dtype=torch.float16)
     W = torch.zeros(128, 100, device="cuda", dtype=torch.float16)

@@ -45,13 +45,11 @@ def sim(pkg, eng_mod):
 @pytest.mark.parametrize("N,C", [(1, 1), (5, 10), (128, 16), (129, 45), (1000, 100), (4097, 102),
                                  (300, 128), (777, 7), (20000, 18)])
 def test_sim_softmax_argmax_matches_oracle(sim, N, C):
-    f, t = synth.pool(N, C, peaked=0.3)
+    f, t = synth.pool(N, C, peaked=0.05 if N % 2 else 0.3)
     F, T = f.half().cuda(), t.half().cuda()
     pred, pp, probs = sim(F, T, 100.0)
     # oracle on the SAME fp16-rounded inputs, fp32 arithmetic (tolerance: fp32 accumulation order +
     # ex2-based exp: 2e-5 absolute on probabilities)
-    _, o_probs, o_pred = leaderboard_ref.softmax_argmax(F.float().cpu().numpy(), T.float().cpu().numpy(),
-                                                        100.0)
     # inputs are already unit rows up to fp16 rounding; the kernel does not renormalise
     lg = 100.0 * (F.float().cpu().numpy() @ T.float().cpu().numpy().T)
     e = np.exp(lg - lg.max(1, keepdims=True))
