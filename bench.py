@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""images/sec of the ViT-B/32 prompt-tune + pseudolabel hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    (N > 1: python -m torch.distributed.run --nproc-per-node N … bench.py --gpus N …)
+
+One step = one pass of the hot path over one batch of B synthetic 224x224x3 images per GPU, in the
+shape of BASELINE.json configs[1] (CoOp textual prompt, EuroSAT C=10, P=16, ViT-B/32) plus the FPL
+pseudolabel assignment (k=16) on the same batch:
+  1. frozen image tower on the batch                       (clip_model.encode_image, textual_prompt.py:99-103)
+  2. text tower with the learnable prefix, with tape       (TextPrefixModel.forward, :94-97)
+  3. cosine logits, cross-entropy, backward to the prefix, SGD update   (:98-135)
+  4. similarity + softmax + argmax + per-class leaderboard update with the current prompts
+                                                           (assign_pseudo_labels, textual_fpl.py:195-283)
+`value` times this with the batch already resident in HBM; `e2e` feeds every step from pinned host
+memory (H2D copy inside the timed region, double buffered) and reads the loss and predictions back.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = "menghini-neurips23-code_b200"
+
+METRIC = "images/sec ViT-B/32 prompt-tune+pseudolabel"
+FLOP_VIT_P0 = 2 * 49 * 3072 * 768 + 12 * (24 * 50 * 768 ** 2 + 4 * 50 ** 2 * 768) + 2 * 768 * 512  # 8.818 G
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="images per GPU per step")
+    ap.add_argument("--classes", type=int, default=10)
+    ap.add_argument("--prefix", type=int, default=16)
+    ap.add_argument("--k", type=int, default=16)
+    ap.add_argument("--cpu-batch", type=int, default=16, help="reference BATCH_SIZE for the CPU arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a, batch):
+    return (f"CoOp prompt-tune step (P={a.prefix}, C={a.classes}, ViT-B/32, SGD) + FPL pseudolabel "
+            f"leaderboard (k={a.k}) on {batch} synthetic 224x224x3 fp32 images per GPU per step")
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path (fp32 torch on the host cores)
+# --------------------------------------------------------------------------------------------------
+def cpu_arm(a, steps, warmup, budget_s=None):
+    from oracle import clip_ref, leaderboard_ref, prompt_ref, synth
+
+    synthetic = importlib.import_module(PKG + ".synthetic")
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = clip_ref.build_model(synthetic.synthetic_state_dict(1234))
+    classes = [" ".join(c.split("_")) for c in synth.class_names(a.classes, seed=1)]
+    B = a.cpu_batch
+    img = synth.images(B, seed=0)
+    labels = torch.arange(B) % a.classes
+    prefix = synth.text_prefix(a.prefix)
+    boards_probs, boards_pred = [], []
+
+    def step(prefix):
+        loss, grad, logits = prompt_ref.coop_step(model, prefix, classes, img, labels)
+        prefix = prefix - 1e-4 * grad
+        probs = torch.softmax(logits, dim=-1)          # textual_fpl.py:226-228
+        boards_probs.append(probs.numpy())
+        boards_pred.append(torch.argmax(logits, dim=1).numpy())
+        return prefix
+
+    for _ in range(warmup):
+        prefix = step(prefix)
+    boards_probs.clear(); boards_pred.clear()
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        prefix = step(prefix)
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
+    import numpy as np
+    pr, pd = np.concatenate(boards_probs), np.concatenate(boards_pred)
+    leaderboard_ref.leaderboard(pr, pd, a.k, list(range(len(pd))))
+    dt = time.perf_counter() - t0
+    return {"value": done * B / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{done} steps of the same step at the reference BATCH_SIZE={B} "
+                      f"(fp32 torch CPU oracle of the reference path, {dt:.1f} s)"}, dt / done * 1e3, done
+
+
+def run_reference(a, rank):
+    if rank != 0:
+        return
+    base, ms, done = cpu_arm(a, a.steps, min(a.warmup, 1), budget_s=150.0)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "images/s",
+            "n_gpus": a.gpus, "steps": done, "warmup": min(a.warmup, 1), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": workload_name(a, a.cpu_batch),
+                                            "note": "reference CPU path (oracle port), bounded sample"},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler (NVML) — runs during the timed region
+# --------------------------------------------------------------------------------------------------
+class Clocks:
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._stop = [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self.nv:
+            self.t.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self.nv:
+            self.t.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            p = json.load(open(path))
+            return {"hbm_gbs": float(p["hbm_gbs"]),
+                    "tflops": float(p.get("bf16_tflops_sustained", p.get("bf16_tflops"))),
+                    "src": "measured (MEASURED_PEAKS.json: hbm_gbs, bf16_tflops_sustained)"}
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0,
+            "src": "fallback (B200_PROFILING.md: 6.65 TB/s copy, 1.4 PFLOP/s sustained cuBLAS bf16)"}
+
+
+# --------------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------------
+def run_b200(a, rank, local_rank, world):
+    import torch.distributed as dist
+
+    pkg = importlib.import_module(PKG)
+    clip = importlib.import_module(PKG + ".clip")
+    models = importlib.import_module(PKG + ".models")
+    engine_mod = importlib.import_module(PKG + ".engine")
+    gdist = importlib.import_module(PKG + ".dist")
+    synthetic = importlib.import_module(PKG + ".synthetic")
+    if not torch.cuda.is_available():
+        raise pkg.GripB200Error("bench.py needs a B200: there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, C, P, k = a.batch, a.classes, a.prefix, a.k
+    model, _ = clip.load("ViT-B/32", dev, state_dict=synthetic.synthetic_state_dict(1234))
+    eng = model.engine
+    ctx = eng.ctx
+    g = torch.Generator().manual_seed(1)
+    words = ["annual", "crop", "forest", "highway", "industrial", "pasture", "river", "lake", "residential",
+             "vegetation", "sea", "road", "land", "buildings"]
+    classes = [" ".join(words[int(torch.randint(0, len(words), (1,), generator=g))]
+                        for _ in range(int(torch.randint(1, 5, (1,), generator=g)))) + f" {j}"
+               for j in range(C)]
+    gp = torch.Generator().manual_seed(2)
+    cte = models.CustomTextEncoder(model, dev, torch.float16)
+    tpm = models.TextPrefixModel((0.02 * torch.randn(1, P, 512, generator=gp)).to(dev), cte, classes, device=dev)
+    opt = torch.optim.SGD([tpm.prefix], lr=1e-4)   # WARMUP_LR of textual_prompt_config.yml
+    scale = eng.logit_scale_exp
+    total_steps = a.warmup + a.steps + 3 + a.warmup + a.steps
+    n_total = total_steps * world * B
+    rank_all = torch.randperm(n_total, generator=torch.Generator().manual_seed(7)).to(torch.int32).to(dev)
+    board = engine_mod.Leaderboard(C, k, dev)
+    state = {"step": 0, "board": board}
+
+    gi = torch.Generator().manual_seed(100 + rank)
+    host = [torch.randn(B, 3, 224, 224, generator=gi).pin_memory() for _ in range(2)]
+    host_labels = [(torch.randint(0, C, (B,), generator=gi)).pin_memory() for _ in range(2)]
+    dev_img = [h.to(dev) for h in host]
+    dev_lab = [h.to(dev) for h in host_labels]
+    out_pred = torch.empty(B, dtype=torch.int32).pin_memory()
+    out_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def step(img, labels):
+        s = state["step"]
+        with torch.no_grad():
+            feat, featn, _ = eng.vit_forward(img, None, want_feat=True, want_featn=True)
+            imfn = feat / feat.norm(dim=-1, keepdim=True)
+        tf = tpm(classes)
+        tfn = tf / tf.norm(dim=-1, keepdim=True)
+        logits = scale * imfn @ tfn.t()
+        loss = torch.nn.functional.cross_entropy(logits, labels)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if world > 1:
+            gdist.allreduce_mean_(tpm.prefix.grad)
+        opt.step()
+        protos = tfn.detach().half()
+        idx0 = (s * world + rank) * B
+
+        def scan(st):
+            b = engine_mod.Leaderboard(C, k, dev, state=st)
+            state["pred"] = b.scan(featn, protos, scale, mode=1, idx0=idx0, rank=rank_all)[0]
+            return b.state
+
+        if world > 1:
+            state["board"].state = gdist.ordered_handoff(state["board"].state, scan, ring=True)
+        else:
+            scan(state["board"].state)
+        state["step"] = s + 1
+        return loss
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launches
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, ctx.launches - l0
+
+    # ---- device-resident arm -------------------------------------------------------------------
+    for i in range(a.warmup):
+        step(dev_img[i % 2], dev_lab[i % 2])
+    with Clocks(local_rank) as clk:
+        ms, launches = timed(lambda i: step(dev_img[i % 2], dev_lab[i % 2]), a.steps)
+    value = a.steps * B * world / (ms / 1e3)
+
+    # ---- roofline: per-launch event timing of the GEMM (tensor) and sim (HBM) kernels in 3 more steps
+    ctx.profile_begin()
+    for i in range(3):
+        step(dev_img[i % 2], dev_lab[i % 2])
+    (g_n, g_ms, g_flop), (s_n, s_ms, s_bytes) = ctx.profile_end()
+    pk = peaks()
+    achieved = g_flop / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "gemm_f16_tcgen05_kernel", "achieved": achieved,
+                "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
+                "traffic": None, "peak_source": pk["src"], "launches_timed": g_n,
+                "gemm_share_of_step": g_ms / 3 / (ms / a.steps),
+                "step_vit_fwd_frac_of_peak": B * FLOP_VIT_P0 / (ms / a.steps * 1e-3) / 1e12 / pk["tflops"]}
+
+    # pool-scale sim kernel (HBM bound): N = 2^20 rows against C=100 prototypes, timed alone
+    roofline_sim = None
+    if rank == 0:
+        Np, Cp = 1 << 20, 100
+        F = torch.nn.functional.normalize(torch.randn(Np, 512, device=dev), dim=1).half()
+        T = torch.nn.functional.normalize(torch.randn(Cp, 512, device=dev), dim=1).half()
+        for _ in range(3):
+            eng.sim_softmax_argmax(F, T, 100.0)
+        ctx.profile_begin()
+        for _ in range(10):
+            eng.sim_softmax_argmax(F, T, 100.0)
+        (_, _, _), (n1, ms1, by1) = ctx.profile_end()
+        gbs = by1 / (ms1 * 1e-3) / 1e9
+        roofline_sim = {"bound": "hbm", "kernel": "sim_softmax_argmax_kernel",
+                        "workload": f"pool N={Np}, C={Cp}, fp16 features (1 GiB > L2)", "achieved": gbs,
+                        "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"], "traffic": None,
+                        "launches_timed": n1, "images_per_s": Np * n1 / (ms1 * 1e-3)}
+        del F, T
+
+    # ---- end-to-end arm: pinned host → device every step, loss + predictions read back ---------
+    copy_stream = torch.cuda.Stream(device=dev)
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    main = torch.cuda.current_stream()
+
+    def prefetch(i):
+        b = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[b])
+            dev_img[b].copy_(host[b], non_blocking=True)
+            dev_lab[b].copy_(host_labels[b], non_blocking=True)
+            copied[b].record(copy_stream)
+
+    def e2e_step(i):
+        b = i % 2
+        prefetch(i + 1)               # next batch streams in while this one computes
+        main.wait_event(copied[b])
+        loss = step(dev_img[b], dev_lab[b])
+        consumed[b].record(main)
+        out_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+        out_pred.copy_(state["pred"], non_blocking=True)
+        main.synchronize()            # the caller reads loss / predictions every step
+
+    for b in range(2):
+        consumed[b].record(main)
+    prefetch(0)
+    for i in range(a.warmup):
+        e2e_step(i)
+    ms_e2e, _ = timed(lambda i: e2e_step(i + a.warmup), a.steps)
+    e2e_value = a.steps * B * world / (ms_e2e / 1e3)
+    h2d = B * 3 * 224 * 224 * 4 + B * 8
+    d2h = 4 + B * 4
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f16 (fp32 accumulate)",
+                "data": "synthetic",
+                "config": {"workload": workload_name(a, B), "weights": "random-init ViT-B/32 (seed 1234)",
+                           "l2_policy": "inputs larger than L2 (616 MB image batch per step)",
+                           "parallelism": f"dp{world}: image batch and pool sharded, prefix-grad all-reduce, "
+                                          f"ordered leaderboard hand-off" if world > 1 else "single GPU",
+                           "text_positions": "positions after EOT skipped (exact under the causal mask)"},
+                "clocks": clk.summary(), "gpu_launches": launches,
+                "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / a.steps,
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "roofline": roofline, "roofline_sim": roofline_sim}
+        if world == 1 and not a.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_arm(a, 1000, 1, budget_s=15.0)[0]
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.impl == "reference":
+        run_reference(a, rank)
+        return
+    if world != a.gpus:
+        if a.gpus == 1 and world == 1:
+            pass
+        else:
+            raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run "
+                             f"--nproc-per-node {a.gpus}")
+    run_b200(a, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()
