@@ -24,6 +24,53 @@ import numpy as np
 ALL_UNLABELED_K = 10000000  # utils/clip_pseudolabels.py:27 — "label every image with its argmax"
 
 
+class Boards:
+    """Resumable form of the same state machine: feed() consecutive index ranges in order (what a
+    shard does after receiving the state from the shard before it)."""
+
+    def __init__(self, c: int, k: int, class_ids: Sequence[int] = None):
+        self.c, self.k = c, k
+        self.class_ids = list(range(c)) if class_ids is None else list(class_ids)
+        self.boards = {}
+        for j in range(c):                                  # dict semantics of :49-51
+            self.boards[self.class_ids[j]] = []
+
+    def feed(self, probs: np.ndarray, pred: Sequence[int], paths: Sequence, idx0: int = 0):
+        """probs/pred: rows of this range; paths[i] tie-break key of GLOBAL image i."""
+        k, boards, cid = self.k, self.boards, self.class_ids
+
+        def key(t):  # sorted(..., reverse=True) on (prob, path) tuples
+            return (t[0], t[1])
+
+        for r in range(probs.shape[0]):
+            i = idx0 + r
+            row = probs[r]
+            j_star = int(pred[r])
+            own = boards[cid[j_star]]
+            p = row[j_star]
+            if len(own) < k:                                   # :73-74
+                own.append((p, paths[i], i))
+            elif own[-1][0] < p:                               # :75-82
+                boards[cid[j_star]] = sorted(own + [(p, paths[i], i)], key=key, reverse=True)[:k]
+            else:                                              # :83-101 (order over j is immaterial)
+                for j in range(self.c):
+                    if j == j_star:
+                        continue
+                    b = boards[cid[j]]
+                    if len(b) < k:
+                        b.append((row[j], paths[i], i))
+                    elif b[-1][0] < row[j]:
+                        boards[cid[j]] = sorted(b + [(row[j], paths[i], i)], key=key, reverse=True)[:k]
+        return self
+
+    def result(self) -> Tuple[List[int], List[int]]:
+        out_idx, out_lab = [], []
+        for cid, b in self.boards.items():                     # :103-109
+            out_idx += [t[2] for t in b]
+            out_lab += [cid for _ in b]
+        return out_idx, out_lab
+
+
 def leaderboard(probs: np.ndarray, pred: Sequence[int], k: int, paths: Sequence,
                 class_ids: Sequence[int] = None) -> Tuple[List[int], List[int]]:
     """Returns (image indices, labels) in the order the reference rebuilds the dataset
@@ -34,39 +81,7 @@ def leaderboard(probs: np.ndarray, pred: Sequence[int], k: int, paths: Sequence,
         class_ids = list(range(c))
     if k == ALL_UNLABELED_K:  # :27-44
         return list(range(n)), [class_ids[int(pred[i])] for i in range(n)]
-    # dict semantics: duplicate class ids collapse onto one board (:49-51)
-    boards = {}
-    for j in range(c):
-        boards[class_ids[j]] = []
-
-    def key(t):  # sorted(..., reverse=True) on (prob, path) tuples
-        return (t[0], t[1])
-
-    for i in range(n):
-        row = probs[i]
-        j_star = int(pred[i])
-        own = boards[class_ids[j_star]]
-        p = row[j_star]
-        if len(own) < k:                                   # :73-74
-            own.append((p, paths[i], i))
-        elif own[-1][0] < p:                               # :75-82
-            boards[class_ids[j_star]] = sorted(own + [(p, paths[i], i)], key=key,
-                                               reverse=True)[:k]
-        else:                                              # :83-101 (order over j is immaterial)
-            for j in range(c):
-                if j == j_star:
-                    continue
-                b = boards[class_ids[j]]
-                if len(b) < k:
-                    b.append((row[j], paths[i], i))
-                elif b[-1][0] < row[j]:
-                    boards[class_ids[j]] = sorted(b + [(row[j], paths[i], i)], key=key,
-                                                  reverse=True)[:k]
-    out_idx, out_lab = [], []
-    for cid, b in boards.items():                          # :103-109
-        out_idx += [t[2] for t in b]
-        out_lab += [cid for _ in b]
-    return out_idx, out_lab
+    return Boards(c, k, class_ids).feed(probs, pred, paths).result()
 
 
 def softmax_argmax(feat: np.ndarray, proto: np.ndarray, scale: float, dtype=np.float32):
