@@ -40,18 +40,29 @@ __device__ __forceinline__ void stage_qkv(const __half* __restrict__ qkv, int L,
   constexpr int Lp = NT * 8;
   constexpr int ldv = Lp + 8;
   const size_t ld = (size_t)3 * D;
-  for (int i = threadIdx.x; i < Lp * 8; i += blockDim.x) {
+  // all global loads of the tile are issued before the first shared-memory store (128 threads, one
+  // 16-byte chunk of Q, K and V each per step): the tile arrives in one round trip instead of kIt
+  constexpr int kIt = (Lp * 8) / 128;
+  uint4 q[kIt], k[kIt], v[kIt];
+#pragma unroll
+  for (int it = 0; it < kIt; ++it) {
+    const int i = it * 128 + threadIdx.x;
     const int r = i >> 3, ch = i & 7;
-    uint4 q = make_uint4(0, 0, 0, 0), k = q, v = q;
+    q[it] = k[it] = v[it] = make_uint4(0, 0, 0, 0);
     if (r < L) {
       const __half* src = qkv + ((size_t)b * L + r) * ld + h * kDh + ch * 8;
-      q = *reinterpret_cast<const uint4*>(src);
-      k = *reinterpret_cast<const uint4*>(src + D);
-      v = *reinterpret_cast<const uint4*>(src + 2 * D);
+      q[it] = *reinterpret_cast<const uint4*>(src);
+      k[it] = *reinterpret_cast<const uint4*>(src + D);
+      v[it] = *reinterpret_cast<const uint4*>(src + 2 * D);
     }
-    *reinterpret_cast<uint4*>(Qs + r * kQKld + ch * 8) = q;
-    *reinterpret_cast<uint4*>(Ks + r * kQKld + ch * 8) = k;
-    const __half* vh = reinterpret_cast<const __half*>(&v);
+  }
+#pragma unroll
+  for (int it = 0; it < kIt; ++it) {
+    const int i = it * 128 + threadIdx.x;
+    const int r = i >> 3, ch = i & 7;
+    *reinterpret_cast<uint4*>(Qs + r * kQKld + ch * 8) = q[it];
+    *reinterpret_cast<uint4*>(Ks + r * kQKld + ch * 8) = k[it];
+    const __half* vh = reinterpret_cast<const __half*>(&v[it]);
 #pragma unroll
     for (int e = 0; e < 8; ++e) Vt[(ch * 8 + e) * ldv + r] = vh[e];
   }

@@ -190,13 +190,14 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 __device__ __forceinline__ float quick_gelu(float x) {
-  // x * sigmoid(1.702 x)   (openai/CLIP QuickGELU)
-  return x / (1.0f + __expf(-1.702f * x));
+  // x * sigmoid(1.702 x)   (openai/CLIP QuickGELU); ex2.approx + rcp.approx: ≈1e-7 relative, far
+  // below the fp16 rounding of the stored activation, and 5 instructions instead of a full division
+  return __fdividef(x, 1.0f + __expf(-1.702f * x));
 }
 
 __device__ __forceinline__ float quick_gelu_grad(float x) {
   // d/dx [x·σ(1.702x)] = σ + 1.702·x·σ·(1−σ)
-  const float s = 1.0f / (1.0f + __expf(-1.702f * x));
+  const float s = __fdividef(1.0f, 1.0f + __expf(-1.702f * x));
   return s + 1.702f * x * s * (1.0f - s);
 }
 

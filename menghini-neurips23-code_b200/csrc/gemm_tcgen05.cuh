@@ -2,12 +2,13 @@
 //
 //   out[M,N] = epilogue( A[M,K] · W[N,K]ᵀ )        A, W fp16 K-major; fp32 accumulate in TMEM
 //
-// Roles (one CTA per SM, 256 threads):
+// Roles (one CTA per SM, 384 threads):
 //   warp 0   TMA producer   – cp.async.bulk.tensor (128B swizzle) into a kStages ring
 //   warp 1   MMA issuer     – one elected lane issues tcgen05.mma (128×BN×16), commits to mbarriers
 //   warp 2   TMEM allocator – 2×BN fp32 columns (double-buffered accumulator)
-//   warps 4-7 epilogue      – tcgen05.ld (one accumulator row per thread) → bias / QuickGELU /
-//                             residual / fp32|fp16 store, overlapped with the next tile's MMAs
+//   warps 4-11 epilogue     – tcgen05.ld (one accumulator row per thread, two warps per TMEM lane
+//                             quadrant) → bias / QuickGELU / residual / fp32|fp16 store, overlapped
+//                             with the next tile's MMAs
 //
 // This is the contraction behind every nn.Linear / conv1 / projection on the CLIP towers
 // (reference call sites: third-party clip.model.ResidualAttentionBlock via
@@ -20,7 +21,7 @@ namespace gb {
 constexpr int kBM = 128;   // rows per tile  (UMMA M)
 constexpr int kBK = 64;    // fp16 elements per k-block = one 128 B swizzle atom
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;  // TMA, MMA, TMEM-alloc, idle + 8 epilogue warps
 
 struct GemmParams {
   int M, N, K;
@@ -84,7 +85,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], 8);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -144,25 +145,46 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    // ===================== epilogue (8 warps) =====================
+    // TMEM lane quadrant q = warp % 4 (hardware rule); the two warps of a quadrant split the BN
+    // columns.  The operand that has to come from global memory (residual, or the saved
+    // pre-activation for act 2) is prefetched one 32-column chunk ahead — the first chunk before the
+    // accumulator is even ready — so its latency hides behind the TMEM read-out of the previous one.
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    constexpr int kChunks = BN / 64;  // 32-column chunks per warp
+    const __half* pre_base = (p.act == 2) ? p.aux : p.resid;
+    const int pre_ld = (p.act == 2) ? p.ldo : p.ldr;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int m0 = (tile / n_tiles) * kBM;
-      const int n0 = (tile % n_tiles) * BN;
+      const int n0 = (tile % n_tiles) * BN + half * (BN / 2);
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
+      const bool has_pre = pre_base != nullptr && row_ok;
+      uint4 pre[4], pre_next[4];
+      if (has_pre) {
+        const uint4* r4 = reinterpret_cast<const uint4*>(pre_base + (size_t)row * pre_ld + n0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pre[j] = r4[j];
+      }
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
+      const uint32_t taddr =
+          tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + half * (BN / 2);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < kChunks; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
-        tmem_ld_wait();
         const int col0 = n0 + c * 32;
+        if (has_pre && c + 1 < kChunks) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(pre_base + (size_t)row * pre_ld + col0 + 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pre_next[j] = r4[j];
+        }
+        tmem_ld_wait();
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -170,8 +192,8 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(b4 + j);
-            f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+            const float4 bb = __ldg(b4 + j);
+            f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
           }
         }
         if (p.act == 1) {
@@ -189,12 +211,10 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
-        } else if (p.act == 2 && row_ok) {
-          const uint4* a4 = reinterpret_cast<const uint4*>(p.aux + (size_t)row * p.ldo + col0);
+        } else if (p.act == 2 && has_pre) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint4 r = a4[j];
-            const __half2* h = reinterpret_cast<const __half2*>(&r);
+            const __half2* h = reinterpret_cast<const __half2*>(&pre[j]);
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               const float2 x = __half22float2(h[t]);
@@ -204,12 +224,10 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           }
         }
         if (row_ok) {
-          if (p.resid != nullptr) {
-            const uint4* r4 = reinterpret_cast<const uint4*>(p.resid + (size_t)row * p.ldr + col0);
+          if (p.act != 2 && has_pre) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint4 r = r4[j];
-              const __half2* h = reinterpret_cast<const __half2*>(&r);
+              const __half2* h = reinterpret_cast<const __half2*>(&pre[j]);
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
                 const float2 rf = __half22float2(h[t]);
@@ -238,6 +256,8 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
             }
           }
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pre[j] = pre_next[j];
       }
       tc_fence_before();
       __syncwarp();

@@ -9,6 +9,7 @@ forwards of models/clip_encoders.py:43-90,123-194 and autograd w.r.t. the prompt
 from __future__ import annotations
 
 import ctypes
+import weakref
 from typing import Optional
 
 import torch
@@ -42,8 +43,9 @@ class Engine:
         self._keep = []  # device tensors referenced by the C-side tables
         sd = state_dict
         with torch.cuda.device(self.device):
-            self._pack_vit(sd)
-            self._pack_text(sd)
+            self._vw = self._pack_vit(sd)
+            self._tw = self._pack_text(sd)
+        self._bind(force=True)
         ls = sd["logit_scale"]
         self.logit_scale_exp = float(torch.as_tensor(ls).float().exp().item())
 
@@ -98,7 +100,7 @@ class Engine:
         w.proj = ptr(proj)
         blocks = self._blocks(sd, "visual.transformer.", V_LAYERS)
         w.blocks = ctypes.cast(blocks, ctypes.POINTER(BlockWeights))
-        self.ctx.check(self.lib.gb_vit_set_weights(self.ctx.h, ctypes.byref(w)), "gb_vit_set_weights")
+        return w
 
     def _pack_text(self, sd):
         w = TextWeights()
@@ -112,7 +114,16 @@ class Engine:
         w.proj = ptr(proj)
         blocks = self._blocks(sd, "transformer.", T_LAYERS)
         w.blocks = ctypes.cast(blocks, ctypes.POINTER(BlockWeights))
-        self.ctx.check(self.lib.gb_text_set_weights(self.ctx.h, ctypes.byref(w)), "gb_text_set_weights")
+        return w
+
+    def _bind(self, force=False):
+        """A gb_ctx holds ONE weight table per tower; several Engines may share the device's ctx, so
+        each call makes sure the table currently bound is this engine's (host-side struct copy)."""
+        bound = getattr(self.ctx, "_bound_engine", None)
+        if force or bound is None or bound() is not self:
+            self.ctx.check(self.lib.gb_vit_set_weights(self.ctx.h, ctypes.byref(self._vw)), "gb_vit_set_weights")
+            self.ctx.check(self.lib.gb_text_set_weights(self.ctx.h, ctypes.byref(self._tw)), "gb_text_set_weights")
+            self.ctx._bound_engine = weakref.ref(self)
 
     # ---- towers -------------------------------------------------------------------------------
     def tape_bytes(self, samples, L, D, layers=12) -> int:
@@ -139,6 +150,7 @@ class Engine:
         tp = None
         if tape:
             tp = torch.empty(self.tape_bytes(B, 50 + P, V_WIDTH), device=self.device, dtype=torch.uint8)
+        self._bind()
         rc = self.lib.gb_vit_forward(self.ctx.h, ptr(img), int(img.dtype == torch.float32),
                                      ptr(prefix) if P else None, B, P, ptr(feat), ptr(featn), ptr(tp),
                                      stream_ptr())
@@ -150,6 +162,7 @@ class Engine:
         dfeat = dfeat.detach().to(self.device, torch.float32).contiguous()
         B, P = dfeat.shape[0], prefix.shape[0]
         dprefix = torch.empty(P, V_WIDTH, device=self.device, dtype=torch.float32)
+        self._bind()
         rc = self.lib.gb_vit_backward_prefix(self.ctx.h, ptr(dfeat), ptr(prefix), B, P, ptr(tape),
                                              ptr(dprefix), stream_ptr())
         self.ctx.check(rc, "gb_vit_backward_prefix")
@@ -176,6 +189,7 @@ class Engine:
         tp = None
         if tape:
             tp = torch.empty(self.tape_bytes(C, Lt, T_WIDTH), device=self.device, dtype=torch.uint8)
+        self._bind()
         rc = self.lib.gb_text_forward(self.ctx.h, ptr(ids_d), ids_d.stride(0), ptr(eot_d),
                                       ptr(prefix) if P else None, C, P, Lt, ptr(feat), ptr(featn),
                                       ptr(tp), stream_ptr())
@@ -187,6 +201,7 @@ class Engine:
         dfeat = dfeat.detach().to(self.device, torch.float32).contiguous()
         C = dfeat.shape[0]
         dprefix = torch.empty(P, T_WIDTH, device=self.device, dtype=torch.float32)
+        self._bind()
         rc = self.lib.gb_text_backward_prefix(self.ctx.h, ptr(dfeat), ptr(eot_d), C, P, Lt, ptr(tape),
                                               ptr(dprefix), stream_ptr())
         self.ctx.check(rc, "gb_text_backward_prefix")
