@@ -33,12 +33,13 @@ __device__ __forceinline__ uint32_t lds32(const __half* p) {
   return *reinterpret_cast<const uint32_t*>(p);
 }
 
-// Stage Q, K (row-major, padded) and Vᵀ of one (sample, head) in shared memory; rows ≥ L are zero.
+// Stage Q, K, V (row-major, rows padded to 72 halves) of one (sample, head) in shared memory; rows ≥ L
+// are zero.  The transposed operands the PV product needs come from ldmatrix.trans, not from a
+// transposed copy (2-byte scattered stores were 8-way bank conflicted).
 template <int NT>
 __device__ __forceinline__ void stage_qkv(const __half* __restrict__ qkv, int L, int D, int b,
-                                          int h, __half* Qs, __half* Ks, __half* Vt) {
+                                          int h, __half* Qs, __half* Ks, __half* Vs) {
   constexpr int Lp = NT * 8;
-  constexpr int ldv = Lp + 8;
   const size_t ld = (size_t)3 * D;
   // all global loads of the tile are issued before the first shared-memory store (128 threads, one
   // 16-byte chunk of Q, K and V each per step): the tile arrives in one round trip instead of kIt
@@ -62,10 +63,17 @@ __device__ __forceinline__ void stage_qkv(const __half* __restrict__ qkv, int L,
     const int r = i >> 3, ch = i & 7;
     *reinterpret_cast<uint4*>(Qs + r * kQKld + ch * 8) = q[it];
     *reinterpret_cast<uint4*>(Ks + r * kQKld + ch * 8) = k[it];
-    const __half* vh = reinterpret_cast<const __half*>(&v[it]);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) Vt[(ch * 8 + e) * ldv + r] = vh[e];
+    *reinterpret_cast<uint4*>(Vs + r * kQKld + ch * 8) = v[it];
   }
+}
+
+// Four transposed 8x8 b16 tiles in one instruction; lane l supplies the row address of row l%8 of
+// tile l/8.  With .trans, thread (g = lane/4, t = lane%4) receives {M[2t][g], M[2t+1][g]} of each
+// tile — exactly the "col" B fragment of mma.m16n8k16 when M is stored [k][n] row-major.
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const __half* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
 }
 
 // S = scale·Q·Kᵀ with masking, then row soft-max, all in the m16n8 accumulator layout:
@@ -135,13 +143,12 @@ __global__ void __launch_bounds__(128)
 attn_fwd_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int L, int D,
                 int causal) {
   constexpr int Lp = NT * 8;  // multiple of 16
-  constexpr int ldv = Lp + 8;
   extern __shared__ __align__(16) uint8_t attn_smem[];
   __half* Qs = reinterpret_cast<__half*>(attn_smem);
   __half* Ks = Qs + Lp * kQKld;
-  __half* Vt = Ks + Lp * kQKld;
+  __half* Vs = Ks + Lp * kQKld;
   const int h = blockIdx.x, b = blockIdx.y;
-  stage_qkv<NT>(qkv, L, D, b, h, Qs, Ks, Vt);
+  stage_qkv<NT>(qkv, L, D, b, h, Qs, Ks, Vs);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -160,23 +167,31 @@ attn_fwd_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int L,
       a[1] = pack_h2(s[2 * kt][2] * inv1, s[2 * kt][3] * inv1);
       a[2] = pack_h2(s[2 * kt + 1][0] * inv0, s[2 * kt + 1][1] * inv0);
       a[3] = pack_h2(s[2 * kt + 1][2] * inv1, s[2 * kt + 1][3] * inv1);
+      // B[k = key][n = dh] = V[key][dh]: tiles (keys 0-7 | 8-15) × (dh block dn | dn+1)
+      const __half* vrow = Vs + (kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * kQKld + (lane >> 4) * 8;
 #pragma unroll
-      for (int dn = 0; dn < 8; ++dn) {
-        const uint32_t b0 = lds32(Vt + (dn * 8 + g) * ldv + kt * 16 + 2 * t);
-        const uint32_t b1 = lds32(Vt + (dn * 8 + g) * ldv + kt * 16 + 8 + 2 * t);
-        mma16816(o[dn], a, b0, b1);
+      for (int dn = 0; dn < 8; dn += 2) {
+        uint32_t bf[4];
+        ldmatrix_x4_trans(bf, vrow + dn * 8);
+        mma16816(o[dn], a, bf[0], bf[1]);
+        mma16816(o[dn + 1], a, bf[2], bf[3]);
       }
     }
-    const int ra = r0 + g, rb = r0 + g + 8;
+    // stage the 16x64 output tile in this warp's own (no longer needed) Q rows, then write whole
+    // 128-byte rows
+    __syncwarp();
 #pragma unroll
     for (int dn = 0; dn < 8; ++dn) {
-      const int col = h * kDh + dn * 8 + 2 * t;
-      if (ra < L)
-        *reinterpret_cast<__half2*>(out + ((size_t)b * L + ra) * D + col) =
-            __floats2half2_rn(o[dn][0], o[dn][1]);
-      if (rb < L)
-        *reinterpret_cast<__half2*>(out + ((size_t)b * L + rb) * D + col) =
-            __floats2half2_rn(o[dn][2], o[dn][3]);
+      *reinterpret_cast<uint32_t*>(Qs + (r0 + g) * kQKld + dn * 8 + 2 * t) = pack_h2(o[dn][0], o[dn][1]);
+      *reinterpret_cast<uint32_t*>(Qs + (r0 + g + 8) * kQKld + dn * 8 + 2 * t) = pack_h2(o[dn][2], o[dn][3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + i * 4 + (lane >> 3), ch = lane & 7;
+      if (r < L)
+        *reinterpret_cast<uint4*>(out + ((size_t)b * L + r) * D + h * kDh + ch * 8) =
+            *reinterpret_cast<const uint4*>(Qs + r * kQKld + ch * 8);
     }
   }
 }
@@ -379,7 +394,7 @@ attn_bwd_kernel(const __half* __restrict__ qkv, const __half* __restrict__ dout,
 template <int NT>
 size_t fwd_smem() {
   constexpr int Lp = NT * 8;
-  return (size_t)(2 * Lp * kQKld + kDh * (Lp + 8)) * 2;
+  return (size_t)(3 * Lp * kQKld) * 2;
 }
 template <int NT>
 size_t bwd_smem() {

@@ -26,7 +26,7 @@ constexpr int kSimBM = 128;
 constexpr int kSimK = 512;
 constexpr int kSimKBlocks = kSimK / 64;  // 8
 constexpr int kSimStages = 5;
-constexpr int kSimThreads = 256;
+constexpr int kSimThreads = 384;  // TMA, MMA, TMEM-alloc, idle + 2 epilogue groups of 4 warps
 constexpr int kSimABytes = kSimBM * 64 * 2;  // 16 KB per stage
 
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
@@ -40,13 +40,16 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
       : "memory");
 }
 
-// logit and probability of one accumulator element — explicit rounding steps (no FMA contraction) so
-// that every pass of the epilogue, and every launch mode, produces identical bits.
-__device__ __forceinline__ float sim_logit(uint32_t acc, float scale) {
-  return __fmul_rn(__uint_as_float(acc), scale);
+// logit (in log2 units) and un-normalised probability of one accumulator element — explicit rounding
+// steps (no FMA contraction) so that every pass of the epilogue, and every launch mode, produces
+// identical bits:  l = rn(acc·s2),  e = ex2.approx.ftz(rn(l − max))  with s2 = rn(scale·log2 e).
+__device__ __forceinline__ float sim_logit(uint32_t acc, float scale2) {
+  return __fmul_rn(__uint_as_float(acc), scale2);
 }
-__device__ __forceinline__ float sim_exp(uint32_t acc, float scale, float mx) {
-  return __expf(__fsub_rn(sim_logit(acc, scale), mx));
+__device__ __forceinline__ float sim_exp(uint32_t acc, float scale2, float mx) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fsub_rn(sim_logit(acc, scale2), mx)));
+  return r;
 }
 
 struct SimParams {
@@ -55,7 +58,7 @@ struct SimParams {
   int BN;          // C rounded up to 16 (UMMA N)
   int tile_begin;  // first 128-row tile of this launch
   int tile_end;    // one past the last tile
-  float scale;     // logit_scale.exp()
+  float scale2;    // logit_scale.exp() · log2(e): logits are carried in log2 units
   int mode;        // 0: pred = argmax(probs) (clip_pseudolabels.py:63); 1: argmax(logits) (textual_fpl.py:228)
   int32_t* pred;   // [N]
   float* p_pred;   // [N]
@@ -159,92 +162,108 @@ sim_softmax_argmax_kernel(const __grid_constant__ CUtensorMap tmF,
       }
     }
   } else if (warp >= 4) {
+    // ===================== epilogue: two groups of 4 warps, one per accumulator stage ============
+    // Group g = (warp-4)/4 owns accumulator stage g and therefore every second tile of this CTA, so
+    // a tile's soft-max may take two MMA-tile times.  Within a group, warp q reads TMEM lane quadrant
+    // q; thread = image row.  Logits are kept in log2 units: l = rn(acc·s2), s2 = scale·log2(e).
     const int q = warp & 3;
+    const int grp = (warp - 4) >> 2;
     const int C = p.C;
     const int chunks = p.BN >> 4;
+    const bool want_rows = p.probs != nullptr;
+    const bool filt = p.lb != nullptr;
     int it = 0;
     for (int tile = p.tile_begin + blockIdx.x; tile < p.tile_end; tile += gridDim.x, ++it) {
-      const int as = it & 1;
+      if ((it & 1) != grp) continue;
+      const int n_mine = it >> 1;
       const int row = tile * kSimBM + q * 32 + lane;
       const bool row_ok = row < p.N;
-      mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+      mbar_wait(&tfull_bar[grp], n_mine & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 128;
-      // pass 1: row max / first arg-max of the logits
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + grp * 128;
+      uint32_t v[2][16];
+      // ---- pass 1: row max and its first index ----
       float mx = -INFINITY;
       int am = 0;
-      for (int c = 0; c < chunks; ++c) {
-        uint32_t v[16];
-        tmem_ld_32x16(taddr + c * 16, v);
-        tmem_ld_wait();
+      tmem_ld_32x16(taddr, v[0]);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int col = c * 16 + j;
-          const float x = sim_logit(v[j], p.scale);
-          if (col < C && x > mx) { mx = x; am = col; }
-        }
-      }
-      // pass 2: soft-max denominator
-      float sum = 0.f;
-      for (int c = 0; c < chunks; ++c) {
-        uint32_t v[16];
-        tmem_ld_32x16(taddr + c * 16, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int col = c * 16 + j;
-          if (col < C) sum += sim_exp(v[j], p.scale, mx);
-        }
-      }
-      const float inv = __frcp_rn(sum);
-      const float pmax = inv;  // exp(0) · inv
-      int pred = am;
-      bool survive = false;
-      const bool want_rows = p.probs != nullptr;
-      const bool filt = p.lb != nullptr;
-      if (want_rows || filt || p.mode == 0) {
-        // pass 3: probabilities → optional row store, arg-max over probs, leaderboard pre-filter
-        int first_pmax = -1;
-        for (int c = 0; c < chunks; ++c) {
-          uint32_t v[16];
-          tmem_ld_32x16(taddr + c * 16, v);
+      for (int c = 0; c < 8; ++c) {
+        if (c < chunks) {
           tmem_ld_wait();
+          if (c + 1 < chunks) tmem_ld_32x16(taddr + (c + 1) * 16, v[(c + 1) & 1]);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = c * 16 + j;
+            const float x = sim_logit(v[c & 1][j], p.scale2);
+            if (col < C && x > mx) { mx = x; am = col; }
+          }
+        }
+      }
+      // ---- pass 2: Σ 2^(l−max); first index whose probability equals the maximum; loose filter ----
+      // p_j = rn(e_j·inv) equals p_max = inv only for e_j = 1 or e_j = 1−2^-24 (any smaller e_j is
+      // more than half an ulp away), so arg-max over the PROBABILITIES (clip_pseudolabels.py:63)
+      // needs just the first column of each of those two values.
+      float sum = 0.f;
+      int first_one = am, first_near = 0x7fffffff;
+      bool loose = false;
+      tmem_ld_32x16(taddr, v[0]);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (c < chunks) {
+          tmem_ld_wait();
+          if (c + 1 < chunks) tmem_ld_32x16(taddr + (c + 1) * 16, v[(c + 1) & 1]);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int col = c * 16 + j;
             if (col < C) {
-              const float pj = __fmul_rn(sim_exp(v[j], p.scale, mx), inv);
-              if (first_pmax < 0 && pj == pmax) first_pmax = col;
-              if (filt && pj > s_lb[col]) survive = true;
-              if (want_rows && row_ok) p.probs[(size_t)row * C + col] = pj;
+              const float e = sim_exp(v[c & 1][j], p.scale2, mx);
+              sum += e;
+              if (p.mode == 0) {
+                if (e == 1.0f) first_one = min(first_one, col);
+                if (__float_as_uint(e) == 0x3F7FFFFFu) first_near = min(first_near, col);
+              }
+              // p_j ≤ e_j (Σ ≥ 1): rows with no e_j above its board bound can never be admitted
+              if (filt && e * 1.000001f > s_lb[col]) loose = true;
             }
           }
         }
-        if (p.mode == 0 && first_pmax >= 0) pred = first_pmax;
       }
-      // the accumulator may be recycled only after the LAST read; the candidate-row pass below
-      // re-reads it, so release after that
-      survive = survive && row_ok;
-      if (filt) {
-        const uint32_t ballot = __ballot_sync(0xffffffffu, survive);
-        if (lane == 0) p.flags[(tile * kSimBM + q * 32) >> 5] = ballot;
-        // tcgen05.ld is warp-collective: every lane re-reads the accumulator, only the flagged
-        // rows store their probabilities
-        if (!want_rows && ballot != 0) {
-          float* dst = p.cand_rows + (size_t)(row - p.tile_begin * kSimBM) * C;
-          for (int c = 0; c < chunks; ++c) {
-            uint32_t v[16];
-            tmem_ld_32x16(taddr + c * 16, v);
-            tmem_ld_wait();
-            if (survive) {
+      const float inv = __frcp_rn(sum);
+      const float pmax = inv;  // rn(1·inv)
+      int pred = am;
+      if (p.mode == 0) {
+        pred = first_one;
+        if (first_near < pred && __fmul_rn(__uint_as_float(0x3F7FFFFFu), inv) == inv) pred = first_near;
+      }
+      // ---- pass 3 (only where needed): probabilities → row store / exact pre-filter ----
+      loose = loose && row_ok;
+      const uint32_t loose_mask = __ballot_sync(0xffffffffu, loose);
+      bool survive = false;
+      if (want_rows || loose_mask != 0) {
+        float* dst = want_rows ? p.probs + (size_t)row * C
+                               : p.cand_rows + (size_t)(row - p.tile_begin * kSimBM) * C;
+        const bool store = row_ok && (want_rows || loose);
+        tmem_ld_32x16(taddr, v[0]);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int col = c * 16 + j;
-                if (col < C) dst[col] = __fmul_rn(sim_exp(v[j], p.scale, mx), inv);
+        for (int c = 0; c < 8; ++c) {
+          if (c < chunks) {
+            tmem_ld_wait();
+            if (c + 1 < chunks) tmem_ld_32x16(taddr + (c + 1) * 16, v[(c + 1) & 1]);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int col = c * 16 + j;
+              if (col < C) {
+                const float pj = __fmul_rn(sim_exp(v[c & 1][j], p.scale2, mx), inv);
+                if (filt && pj > s_lb[col]) survive = true;
+                if (store) dst[col] = pj;
               }
             }
           }
         }
+      }
+      if (filt) {
+        const uint32_t ballot = __ballot_sync(0xffffffffu, survive && row_ok);
+        if (lane == 0) p.flags[(tile * kSimBM + q * 32) >> 5] = ballot;
       }
       if (row_ok) {
         p.pred[row] = pred;
@@ -252,7 +271,7 @@ sim_softmax_argmax_kernel(const __grid_constant__ CUtensorMap tmF,
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) mbar_arrive(&tempty_bar[grp]);
     }
   }
 
@@ -614,7 +633,7 @@ int launch_sim(gb_ctx* c, const void* F, const void* T, float scale, int N, int 
   p.C = C; p.BN = BN;
   p.tile_begin = row_begin / kSimBM;
   p.tile_end = (p.N + kSimBM - 1) / kSimBM;
-  p.scale = scale; p.mode = mode;
+  p.scale2 = scale * 1.4426950408889634f; p.mode = mode;
   p.pred = pred; p.p_pred = p_pred; p.probs = probs;
   p.lb = lb; p.flags = flags; p.cand_rows = cand_rows;
   const int tiles = p.tile_end - p.tile_begin;
