@@ -1,4 +1,5 @@
 // Host launcher + C-ABI entry for the tcgen05 GEMM.
+#include <stdlib.h>
 #include "ctx.h"
 #include "gemm_tcgen05.cuh"
 
@@ -25,6 +26,27 @@ static int launch_gemm_bn(gb_ctx* c, const CUtensorMap& tmA, const CUtensorMap& 
   return GB_OK;
 }
 
+static int launch_gemm_2cta(gb_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                           const CUtensorMap& tmC, const GemmParams& p, cudaStream_t st) {
+  using Cfg = Gemm2Cfg;
+  static bool attr_set[16] = {false};
+  if (!attr_set[c->device & 15]) {
+    GB_CUDA(c, cudaFuncSetAttribute(gemm_f16_tcgen05_2cta_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set[c->device & 15] = true;
+  }
+  const int m_pairs = (p.M + 2 * kBM - 1) / (2 * kBM);
+  const int tiles = m_pairs * (p.N / Cfg::BN);
+  const int max_clusters = c->num_sms / 2;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  {
+    gb_prof_scope prof(c, st, 0, 2.0 * p.M * p.N * p.K);
+    gemm_f16_tcgen05_2cta_kernel<<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, tmC, p);
+  }
+  GB_LAUNCH_CHECK(c);
+  return GB_OK;
+}
+
 int gb_launch_gemm(gb_ctx* c, const void* A, int lda, const void* W, int ldw, const float* bias,
                    const void* resid, int ldr, void* out, int ldo, int M, int N, int K, int act,
                    int out_f32, cudaStream_t st, void* aux) {
@@ -42,7 +64,8 @@ int gb_launch_gemm(gb_ctx* c, const void* A, int lda, const void* W, int ldw, co
   // a row's arithmetic must not depend on how many other rows are in the batch (pseudolabels have to
   // be bit-identical however the pool is batched or sharded across GPUs).
   const bool wide = (N % 256 == 0);
-  const int BN = wide ? 256 : 128;
+  // wide tiles run on CTA pairs (each CTA stages half of the 256 W rows); otherwise one CTA, BN = 128
+  const int BN = 128;
   CUtensorMap tmA, tmB;
   int rc = gb_make_tmap_2d_f16(c, &tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, kBM);
   if (rc) return rc;
@@ -54,10 +77,18 @@ int gb_launch_gemm(gb_ctx* c, const void* A, int lda, const void* W, int ldw, co
   p.bias = bias;
   p.resid = reinterpret_cast<const __half*>(resid); p.ldr = ldr;
   p.act = act; p.out_f32 = out_f32;
+  if (getenv("GB_DEBUG_NOSTORE")) p.out_f32 = 2;  // experiment: skip the epilogue's global stores
   p.aux = reinterpret_cast<__half*>(aux);
   if (act == 2 && !aux) return gb_fail(c, GB_ERR_ARG, "gemm: act 2 needs aux");
   if (aux && (out_f32 || (reinterpret_cast<uintptr_t>(aux) & 15))) return gb_fail(c, GB_ERR_ARG, "gemm: aux needs fp16 output layout and 16-byte alignment");
-  return wide ? launch_gemm_bn<256>(c, tmA, tmB, p, st) : launch_gemm_bn<128>(c, tmA, tmB, p, st);
+  if (!wide) return launch_gemm_bn<128>(c, tmA, tmB, p, st);
+  // output tensor map for the TMA-store epilogue (fp16 outputs): 64-column x 32-row boxes
+  CUtensorMap tmC = tmA;
+  if (!out_f32) {
+    rc = gb_make_tmap_2d_f16(c, &tmC, out, (uint64_t)M, (uint64_t)N, (uint64_t)ldo, 32);
+    if (rc) return rc;
+  }
+  return launch_gemm_2cta(c, tmA, tmB, tmC, p, st);
 }
 
 extern "C" int gb_gemm_f16(gb_ctx* c, const void* A, int lda, const void* W, int ldw,

@@ -46,6 +46,120 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// Epilogue of one 128 x BN accumulator tile by the 8 epilogue warps of a CTA.  TMEM lane quadrant
+// q = warp % 4 (hardware rule); the two warps of a quadrant split the BN columns.  The operand that
+// has to come from global memory (residual, or the saved pre-activation for act 2) is prefetched one
+// 32-column chunk ahead — the first chunk before the accumulator is even ready — so its latency hides
+// behind the TMEM read-out of the previous one.  `wait_acc` blocks until the accumulator is complete.
+template <int BN, typename WaitAcc>
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t tmem_acc, int m0,
+                                                   int n_base, int warp, int lane,
+                                                   WaitAcc&& wait_acc) {
+  const int q = warp & 3;
+  const int half = (warp - 4) >> 2;
+  constexpr int kChunks = BN / 64;  // 32-column chunks per warp
+  const __half* pre_base = (p.act == 2) ? p.aux : p.resid;
+  const int pre_ld = (p.act == 2) ? p.ldo : p.ldr;
+  const int n0 = n_base + half * (BN / 2);
+  const int row = m0 + q * 32 + lane;
+  const bool row_ok = row < p.M;
+  const bool has_pre = pre_base != nullptr && row_ok;
+  uint4 pre[4], pre_next[4];
+  if (has_pre) {
+    const uint4* r4 = reinterpret_cast<const uint4*>(pre_base + (size_t)row * pre_ld + n0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pre[j] = r4[j];
+  }
+  wait_acc();
+  tc_fence_after();
+  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + half * (BN / 2);
+#pragma unroll 1
+  for (int c = 0; c < kChunks; ++c) {
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + c * 32, v);
+    const int col0 = n0 + c * 32;
+    if (has_pre && c + 1 < kChunks) {
+      const uint4* r4 = reinterpret_cast<const uint4*>(pre_base + (size_t)row * pre_ld + col0 + 32);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pre_next[j] = r4[j];
+    }
+    tmem_ld_wait();
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    if (p.bias != nullptr) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 bb = __ldg(b4 + j);
+        f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
+      }
+    }
+    if (p.act == 1) {
+      if (p.aux != nullptr && row_ok) {
+        uint4* a4 = reinterpret_cast<uint4*>(p.aux + (size_t)row * p.ldo + col0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 o;
+          __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            h[t] = __floats2half2_rn(f[8 * j + 2 * t], f[8 * j + 2 * t + 1]);
+          a4[j] = o;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
+    } else if (p.act == 2 && has_pre) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __half2* h = reinterpret_cast<const __half2*>(&pre[j]);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 x = __half22float2(h[t]);
+          f[8 * j + 2 * t] *= quick_gelu_grad(x.x);
+          f[8 * j + 2 * t + 1] *= quick_gelu_grad(x.y);
+        }
+      }
+    }
+    if (row_ok && p.out_f32 != 2) {
+      if (p.act != 2 && has_pre) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __half2* h = reinterpret_cast<const __half2*>(&pre[j]);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 rf = __half22float2(h[t]);
+            f[8 * j + 2 * t] += rf.x;
+            f[8 * j + 2 * t + 1] += rf.y;
+          }
+        }
+      }
+      if (p.out_f32) {
+        float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
+                                               (size_t)row * p.ldo + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          o4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+      } else {
+        uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) +
+                                             (size_t)row * p.ldo + col0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 o;
+          __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            h[t] = __floats2half2_rn(f[8 * j + 2 * t], f[8 * j + 2 * t + 1]);
+          o4[j] = o;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pre[j] = pre_next[j];
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -146,119 +260,14 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     }
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps) =====================
-    // TMEM lane quadrant q = warp % 4 (hardware rule); the two warps of a quadrant split the BN
-    // columns.  The operand that has to come from global memory (residual, or the saved
-    // pre-activation for act 2) is prefetched one 32-column chunk ahead — the first chunk before the
-    // accumulator is even ready — so its latency hides behind the TMEM read-out of the previous one.
-    const int q = warp & 3;
-    const int half = (warp - 4) >> 2;
-    constexpr int kChunks = BN / 64;  // 32-column chunks per warp
-    const __half* pre_base = (p.act == 2) ? p.aux : p.resid;
-    const int pre_ld = (p.act == 2) ? p.ldo : p.ldr;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int m0 = (tile / n_tiles) * kBM;
-      const int n0 = (tile % n_tiles) * BN + half * (BN / 2);
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      const bool has_pre = pre_base != nullptr && row_ok;
-      uint4 pre[4], pre_next[4];
-      if (has_pre) {
-        const uint4* r4 = reinterpret_cast<const uint4*>(pre_base + (size_t)row * pre_ld + n0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) pre[j] = r4[j];
-      }
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
-      const uint32_t taddr =
-          tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + half * (BN / 2);
-#pragma unroll 1
-      for (int c = 0; c < kChunks; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c * 32, v);
-        const int col0 = n0 + c * 32;
-        if (has_pre && c + 1 < kChunks) {
-          const uint4* r4 = reinterpret_cast<const uint4*>(pre_base + (size_t)row * pre_ld + col0 + 32);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) pre_next[j] = r4[j];
-        }
-        tmem_ld_wait();
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias != nullptr) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 bb = __ldg(b4 + j);
-            f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
-          }
-        }
-        if (p.act == 1) {
-          if (p.aux != nullptr && row_ok) {
-            uint4* a4 = reinterpret_cast<uint4*>(p.aux + (size_t)row * p.ldo + col0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              __half2* h = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-              for (int t = 0; t < 4; ++t)
-                h[t] = __floats2half2_rn(f[8 * j + 2 * t], f[8 * j + 2 * t + 1]);
-              a4[j] = o;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
-        } else if (p.act == 2 && has_pre) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const __half2* h = reinterpret_cast<const __half2*>(&pre[j]);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float2 x = __half22float2(h[t]);
-              f[8 * j + 2 * t] *= quick_gelu_grad(x.x);
-              f[8 * j + 2 * t + 1] *= quick_gelu_grad(x.y);
-            }
-          }
-        }
-        if (row_ok) {
-          if (p.act != 2 && has_pre) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const __half2* h = reinterpret_cast<const __half2*>(&pre[j]);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float2 rf = __half22float2(h[t]);
-                f[8 * j + 2 * t] += rf.x;
-                f[8 * j + 2 * t + 1] += rf.y;
-              }
-            }
-          }
-          if (p.out_f32) {
-            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) +
-                                                   (size_t)row * p.ldo + col0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              o4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          } else {
-            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) +
-                                                 (size_t)row * p.ldo + col0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              __half2* h = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-              for (int t = 0; t < 4; ++t)
-                h[t] = __floats2half2_rn(f[8 * j + 2 * t], f[8 * j + 2 * t + 1]);
-              o4[j] = o;
-            }
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) pre[j] = pre_next[j];
-      }
+      const int n0 = (tile % n_tiles) * BN;
+      gemm_epilogue_tile<BN>(p, tmem_base + as * BN, m0, n0, warp, lane,
+                             [&]() { mbar_wait(&tfull_bar[as], aphase); });
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
@@ -270,6 +279,277 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// Epilogue of one 128 x 256 accumulator tile with TMA stores (fp16 output).  Each of the 8 epilogue
+// warps owns 32 rows x 128 columns; it converts 64 columns at a time into a private 32 x 128-byte
+// shared-memory slab (128B-swizzled: quarter-warp accesses are conflict-free) and one lane hands the
+// slab to the TMA engine, which writes whole 128-byte lines and clips rows >= M.  Direct per-thread
+// stores (32 row-strided 16-byte pieces per instruction) were the bottleneck of every K=768 GEMM.
+// Two slabs per warp alternate, so a slab is rewritten only after the store issued two chunks
+// earlier has finished reading it.
+template <typename WaitAcc>
+__device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, const CUtensorMap* tmC,
+                                                       uint8_t* slabs, uint32_t tmem_acc, int m0,
+                                                       int n_base, int warp, int lane,
+                                                       WaitAcc&& wait_acc) {
+  constexpr int BN = 256;
+  const int q = warp & 3;
+  const int half = (warp - 4) >> 2;
+  const __half* pre_base = (p.act == 2) ? p.aux : p.resid;
+  const int pre_ld = (p.act == 2) ? p.ldo : p.ldr;
+  const int n0 = n_base + half * (BN / 2);
+  const int row0 = m0 + q * 32;
+  const int row = row0 + lane;
+  const bool row_ok = row < p.M;
+  const bool has_pre = pre_base != nullptr && row_ok;
+  uint4 pre[4], pre_next[4];
+  if (has_pre) {
+    const uint4* r4 = reinterpret_cast<const uint4*>(pre_base + (size_t)row * pre_ld + n0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pre[j] = r4[j];
+  }
+  wait_acc();
+  tc_fence_after();
+  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + half * (BN / 2);
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {  // 32-column chunks; two chunks fill one slab
+    uint32_t v[32];
+    tmem_ld_32x32(taddr + c * 32, v);
+    const int col0 = n0 + c * 32;
+    if (has_pre && c + 1 < 4) {
+      const uint4* r4 = reinterpret_cast<const uint4*>(pre_base + (size_t)row * pre_ld + col0 + 32);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pre_next[j] = r4[j];
+    }
+    uint8_t* slab = slabs + ((c >> 1) & 1) * 4096;
+    if ((c & 1) == 0) {
+      // the store that last used this slab (previous tile) must be done reading it
+      if (lane == 0) tma_store_wait_read<1>();
+      __syncwarp();
+    }
+    tmem_ld_wait();
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    if (p.bias != nullptr) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 bb = __ldg(b4 + j);
+        f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
+      }
+    }
+    if (p.act == 1) {
+      if (p.aux != nullptr && row_ok) {
+        uint4* a4 = reinterpret_cast<uint4*>(p.aux + (size_t)row * p.ldo + col0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 o;
+          __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            h[t] = __floats2half2_rn(f[8 * j + 2 * t], f[8 * j + 2 * t + 1]);
+          a4[j] = o;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
+    } else if (p.act == 2 && has_pre) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __half2* h = reinterpret_cast<const __half2*>(&pre[j]);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 x = __half22float2(h[t]);
+          f[8 * j + 2 * t] *= quick_gelu_grad(x.x);
+          f[8 * j + 2 * t + 1] *= quick_gelu_grad(x.y);
+        }
+      }
+    }
+    if (p.act != 2 && has_pre) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __half2* h = reinterpret_cast<const __half2*>(&pre[j]);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 rf = __half22float2(h[t]);
+          f[8 * j + 2 * t] += rf.x;
+          f[8 * j + 2 * t + 1] += rf.y;
+        }
+      }
+    }
+    // 64 bytes of this thread's row → 16-byte chunks 4·(c&1) … +3 of slab row `lane`
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 o;
+      __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(f[8 * j + 2 * t], f[8 * j + 2 * t + 1]);
+      const int chunk = (c & 1) * 4 + j;
+      *reinterpret_cast<uint4*>(slab + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = o;
+    }
+    if (c & 1) {
+      fence_proxy_async();  // generic-proxy writes → visible to the TMA engine
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmC, slab, n0 + (c >> 1) * 64, row0);
+        tma_store_commit();
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pre[j] = pre_next[j];
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2), N % 256 == 0: a 2-CTA cluster computes 256 x 256 output tiles.
+// CTA r of the pair stages rows [256·mp + 128·r, +128) of A and rows [n0 + 128·r, +128) of W per
+// k-block (32 KB per stage instead of 48 KB → 6 stages), both signalling the LEADER's full barrier;
+// the leader's single MMA thread issues 256x256x16 tcgen05.mma.cta_group::2 instructions whose
+// accumulator rows live in each CTA's own TMEM; commits are multicast to both CTAs' barriers; each
+// CTA's 8 epilogue warps drain their own 128 rows and release the accumulator on the leader.
+// -------------------------------------------------------------------------------------------------
+struct Gemm2Cfg {
+  static constexpr int BN = 256;
+  static constexpr int kStages = 5;
+  static constexpr int kSlabBytes = 8 * 2 * 4096;      // two 32x128 B output slabs per epilogue warp
+  static constexpr int kABytes = kBM * kBK * 2;        // 16 KB: this CTA's 128 rows of A
+  static constexpr int kBBytes = (BN / 2) * kBK * 2;   // 16 KB: this CTA's half of the W tile
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kSlabBytes + 1024 + 256;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
+                             const __grid_constant__ CUtensorMap tmB,
+                             const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+  using Cfg = Gemm2Cfg;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int BN = Cfg::BN;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+  uint8_t* smem_slabs = smem + kStages * Cfg::kStageBytes;  // 1024-aligned: stage bytes are 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_slabs + Cfg::kSlabBytes);
+  uint64_t* full_bar = bars;                      // [kStages]  (used on the leader)
+  uint64_t* empty_bar = bars + kStages;           // [kStages]  (each CTA waits on its own)
+  uint64_t* tfull_bar = bars + 2 * kStages;       // [2]        (each CTA waits on its own)
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]        (used on the leader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  const int m_pairs = (p.M + 2 * kBM - 1) / (2 * kBM);
+  const int n_tiles = p.N / BN;
+  const int num_tiles = m_pairs * n_tiles;
+  const int k_blocks = p.K / kBK;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);   // leader's arrive.expect_tx covering both CTAs' loads
+      mbar_init(&empty_bar[s], 1);  // the leader's multicast commit
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);    // the leader's multicast commit
+      mbar_init(&tempty_bar[s], 16);  // 8 epilogue warps of each CTA
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2cta(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barriers of BOTH CTAs are initialised before anything can signal them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = (tile / n_tiles) * 2 * kBM + rank * kBM;
+        const int n0 = (tile % n_tiles) * BN + rank * (BN / 2);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          tma_load_2d_2cta(smem_a + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * kBK, m0);
+          tma_load_2d_2cta(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBK, n0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(2 * kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k)
+            umma_f16_2cta(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_2cta(&empty_bar[stage], 0b11);  // frees the slot in both CTAs
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2cta(&tfull_bar[as], 0b11);  // accumulator ready in both CTAs
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (8 warps, both CTAs) =====================
+    int it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int m0 = (tile / n_tiles) * 2 * kBM + rank * kBM;
+      const int n0 = (tile % n_tiles) * BN;
+      if (p.out_f32)
+        gemm_epilogue_tile<BN>(p, tmem_base + as * BN, m0, n0, warp, lane,
+                               [&]() { mbar_wait(&tfull_bar[as], aphase); });
+      else
+        gemm_epilogue_tile_tma(p, &tmC, smem_slabs + (warp - 4) * 8192, tmem_base + as * BN, m0, n0,
+                               warp, lane, [&]() { mbar_wait(&tfull_bar[as], aphase); });
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);
+    }
+    if (lane == 0) tma_store_wait_all<0>();  // all output tiles are in global memory before exit
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // nobody leaves while the peer may still read its smem or signal its barriers
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols);
   }
 }
 
