@@ -26,7 +26,8 @@ constexpr int kSimBM = 128;
 constexpr int kSimK = 512;
 constexpr int kSimKBlocks = kSimK / 64;  // 8
 constexpr int kSimStages = 5;
-constexpr int kSimThreads = 384;  // TMA, MMA, TMEM-alloc, idle + 2 epilogue groups of 4 warps
+constexpr int kSimAccStages = 4;  // accumulator stages in TMEM = epilogue groups
+constexpr int kSimThreads = 128 + kSimAccStages * 128;  // TMA, MMA, TMEM-alloc, idle + 4 epilogue groups of 4 warps
 constexpr int kSimABytes = kSimBM * 64 * 2;  // 16 KB per stage
 
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
@@ -80,11 +81,11 @@ sim_softmax_argmax_kernel(const __grid_constant__ CUtensorMap tmF,
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + kSimStages * kSimABytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kSimStages;
-  uint64_t* tfull_bar = bars + 2 * kSimStages;
-  uint64_t* tempty_bar = bars + 2 * kSimStages + 2;
-  uint64_t* t_bar = bars + 2 * kSimStages + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kSimStages + 5);
-  float* s_lb = reinterpret_cast<float*>(bars + 2 * kSimStages + 6);  // [BN]
+  uint64_t* tfull_bar = bars + 2 * kSimStages;                      // [kSimAccStages]
+  uint64_t* tempty_bar = tfull_bar + kSimAccStages;                  // [kSimAccStages]
+  uint64_t* t_bar = tempty_bar + kSimAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_bar + 1);
+  float* s_lb = reinterpret_cast<float*>(t_bar + 2);  // [BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -98,7 +99,7 @@ sim_softmax_argmax_kernel(const __grid_constant__ CUtensorMap tmF,
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kSimAccStages; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 4);
     }
@@ -106,7 +107,7 @@ sim_softmax_argmax_kernel(const __grid_constant__ CUtensorMap tmF,
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 256);  // two accumulator stages of ≤128 fp32 columns
+    tmem_alloc(tmem_slot, 512);  // four accumulator stages of ≤128 fp32 columns
     tmem_relinquish();
   }
   if (p.lb != nullptr)
@@ -143,8 +144,8 @@ sim_softmax_argmax_kernel(const __grid_constant__ CUtensorMap tmF,
       uint32_t phase = 0;
       int it = 0;
       for (int tile = p.tile_begin + blockIdx.x; tile < p.tile_end; tile += gridDim.x, ++it) {
-        const int as = it & 1;
-        mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
+        const int as = it % kSimAccStages;
+        mbar_wait(&tempty_bar[as], ((it / kSimAccStages) & 1) ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * 128;
         for (int kb = 0; kb < kSimKBlocks; ++kb) {
@@ -162,9 +163,9 @@ sim_softmax_argmax_kernel(const __grid_constant__ CUtensorMap tmF,
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue: two groups of 4 warps, one per accumulator stage ============
-    // Group g = (warp-4)/4 owns accumulator stage g and therefore every second tile of this CTA, so
-    // a tile's soft-max may take two MMA-tile times.  Within a group, warp q reads TMEM lane quadrant
+    // ===================== epilogue: four groups of 4 warps, one per accumulator stage ===========
+    // Group g = (warp-4)/4 owns accumulator stage g and therefore every fourth tile of this CTA, so
+    // a tile's soft-max may take four tile times before it holds up the HBM stream.  Within a group, warp q reads TMEM lane quadrant
     // q; thread = image row.  Logits are kept in log2 units: l = rn(acc·s2), s2 = scale·log2(e).
     const int q = warp & 3;
     const int grp = (warp - 4) >> 2;
@@ -174,8 +175,8 @@ sim_softmax_argmax_kernel(const __grid_constant__ CUtensorMap tmF,
     const bool filt = p.lb != nullptr;
     int it = 0;
     for (int tile = p.tile_begin + blockIdx.x; tile < p.tile_end; tile += gridDim.x, ++it) {
-      if ((it & 1) != grp) continue;
-      const int n_mine = it >> 1;
+      if ((it % kSimAccStages) != grp) continue;
+      const int n_mine = it / kSimAccStages;
       const int row = tile * kSimBM + q * 32 + lane;
       const bool row_ok = row < p.N;
       mbar_wait(&tfull_bar[grp], n_mine & 1);
@@ -279,7 +280,7 @@ sim_softmax_argmax_kernel(const __grid_constant__ CUtensorMap tmF,
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -598,7 +599,7 @@ __global__ void lb_export_kernel(void* base, int C, int k, int32_t* out_idx, int
 }
 
 size_t sim_smem_bytes(int BN) {
-  return (size_t)kSimKBlocks * BN * 128 + (size_t)kSimStages * kSimABytes + 1024 + 256 +
+  return (size_t)kSimKBlocks * BN * 128 + (size_t)kSimStages * kSimABytes + 1024 + 512 +
          (size_t)BN * 4;
 }
 constexpr int kLbMaxC = 256;
