@@ -45,7 +45,10 @@ const char* gb_version(void);
  * every tcgen05 GEMM launch (kind 0, work = 2*M*N*K FLOP) and every similarity/softmax/argmax launch
  * (kind 1, work = algorithmic HBM bytes) is bracketed by an event pair on its own stream. */
 typedef struct gb_profile_stats { uint64_t launches; double ms; double work; } gb_profile_stats;
+typedef struct gb_profile_launch { int kind, m, n, k; double ms; double work; } gb_profile_launch;
 int gb_profile_begin(gb_ctx* ctx);
+/* Per-launch records since _begin (call before _end); returns the number of launches recorded. */
+int gb_profile_launches(gb_ctx* ctx, gb_profile_launch* out, int cap);
 int gb_profile_end(gb_ctx* ctx, gb_profile_stats* out, int kinds);
 
 /* ---- op level (unit-testable building blocks) -------------------------------------------- */

@@ -26,6 +26,11 @@ class ProfileStats(Structure):
     _fields_ = [("launches", c_uint64), ("ms", ctypes.c_double), ("work", ctypes.c_double)]
 
 
+class ProfileLaunch(Structure):
+    _fields_ = [("kind", c_int), ("m", c_int), ("n", c_int), ("k", c_int), ("ms", ctypes.c_double),
+                ("work", ctypes.c_double)]
+
+
 class BlockWeights(Structure):
     _fields_ = [(n, P) for n in (
         "ln1_g", "ln1_b", "w_qkv", "b_qkv", "w_o", "b_o", "ln2_g", "ln2_b", "w_fc", "b_fc",
@@ -54,6 +59,7 @@ _SIGNATURES = {
     "gb_version": (c_char_p, []),
     "gb_profile_begin": (c_int, [P]),
     "gb_profile_end": (c_int, [P, POINTER(ProfileStats), c_int]),
+    "gb_profile_launches": (c_int, [P, POINTER(ProfileLaunch), c_int]),
     "gb_gemm_f16": (c_int, [P, P, c_int, P, c_int, P, P, c_int, P, c_int, c_int, c_int, c_int,
                             c_int, c_int, P]),
     "gb_layernorm_f16": (c_int, [P, P, c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, P]),
@@ -148,6 +154,14 @@ class Context:
 
     def profile_begin(self):
         self.check(self.lib.gb_profile_begin(self.h), "gb_profile_begin")
+
+    def profile_launches(self, cap=65536):
+        """Per-launch records (kind, m, n, k, ms, work) since profile_begin; call before profile_end."""
+        arr = (ProfileLaunch * cap)()
+        n = self.lib.gb_profile_launches(self.h, arr, cap)
+        if n < 0:
+            self.check(n, "gb_profile_launches")
+        return [(a.kind, a.m, a.n, a.k, a.ms, a.work) for a in arr[:min(n, cap)]]
 
     def profile_end(self):
         """[(launches, ms, work)] for kind 0 (GEMM, FLOPs) and kind 1 (sim kernel, bytes)."""

@@ -84,6 +84,22 @@ extern "C" int gb_profile_begin(gb_ctx* c) {
   return GB_OK;
 }
 
+extern "C" int gb_profile_launches(gb_ctx* c, gb_profile_launch* out, int cap) {
+  if (!c || (cap > 0 && !out)) return GB_ERR_ARG;
+  if (cudaDeviceSynchronize() != cudaSuccess) return GB_ERR_CUDA;
+  int n = 0;
+  for (auto& r : c->prof) {
+    if (n < cap) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, r.e0, r.e1);
+      out[n].kind = r.kind; out[n].m = r.m; out[n].n = r.n; out[n].k = r.k;
+      out[n].ms = ms; out[n].work = r.work;
+    }
+    ++n;
+  }
+  return n;
+}
+
 extern "C" int gb_profile_end(gb_ctx* c, gb_profile_stats* out, int kinds) {
   if (!c || !out || kinds <= 0) return GB_ERR_ARG;
   c->prof_on = false;

@@ -32,17 +32,18 @@ struct gb_ctx {
   // optional per-launch timing of the two roofline kernels (bench.py): kind 0 = tcgen05 GEMM (work =
   // FLOPs), kind 1 = sim/softmax/argmax (work = algorithmic HBM bytes)
   bool prof_on = false;
-  struct ProfRec { cudaEvent_t e0, e1; int kind; double work; };
+  struct ProfRec { cudaEvent_t e0, e1; int kind; double work; int m, n, k; };
   std::vector<ProfRec> prof;
 };
 
 // RAII helper: records an event pair around one launch when profiling is on.
 struct gb_prof_scope {
   gb_ctx* c; cudaStream_t st; bool on;
-  gb_prof_scope(gb_ctx* c_, cudaStream_t st_, int kind, double work) : c(c_), st(st_), on(c_->prof_on) {
+  gb_prof_scope(gb_ctx* c_, cudaStream_t st_, int kind, double work, int m = 0, int n = 0, int k = 0)
+      : c(c_), st(st_), on(c_->prof_on) {
     if (!on) return;
     gb_ctx::ProfRec r;
-    r.kind = kind; r.work = work;
+    r.kind = kind; r.work = work; r.m = m; r.n = n; r.k = k;
     cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
     cudaEventRecord(r.e0, st);
     c->prof.push_back(r);

@@ -19,7 +19,7 @@ static int launch_gemm_bn(gb_ctx* c, const CUtensorMap& tmA, const CUtensorMap& 
   const int tiles = m_tiles * (p.N / BN);
   const int grid = tiles < c->num_sms ? tiles : c->num_sms;
   {
-    gb_prof_scope prof(c, st, 0, 2.0 * p.M * p.N * p.K);
+    gb_prof_scope prof(c, st, 0, 2.0 * p.M * p.N * p.K, p.M, p.N, p.K);
     gemm_f16_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
   }
   GB_LAUNCH_CHECK(c);
@@ -40,7 +40,7 @@ static int launch_gemm_2cta(gb_ctx* c, const CUtensorMap& tmA, const CUtensorMap
   const int max_clusters = c->num_sms / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   {
-    gb_prof_scope prof(c, st, 0, 2.0 * p.M * p.N * p.K);
+    gb_prof_scope prof(c, st, 0, 2.0 * p.M * p.N * p.K, p.M, p.N, p.K);
     gemm_f16_tcgen05_2cta_kernel<<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, tmC, p);
   }
   GB_LAUNCH_CHECK(c);

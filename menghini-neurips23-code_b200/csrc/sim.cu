@@ -643,7 +643,7 @@ int launch_sim(gb_ctx* c, const void* F, const void* T, float scale, int N, int 
   {
     // algorithmic bytes: one fp16 feature row in, (pred, p_pred) out per image (+ the prob row on request)
     const double rows = (double)(p.N - row_begin);
-    gb_prof_scope prof(c, st, 1, rows * (kSimK * 2 + 8 + (probs ? 4.0 * C : 0.0)));
+    gb_prof_scope prof(c, st, 1, rows * (kSimK * 2 + 8 + (probs ? 4.0 * C : 0.0)), (int)rows, C, kSimK);
     sim_softmax_argmax_kernel<<<grid, kSimThreads, smem, st>>>(tmF, tmT, p);
   }
   GB_LAUNCH_CHECK(c);
