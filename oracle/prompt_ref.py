@@ -61,3 +61,36 @@ def coop_step(model, prefix, classes, images, labels, lr=None):
         with torch.no_grad():
             prefix -= lr * prefix.grad
     return loss.detach(), prefix.grad.detach(), logits.detach()
+
+
+class UPTHead(torch.nn.Module):
+    """The trainable part of UPTModel — models/prompts_models.py:64-153 — restated: CoOp and VPT
+    prompts, four Linear projections and the 1-layer / 1-head prompt-coupling transformer."""
+
+    def __init__(self, coop_embeddings, vpt_embeddings, dim_transformer=128):
+        super().__init__()
+        self.coop_embeddings = torch.nn.Parameter(coop_embeddings)                    # :88
+        self.vpt_embeddings = torch.nn.Parameter(vpt_embeddings)                      # :89
+        self.coop_length, self.coop_dim = coop_embeddings.size()[1], coop_embeddings.size()[2]
+        self.vpt_length, self.vpt_dim = vpt_embeddings.size()[1], vpt_embeddings.size()[2]
+        self.proj_coop_pre = torch.nn.Linear(self.coop_dim, dim_transformer)          # :99-114
+        self.proj_coop_post = torch.nn.Linear(dim_transformer, self.coop_dim)
+        self.proj_vpt_pre = torch.nn.Linear(self.vpt_dim, dim_transformer)
+        self.proj_vpt_post = torch.nn.Linear(dim_transformer, self.vpt_dim)
+        self.transformer = clip_ref.Transformer(width=dim_transformer, layers=1, heads=1)  # :116-119
+
+    def prompts(self):
+        coop = self.proj_coop_pre(self.coop_embeddings)                                # :131-132
+        vpt = self.proj_vpt_pre(self.vpt_embeddings)                                   # :135
+        seq = torch.cat((coop, vpt), dim=0).to(torch.float32)                          # :138
+        out = self.transformer(seq).to(torch.float16)                                  # :141 (hard-coded)
+        n = len(self.coop_embeddings)
+        coop_embs = self.proj_coop_post(out[:n].to(torch.float32)).reshape(-1, self.coop_length, self.coop_dim)
+        vpt_embs = self.proj_vpt_post(out[n:].to(torch.float32)).reshape(-1, self.vpt_length, self.vpt_dim)
+        return coop_embs, vpt_embs                                                     # :144-145
+
+
+def upt_forward(model, head: UPTHead, images, classes):
+    """UPTModel.forward — :129-153: (text features, image features), both un-normalised."""
+    coop_embs, vpt_embs = head.prompts()
+    return text_forward(model, coop_embs, classes), image_forward(model, images, vpt_embs)

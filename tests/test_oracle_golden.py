@@ -93,3 +93,16 @@ def test_prompt_forward_restatements_match_reference_goldens(golden_dir):
                                          torch.tensor([0, 1, 2, 3]))
     assert abs(float(loss) - float(g["coop_loss"])) < 1e-4
     assert np.abs(grad.numpy() - g["coop_grad_prefix"]).max() < 1e-4
+
+
+def test_upt_restatement_matches_reference_golden(golden_dir):
+    g = np.load(f"{golden_dir}/towers_vitb32_seed1234.npz")
+    model = clip_ref.build_model(seed=1234)
+    classes = [" ".join(c.split("_")) for c in synth.class_names(5, seed=1)]
+    head = prompt_ref.UPTHead(synth.text_prefix(4, seed=2), synth.image_prefix(4, seed=3)[None])
+    sd = {k[len("upt_sd."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("upt_sd.")}
+    head.load_state_dict(sd, strict=False)
+    with torch.no_grad():
+        t, v = prompt_ref.upt_forward(model, head, synth.images(2, seed=0), classes)
+    assert np.abs(t.numpy() - g["upt_text"]).max() < 1e-4
+    assert np.abs(v.numpy() - g["upt_visual"]).max() < 1e-4
