@@ -87,7 +87,7 @@ int gb_attention_bwd(gb_ctx* ctx, const void* qkv, const void* dout, void* dqkv,
 /* ---- towers ------------------------------------------------------------------------------- */
 
 /* One ResidualAttentionBlock.  Weights fp16 in nn.Linear layout [out,in]; biases and LayerNorm
- * parameters fp32.  *_t are [in,out] transposed copies used by the prompt-gradient pass
+ * parameters fp32 (ln*_g / ln*_b are always the original γ, β).  *_t are [in,out] transposed copies used by the prompt-gradient pass
  * (may be NULL when only forward is needed). */
 typedef struct gb_block_weights {
   const float* ln1_g; const float* ln1_b;
@@ -97,6 +97,11 @@ typedef struct gb_block_weights {
   const void* w_fc;   const float* b_fc;    /* [4D,D], [4D] */
   const void* w_proj; const float* b_proj;  /* [D,4D], [D]  */
   const void* w_qkv_t; const void* w_o_t; const void* w_fc_t; const void* w_proj_t;
+  /* LayerNorm folding (optional, both or neither).  When s_qkv / s_fc are non-NULL, w_qkv / b_qkv hold
+   * W∘γ1 and b + W·β1 (w_fc / b_fc: γ2, β2) and s_*[n] = Σ_k W'[n,k] in fp32: the forward then never
+   * materialises ln_1(x) / ln_2(x); the GEMM epilogue applies the per-row mean and rstd instead.
+   * The *_t copies stay the transposes of the ORIGINAL weights (the gradient pass uses γ itself). */
+  const float* s_qkv; const float* s_fc;
 } gb_block_weights;
 
 /* Frozen CLIP ViT-B/32 image tower (clip.model.VisionTransformer as re-wired by

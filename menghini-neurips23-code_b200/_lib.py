@@ -34,7 +34,7 @@ class ProfileLaunch(Structure):
 class BlockWeights(Structure):
     _fields_ = [(n, P) for n in (
         "ln1_g", "ln1_b", "w_qkv", "b_qkv", "w_o", "b_o", "ln2_g", "ln2_b", "w_fc", "b_fc",
-        "w_proj", "b_proj", "w_qkv_t", "w_o_t", "w_fc_t", "w_proj_t")]
+        "w_proj", "b_proj", "w_qkv_t", "w_o_t", "w_fc_t", "w_proj_t", "s_qkv", "s_fc")]
 
 
 class VitWeights(Structure):

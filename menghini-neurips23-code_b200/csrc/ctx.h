@@ -82,8 +82,16 @@ inline int gb_fail(gb_ctx* c, int code, const char* fmt, ...) {
 int gb_make_tmap_2d_f16(gb_ctx* c, CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols,
                         uint64_t ld_elems, uint32_t box_rows);
 
+// LayerNorm-folding extras of a GEMM launch (see GemmParams): statistics consumed / produced.
+struct gb_gemm_ln {
+  const float* ln_part = nullptr;  // [ln_parts][M][2] (Σx, Σx²) of A's rows → fold LayerNorm into this GEMM
+  int ln_parts = 0;
+  const float* col_sum = nullptr;  // [N]
+  float* stats_out = nullptr;      // [N/128][M][2] partial statistics of the output rows
+};
+
 // internal launchers shared between op-level and tower-level entry points
 int gb_launch_gemm(gb_ctx* c, const void* A, int lda, const void* W, int ldw, const float* bias,
                    const void* resid, int ldr, void* out, int ldo, int M, int N, int K, int act,
-                   int out_f32, cudaStream_t st, void* aux = nullptr);
+                   int out_f32, cudaStream_t st, void* aux = nullptr, const struct gb_gemm_ln* ln = nullptr);
 int gb_ws_reserve(gb_ctx* c, size_t bytes);

@@ -49,7 +49,7 @@ static int launch_gemm_2cta(gb_ctx* c, const CUtensorMap& tmA, const CUtensorMap
 
 int gb_launch_gemm(gb_ctx* c, const void* A, int lda, const void* W, int ldw, const float* bias,
                    const void* resid, int ldr, void* out, int ldo, int M, int N, int K, int act,
-                   int out_f32, cudaStream_t st, void* aux) {
+                   int out_f32, cudaStream_t st, void* aux, const gb_gemm_ln* ln) {
   if (!A || !W || !out) return gb_fail(c, GB_ERR_ARG, "gemm: null pointer");
   if (M <= 0) return GB_OK;
   if (K % kBK != 0 || N % 128 != 0 || lda % 8 != 0 || ldw % 8 != 0 || ldo % 8 != 0 ||
@@ -79,6 +79,15 @@ int gb_launch_gemm(gb_ctx* c, const void* A, int lda, const void* W, int ldw, co
   p.act = act; p.out_f32 = out_f32;
   if (getenv("GB_DEBUG_NOSTORE")) p.out_f32 = 2;  // experiment: skip the epilogue's global stores
   p.aux = reinterpret_cast<__half*>(aux);
+  p.ln_part = nullptr; p.ln_parts = 0; p.ln_dim = K; p.col_sum = nullptr; p.stats_out = nullptr;
+  if (ln) {
+    if (out_f32 || N % 256 != 0)
+      return gb_fail(c, GB_ERR_ARG, "gemm: LayerNorm folding needs fp16 output and N %% 256 == 0");
+    if ((ln->ln_part != nullptr) != (ln->col_sum != nullptr) || (ln->ln_part && ln->ln_parts <= 0))
+      return gb_fail(c, GB_ERR_ARG, "gemm: inconsistent LayerNorm folding arguments");
+    p.ln_part = ln->ln_part; p.ln_parts = ln->ln_parts; p.col_sum = ln->col_sum;
+    p.stats_out = ln->stats_out;
+  }
   if (act == 2 && !aux) return gb_fail(c, GB_ERR_ARG, "gemm: act 2 needs aux");
   if (aux && (out_f32 || (reinterpret_cast<uintptr_t>(aux) & 15))) return gb_fail(c, GB_ERR_ARG, "gemm: aux needs fp16 output layout and 16-byte alignment");
   if (!wide) return launch_gemm_bn<128>(c, tmA, tmB, p, st);

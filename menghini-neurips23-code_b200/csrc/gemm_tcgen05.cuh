@@ -34,6 +34,16 @@ struct GemmParams {
   int out_f32;  // 1 → fp32 store
   __half* aux;  // [M,ldo] fp16 or nullptr.  act 1: receives the pre-activation (tape for backward);
                 // act 2: the saved pre-activation that is read.
+  // LayerNorm folded into the contraction (CTA-pair kernel, fp16 output only).  With W' = W∘γ,
+  // s_n = Σ_k W'[n,k] and b' = b + W·β:   LN(x)·Wᵀ + b = rstd_r·(x·W'ᵀ − μ_r·s_n) + b'_n,
+  // so A is the raw residual stream and the row statistics are applied in the epilogue.
+  const float* ln_part;  // [ln_parts][M][2] partial (Σx, Σx²) of each row of A, or nullptr
+  int ln_parts;
+  int ln_dim;            // row length D of the normalised rows (= K)
+  const float* col_sum;  // s_n, [N]
+  // partial (Σ, Σ²) of every OUTPUT row over this warp's 128 columns, [N/128][M][2], or nullptr: the
+  // statistics the next LayerNorm needs, produced where the rows are written.
+  float* stats_out;
 };
 
 template <int BN>
@@ -310,6 +320,21 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
 #pragma unroll
     for (int j = 0; j < 4; ++j) pre[j] = r4[j];
   }
+  // row statistics of the folded LayerNorm: partial sums are combined in a fixed order (deterministic)
+  float ln_mean = 0.f, ln_rstd = 1.f;
+  const bool ln = p.ln_part != nullptr;
+  if (ln && row_ok) {
+    float sx = 0.f, sq = 0.f;
+    for (int i = 0; i < p.ln_parts; ++i) {
+      const float2 t = *reinterpret_cast<const float2*>(p.ln_part + ((size_t)i * p.M + row) * 2);
+      sx += t.x;
+      sq += t.y;
+    }
+    const float inv_d = 1.0f / (float)p.ln_dim;
+    ln_mean = sx * inv_d;
+    ln_rstd = rsqrtf(fmaxf(sq * inv_d - ln_mean * ln_mean, 0.f) + 1e-5f);
+  }
+  float st_sum = 0.f, st_sq = 0.f;
   wait_acc();
   tc_fence_after();
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + half * (BN / 2);
@@ -333,6 +358,17 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
     float f[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    if (ln) {
+      const float4* s4 = reinterpret_cast<const float4*>(p.col_sum + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 ss = __ldg(s4 + j);
+        f[4 * j + 0] = (f[4 * j + 0] - ln_mean * ss.x) * ln_rstd;
+        f[4 * j + 1] = (f[4 * j + 1] - ln_mean * ss.y) * ln_rstd;
+        f[4 * j + 2] = (f[4 * j + 2] - ln_mean * ss.z) * ln_rstd;
+        f[4 * j + 3] = (f[4 * j + 3] - ln_mean * ss.w) * ln_rstd;
+      }
+    }
     if (p.bias != nullptr) {
       const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
@@ -386,7 +422,14 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
       uint4 o;
       __half2* h = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-      for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(f[8 * j + 2 * t], f[8 * j + 2 * t + 1]);
+      for (int t = 0; t < 4; ++t) {
+        h[t] = __floats2half2_rn(f[8 * j + 2 * t], f[8 * j + 2 * t + 1]);
+        if (p.stats_out != nullptr) {  // statistics of the values as stored (fp16-rounded)
+          const float2 r = __half22float2(h[t]);
+          st_sum += r.x + r.y;
+          st_sq += r.x * r.x + r.y * r.y;
+        }
+      }
       const int chunk = (c & 1) * 4 + j;
       *reinterpret_cast<uint4*>(slab + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = o;
     }
@@ -401,6 +444,9 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
 #pragma unroll
     for (int j = 0; j < 4; ++j) pre[j] = pre_next[j];
   }
+  if (p.stats_out != nullptr && row_ok)
+    *reinterpret_cast<float2*>(p.stats_out + ((size_t)(n0 >> 7) * p.M + row) * 2) =
+        make_float2(st_sum, st_sq);
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256)
 vit_assemble_lnpre_kernel(const __half* __restrict__ patch, const float* __restrict__ cls,
                           const float* __restrict__ pos, const float* __restrict__ prefix, int P,
                           const float* __restrict__ gamma, const float* __restrict__ beta,
-                          __half* __restrict__ x, int B, float eps) {
+                          __half* __restrict__ x, int B, float eps, float* __restrict__ stats) {
   constexpr int D = 768, V = 3;
   const int L = 50 + P;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -176,6 +176,7 @@ vit_assemble_lnpre_kernel(const __half* __restrict__ patch, const float* __restr
 #pragma unroll
   for (int i = 0; i < V * 8; ++i) { const float d = f[i] - mean; q += d * d; }
   const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+  float st_sum = 0.f, st_sq = 0.f;
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     const int col = (v * 32 + lane) * 8;
@@ -187,9 +188,16 @@ vit_assemble_lnpre_kernel(const __half* __restrict__ patch, const float* __restr
       const float o0 = (f[v * 8 + 2 * t] - mean) * rstd * __ldg(gamma + c0) + __ldg(beta + c0);
       const float o1 = (f[v * 8 + 2 * t + 1] - mean) * rstd * __ldg(gamma + c0 + 1) + __ldg(beta + c0 + 1);
       h[t] = __floats2half2_rn(o0, o1);
+      const float2 r = __half22float2(h[t]);
+      st_sum += r.x + r.y;
+      st_sq += r.x * r.x + r.y * r.y;
     }
     *reinterpret_cast<uint4*>(x + (size_t)warp * D + col) = u;
   }
+  // (Σ, Σ²) of the stored row: the statistics of the first block's folded ln_1
+  st_sum = warp_sum(st_sum);
+  st_sq = warp_sum(st_sq);
+  if (stats != nullptr && lane == 0) *reinterpret_cast<float2*>(stats + (size_t)warp * 2) = make_float2(st_sum, st_sq);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -201,8 +209,9 @@ vit_assemble_lnpre_kernel(const __half* __restrict__ patch, const float* __restr
 __global__ void __launch_bounds__(256)
 text_assemble_kernel(const int32_t* __restrict__ ids, int ld_ids, const __half* __restrict__ tok_emb,
                      const float* __restrict__ pos, const float* __restrict__ prefix, int P,
-                     __half* __restrict__ x, int C, int ctx_len) {
+                     __half* __restrict__ x, int C, int ctx_len, float* __restrict__ stats) {
   constexpr int D = 512, V = 2;
+  float st_sum = 0.f, st_sq = 0.f;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= C * ctx_len) return;
@@ -232,9 +241,17 @@ text_assemble_kernel(const int32_t* __restrict__ ids, int ld_ids, const __half* 
     uint4 o;
     __half2* h = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-    for (int t = 0; t < 4; ++t) h[t] = __floats2half2_rn(a[2 * t], a[2 * t + 1]);
+    for (int t = 0; t < 4; ++t) {
+      h[t] = __floats2half2_rn(a[2 * t], a[2 * t + 1]);
+      const float2 r = __half22float2(h[t]);
+      st_sum += r.x + r.y;
+      st_sq += r.x * r.x + r.y * r.y;
+    }
     *reinterpret_cast<uint4*>(x + (size_t)warp * D + col) = o;
   }
+  st_sum = warp_sum(st_sum);
+  st_sq = warp_sum(st_sq);
+  if (stats != nullptr && lane == 0) *reinterpret_cast<float2*>(stats + (size_t)warp * 2) = make_float2(st_sum, st_sq);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -466,10 +483,10 @@ int gb_launch_im2col(gb_ctx* c, const void* img, int img_f32, void* out, int B, 
 
 int gb_launch_vit_assemble(gb_ctx* c, const void* patch, const float* cls, const float* pos,
                            const float* prefix, int P, const float* gamma, const float* beta,
-                           void* x, int B, cudaStream_t st) {
+                           void* x, int B, cudaStream_t st, float* stats) {
   if (B <= 0) return GB_OK;
   vit_assemble_lnpre_kernel<<<warps_grid((long long)B * (50 + P)), 256, 0, st>>>(
-      (const __half*)patch, cls, pos, prefix, P, gamma, beta, (__half*)x, B, 1e-5f);
+      (const __half*)patch, cls, pos, prefix, P, gamma, beta, (__half*)x, B, 1e-5f, stats);
   GB_LAUNCH_CHECK(c);
   return GB_OK;
 }
@@ -489,10 +506,10 @@ int gb_launch_eot_rows(gb_ctx* c, const int32_t* eot, int32_t* rows, int C, int 
 
 int gb_launch_text_assemble(gb_ctx* c, const int32_t* ids, int ld_ids, const void* tok_emb,
                             const float* pos, const float* prefix, int P, void* x, int C, int ctx_len,
-                            cudaStream_t st) {
+                            cudaStream_t st, float* stats) {
   if (C <= 0) return GB_OK;
   text_assemble_kernel<<<warps_grid((long long)C * ctx_len), 256, 0, st>>>(
-      ids, ld_ids, (const __half*)tok_emb, pos, prefix, P, (__half*)x, C, ctx_len);
+      ids, ld_ids, (const __half*)tok_emb, pos, prefix, P, (__half*)x, C, ctx_len, stats);
   GB_LAUNCH_CHECK(c);
   return GB_OK;
 }

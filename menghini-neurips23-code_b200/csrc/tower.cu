@@ -9,8 +9,10 @@
 //
 // Layout: tokens of all samples form one flat row dimension M = samples·L (sample-major), fp16
 // residual stream, fp32 LayerNorm statistics, fp32 accumulation in every contraction.  Each block is
-//   LN → GEMM(+bias) → attention → GEMM(+bias,+residual) → LN → GEMM(+bias,QuickGELU) → GEMM(+bias,+residual)
-// = 7 launches; LayerNorm affine, bias, activation and residual adds live in GEMM epilogues.
+//   GEMM(ln_1 folded, +bias) → attention → GEMM(+bias,+residual) → GEMM(ln_2 folded, +bias, QuickGELU)
+//   → GEMM(+bias,+residual)
+// = 5 launches; LayerNorm (as folded weights + epilogue row statistics), bias, activation and residual
+// adds all live in GEMM epilogues.
 #include <string.h>
 
 #include "ctx.h"
@@ -25,10 +27,10 @@ int gb_launch_layernorm_bwd(gb_ctx* c, const void* dy, int lddy, const void* x, 
 int gb_launch_im2col(gb_ctx* c, const void* img, int img_f32, void* out, int B, cudaStream_t st);
 int gb_launch_vit_assemble(gb_ctx* c, const void* patch, const float* cls, const float* pos,
                            const float* prefix, int P, const float* gamma, const float* beta,
-                           void* x, int B, cudaStream_t st);
+                           void* x, int B, cudaStream_t st, float* stats);
 int gb_launch_text_assemble(gb_ctx* c, const int32_t* ids, int ld_ids, const void* tok_emb,
                             const float* pos, const float* prefix, int P, void* x, int C, int Lt,
-                            cudaStream_t st);
+                            cudaStream_t st, float* stats);
 int gb_launch_l2norm512(gb_ctx* c, const float* x, void* y16, float* y32, int rows, cudaStream_t st);
 int gb_launch_prefix_grad(gb_ctx* c, const void* dx, int L, int S, int P, int D, const float* prefix,
                           const float* gamma, int ln_pre, float inv_scale, float* dprefix,
@@ -82,24 +84,44 @@ struct Tape {
 
 // Runs `layers` residual attention blocks over x (fp16 [M,D]).  Without a tape x is updated in
 // place; with a tape layer l reads tape.x0(l) and leaves its output in tape.x0(l+1) / x_final.
+// When the block table carries LayerNorm-folded weights (s_qkv / s_fc non-null) ln_1 and ln_2 are not
+// separate passes: the in-proj / c_fc GEMMs read the raw residual stream and apply the row statistics
+// in their epilogue, and the two residual GEMMs emit the (Σ, Σ²) partials of the rows they write.
+// st_a / st_b: [D/128][M][2] floats each; st_a holds the statistics of x on entry (1 part).
 int run_blocks(gb_ctx* c, const gb_tower* t, int S, int L, int causal, void* x, const Tape* tape,
-               void* h, void* qkv_ws, void* a, void* g, cudaStream_t st) {
+               void* h, void* qkv_ws, void* a, void* g, float* st_a, float* st_b, cudaStream_t st) {
   const int D = t->width, M = S * L;
   int rc;
+  int parts_in = 1;  // partial-sum pairs describing the rows of the current residual stream
   for (int l = 0; l < t->layers; ++l) {
     const gb_block_weights& w = t->blocks[l];
     void* x0 = tape ? tape->x0(l) : x;
     void* x1 = tape ? tape->x1(l) : x;
     void* x2 = tape ? (l + 1 < t->layers ? tape->x0(l + 1) : tape->x_final(t->layers)) : x;
     void* qkv = tape ? tape->qkv(l) : qkv_ws;
-    if ((rc = gb_launch_layernorm(c, x0, D, nullptr, 1, w.ln1_g, w.ln1_b, h, D, M, D, 0, st))) return rc;
-    if ((rc = gb_launch_gemm(c, h, D, w.w_qkv, D, w.b_qkv, nullptr, 0, qkv, 3 * D, M, 3 * D, D, 0, 0, st))) return rc;
+    const bool fold = w.s_qkv != nullptr && w.s_fc != nullptr;
+    if (fold) {
+      gb_gemm_ln ln1; ln1.ln_part = st_a; ln1.ln_parts = parts_in; ln1.col_sum = w.s_qkv;
+      if ((rc = gb_launch_gemm(c, x0, D, w.w_qkv, D, w.b_qkv, nullptr, 0, qkv, 3 * D, M, 3 * D, D, 0, 0, st, nullptr, &ln1))) return rc;
+    } else {
+      if ((rc = gb_launch_layernorm(c, x0, D, nullptr, 1, w.ln1_g, w.ln1_b, h, D, M, D, 0, st))) return rc;
+      if ((rc = gb_launch_gemm(c, h, D, w.w_qkv, D, w.b_qkv, nullptr, 0, qkv, 3 * D, M, 3 * D, D, 0, 0, st))) return rc;
+    }
     if ((rc = gb_launch_attn_fwd(c, qkv, a, S, L, D, causal, st))) return rc;
-    if ((rc = gb_launch_gemm(c, a, D, w.w_o, D, w.b_o, x0, D, x1, D, M, D, D, 0, 0, st))) return rc;
-    if ((rc = gb_launch_layernorm(c, x1, D, nullptr, 1, w.ln2_g, w.ln2_b, h, D, M, D, 0, st))) return rc;
-    if ((rc = gb_launch_gemm(c, h, D, w.w_fc, D, w.b_fc, nullptr, 0, g, 4 * D, M, 4 * D, D, 1, 0, st,
-                             tape ? tape->f(l) : nullptr))) return rc;
-    if ((rc = gb_launch_gemm(c, g, 4 * D, w.w_proj, 4 * D, w.b_proj, x1, D, x2, D, M, D, 4 * D, 0, 0, st))) return rc;
+    gb_gemm_ln so; so.stats_out = fold ? st_b : nullptr;
+    if ((rc = gb_launch_gemm(c, a, D, w.w_o, D, w.b_o, x0, D, x1, D, M, D, D, 0, 0, st, nullptr, fold ? &so : nullptr))) return rc;
+    if (fold) {
+      gb_gemm_ln ln2; ln2.ln_part = st_b; ln2.ln_parts = D / 128; ln2.col_sum = w.s_fc;
+      if ((rc = gb_launch_gemm(c, x1, D, w.w_fc, D, w.b_fc, nullptr, 0, g, 4 * D, M, 4 * D, D, 1, 0, st,
+                               tape ? tape->f(l) : nullptr, &ln2))) return rc;
+    } else {
+      if ((rc = gb_launch_layernorm(c, x1, D, nullptr, 1, w.ln2_g, w.ln2_b, h, D, M, D, 0, st))) return rc;
+      if ((rc = gb_launch_gemm(c, h, D, w.w_fc, D, w.b_fc, nullptr, 0, g, 4 * D, M, 4 * D, D, 1, 0, st,
+                               tape ? tape->f(l) : nullptr))) return rc;
+    }
+    gb_gemm_ln sp; sp.stats_out = fold ? st_a : nullptr;
+    if ((rc = gb_launch_gemm(c, g, 4 * D, w.w_proj, 4 * D, w.b_proj, x1, D, x2, D, M, D, 4 * D, 0, 0, st, nullptr, fold ? &sp : nullptr))) return rc;
+    parts_in = D / 128;
   }
   return GB_OK;
 }
@@ -197,6 +219,7 @@ extern "C" int gb_vit_forward(gb_ctx* c, const void* img, int img_f32, const flo
     Bump b(nullptr);
     b.take(h2(M, D)); b.take(h2(M, D)); b.take(h2(M, 3 * D)); b.take(h2(M, D));
     b.take(h2(M > (size_t)B * 49 ? M : (size_t)B * 49, 4 * D)); b.take(h2(B, D)); b.take((size_t)B * 512 * 4);
+    b.take(M * (D / 128) * 8); b.take(M * (D / 128) * 8);
     need = b.off;
   }
   int rc = gb_ws_reserve(c, need);
@@ -209,6 +232,8 @@ extern "C" int gb_vit_forward(gb_ctx* c, const void* img, int img_f32, const flo
   void* g = b.take(h2(M > (size_t)B * 49 ? M : (size_t)B * 49, 4 * D));
   void* cls_ln = b.take(h2(B, D));
   float* feat_ws = reinterpret_cast<float*>(b.take((size_t)B * 512 * 4));
+  float* st_a = reinterpret_cast<float*>(b.take(M * (D / 128) * 8));
+  float* st_b = reinterpret_cast<float*>(b.take(M * (D / 128) * 8));
   Tape tape{reinterpret_cast<uint8_t*>(tape_mem), M, (size_t)D};
   void* x = tape_mem ? tape.x0(0) : x_ws;
   const gb_vit_weights& w = t->vit;
@@ -216,8 +241,8 @@ extern "C" int gb_vit_forward(gb_ctx* c, const void* img, int img_f32, const flo
   if ((rc = gb_launch_im2col(c, img, img_f32, g, B, st))) return rc;
   if ((rc = gb_launch_gemm(c, g, 3072, w.conv_w, 3072, nullptr, nullptr, 0, a, D, B * 49, D, 3072, 0, 0, st))) return rc;
   // CLS + pos-emb, prefix rows, ln_pre: :135-157
-  if ((rc = gb_launch_vit_assemble(c, a, w.cls, w.pos, prefix, P, w.ln_pre_g, w.ln_pre_b, x, B, st))) return rc;
-  if ((rc = run_blocks(c, t, B, L, 0, x, tape_mem ? &tape : nullptr, h, qkv, a, g, st))) return rc;
+  if ((rc = gb_launch_vit_assemble(c, a, w.cls, w.pos, prefix, P, w.ln_pre_g, w.ln_pre_b, x, B, st, st_a))) return rc;
+  if ((rc = run_blocks(c, t, B, L, 0, x, tape_mem ? &tape : nullptr, h, qkv, a, g, st_a, st_b, st))) return rc;
   const void* xf = tape_mem ? tape.x_final(t->layers) : x;
   // ln_post(x[:,0,:]) @ proj: :189-192
   if ((rc = gb_launch_layernorm(c, xf, D, nullptr, L, w.ln_post_g, w.ln_post_b, cls_ln, D, B, D, 0, st))) return rc;
@@ -284,6 +309,7 @@ extern "C" int gb_text_forward(gb_ctx* c, const int32_t* ids, int ld_ids, const 
     Bump b(nullptr);
     b.take(h2(M, D)); b.take(h2(M, D)); b.take(h2(M, 3 * D)); b.take(h2(M, D)); b.take(h2(M, 4 * D));
     b.take(h2(C, D)); b.take((size_t)C * 512 * 4); b.take((size_t)C * 4);
+    b.take(M * (D / 128) * 8); b.take(M * (D / 128) * 8);
     need = b.off;
   }
   int rc = gb_ws_reserve(c, need);
@@ -297,11 +323,13 @@ extern "C" int gb_text_forward(gb_ctx* c, const int32_t* ids, int ld_ids, const 
   void* eot_ln = b.take(h2(C, D));
   float* feat_ws = reinterpret_cast<float*>(b.take((size_t)C * 512 * 4));
   int32_t* rows = reinterpret_cast<int32_t*>(b.take((size_t)C * 4));
+  float* st_a = reinterpret_cast<float*>(b.take(M * (D / 128) * 8));
+  float* st_b = reinterpret_cast<float*>(b.take(M * (D / 128) * 8));
   Tape tape{reinterpret_cast<uint8_t*>(tape_mem), M, (size_t)D};
   void* x = tape_mem ? tape.x0(0) : x_ws;
   // token embedding, prefix overwrite of rows 1..P, + positional embedding: models/clip_encoders.py:63-74
-  if ((rc = gb_launch_text_assemble(c, ids, ld_ids, w.tok_emb, w.pos, prefix, P, x, C, L, st))) return rc;
-  if ((rc = run_blocks(c, t, C, L, 1, x, tape_mem ? &tape : nullptr, h, qkv, a, g, st))) return rc;
+  if ((rc = gb_launch_text_assemble(c, ids, ld_ids, w.tok_emb, w.pos, prefix, P, x, C, L, st, st_a))) return rc;
+  if ((rc = run_blocks(c, t, C, L, 1, x, tape_mem ? &tape : nullptr, h, qkv, a, g, st_a, st_b, st))) return rc;
   const void* xf = tape_mem ? tape.x_final(t->layers) : x;
   // ln_final, EOT-row gather, @ text_projection: :85-89
   if ((rc = gb_launch_eot_rows(c, eot, rows, C, L, st))) return rc;

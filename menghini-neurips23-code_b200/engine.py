@@ -35,11 +35,12 @@ def _require_cuda(device) -> torch.device:
 class Engine:
     """Frozen towers of one CLIP ViT-B/32 on one GPU."""
 
-    def __init__(self, state_dict, device="cuda:0", with_grad: bool = True):
+    def __init__(self, state_dict, device="cuda:0", with_grad: bool = True, fold_ln: bool = True):
         self.device = _require_cuda(device)
         self.ctx = Context.get(self.device.index)
         self.lib = self.ctx.lib
         self.with_grad = with_grad
+        self.fold_ln = fold_ln
         self._keep = []  # device tensors referenced by the C-side tables
         sd = state_dict
         with torch.cuda.device(self.device):
@@ -69,12 +70,25 @@ class Engine:
             b = arr[i]
             w_qkv, w_o = self._f16(sd[p + "attn.in_proj_weight"]), self._f16(sd[p + "attn.out_proj.weight"])
             w_fc, w_proj = self._f16(sd[p + "mlp.c_fc.weight"]), self._f16(sd[p + "mlp.c_proj.weight"])
-            b.ln1_g, b.ln1_b = ptr(self._f32(sd[p + "ln_1.weight"])), ptr(self._f32(sd[p + "ln_1.bias"]))
-            b.ln2_g, b.ln2_b = ptr(self._f32(sd[p + "ln_2.weight"])), ptr(self._f32(sd[p + "ln_2.bias"]))
-            b.w_qkv, b.w_o, b.w_fc, b.w_proj = ptr(w_qkv), ptr(w_o), ptr(w_fc), ptr(w_proj)
-            b.b_qkv = ptr(self._f32(sd[p + "attn.in_proj_bias"].half()))
+            g1, b1 = self._f32(sd[p + "ln_1.weight"]), self._f32(sd[p + "ln_1.bias"])
+            g2, b2 = self._f32(sd[p + "ln_2.weight"]), self._f32(sd[p + "ln_2.bias"])
+            b.ln1_g, b.ln1_b, b.ln2_g, b.ln2_b = ptr(g1), ptr(b1), ptr(g2), ptr(b2)
+            b_qkv = self._f32(sd[p + "attn.in_proj_bias"].half())
+            b_fc = self._f32(sd[p + "mlp.c_fc.bias"].half())
+            if self.fold_ln:
+                # LN(x)·Wᵀ + b = rstd·(x·(W∘γ)ᵀ − μ·s) + (b + W·β),  s_n = Σ_k (W∘γ)[n,k]  (γ, β frozen)
+                wq_g = self._f16(w_qkv.float() * g1)
+                wf_g = self._f16(w_fc.float() * g2)
+                b.w_qkv, b.w_fc = ptr(wq_g), ptr(wf_g)
+                b.s_qkv = ptr(self._f32(wq_g.float().sum(dim=1)))
+                b.s_fc = ptr(self._f32(wf_g.float().sum(dim=1)))
+                b.b_qkv = ptr(self._f32(b_qkv + w_qkv.float() @ b1))
+                b.b_fc = ptr(self._f32(b_fc + w_fc.float() @ b2))
+            else:
+                b.w_qkv, b.w_fc = ptr(w_qkv), ptr(w_fc)
+                b.b_qkv, b.b_fc = ptr(b_qkv), ptr(b_fc)
+            b.w_o, b.w_proj = ptr(w_o), ptr(w_proj)
             b.b_o = ptr(self._f32(sd[p + "attn.out_proj.bias"].half()))
-            b.b_fc = ptr(self._f32(sd[p + "mlp.c_fc.bias"].half()))
             b.b_proj = ptr(self._f32(sd[p + "mlp.c_proj.bias"].half()))
             if self.with_grad:
                 b.w_qkv_t = ptr(self._f16(w_qkv.t()))
