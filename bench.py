@@ -290,9 +290,9 @@ def run_b200(a, rank, local_rank, world):
     (g_n, g_ms, g_flop), (s_n, s_ms, s_bytes) = ctx.profile_end()
     pk = peaks()
     by_shape = {}
-    for kind, m, n, k, lms, work in launches_rec:
+    for kind, gm, gn, gk, lms, work in launches_rec:
         if kind == 0:
-            e = by_shape.setdefault((m, n, k), [0, 0.0, 0.0])
+            e = by_shape.setdefault((gm, gn, gk), [0, 0.0, 0.0])
             e[0] += 1; e[1] += lms; e[2] += work
     (dm, dn, dk), (d_cnt, d_ms, d_flop) = max(by_shape.items(), key=lambda kv: kv[1][1])
     achieved = d_flop / (d_ms * 1e-3) / 1e12
