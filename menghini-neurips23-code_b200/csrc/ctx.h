@@ -84,9 +84,8 @@ int gb_make_tmap_2d_f16(gb_ctx* c, CUtensorMap* out, const void* ptr, uint64_t r
 
 // LayerNorm-folding extras of a GEMM launch (see GemmParams): statistics consumed / produced.
 struct gb_gemm_ln {
-  const float* ln_part = nullptr;  // [ln_parts][M][2] (Σx, Σx²) of A's rows → fold LayerNorm into this GEMM
-  int ln_parts = 0;
-  const float* col_sum = nullptr;  // [N]
+  const float* ln_stats = nullptr;  // [M][2] (μ·rstd, rstd) of A's rows → fold LayerNorm into this GEMM
+  const float* col_sum = nullptr;   // [N]
   float* stats_out = nullptr;      // [N/128][M][2] partial statistics of the output rows
 };
 

@@ -79,13 +79,13 @@ int gb_launch_gemm(gb_ctx* c, const void* A, int lda, const void* W, int ldw, co
   p.act = act; p.out_f32 = out_f32;
   if (getenv("GB_DEBUG_NOSTORE")) p.out_f32 = 2;  // experiment: skip the epilogue's global stores
   p.aux = reinterpret_cast<__half*>(aux);
-  p.ln_part = nullptr; p.ln_parts = 0; p.ln_dim = K; p.col_sum = nullptr; p.stats_out = nullptr;
+  p.ln_stats = nullptr; p.col_sum = nullptr; p.stats_out = nullptr;
   if (ln) {
     if (out_f32 || N % 256 != 0)
       return gb_fail(c, GB_ERR_ARG, "gemm: LayerNorm folding needs fp16 output and N %% 256 == 0");
-    if ((ln->ln_part != nullptr) != (ln->col_sum != nullptr) || (ln->ln_part && ln->ln_parts <= 0))
+    if ((ln->ln_stats != nullptr) != (ln->col_sum != nullptr))
       return gb_fail(c, GB_ERR_ARG, "gemm: inconsistent LayerNorm folding arguments");
-    p.ln_part = ln->ln_part; p.ln_parts = ln->ln_parts; p.col_sum = ln->col_sum;
+    p.ln_stats = ln->ln_stats; p.col_sum = ln->col_sum;
     p.stats_out = ln->stats_out;
   }
   if (act == 2 && !aux) return gb_fail(c, GB_ERR_ARG, "gemm: act 2 needs aux");

@@ -37,10 +37,8 @@ struct GemmParams {
   // LayerNorm folded into the contraction (CTA-pair kernel, fp16 output only).  With W' = W∘γ,
   // s_n = Σ_k W'[n,k] and b' = b + W·β:   LN(x)·Wᵀ + b = rstd_r·(x·W'ᵀ − μ_r·s_n) + b'_n,
   // so A is the raw residual stream and the row statistics are applied in the epilogue.
-  const float* ln_part;  // [ln_parts][M][2] partial (Σx, Σx²) of each row of A, or nullptr
-  int ln_parts;
-  int ln_dim;            // row length D of the normalised rows (= K)
-  const float* col_sum;  // s_n, [N]
+  const float* ln_stats;  // [M][2] = (μ·rstd, rstd) of each row of A, or nullptr
+  const float* col_sum;   // s_n, [N]
   // partial (Σ, Σ²) of every OUTPUT row over this warp's 128 columns, [N/128][M][2], or nullptr: the
   // statistics the next LayerNorm needs, produced where the rows are written.
   float* stats_out;
@@ -302,8 +300,8 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 template <typename WaitAcc>
 __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, const CUtensorMap* tmC,
                                                        uint8_t* slabs, uint32_t tmem_acc, int m0,
-                                                       int n_base, int warp, int lane,
-                                                       WaitAcc&& wait_acc) {
+                                                       int n_base, int warp, int lane, float2& ln_st,
+                                                       int next_m0, WaitAcc&& wait_acc) {
   constexpr int BN = 256;
   const int q = warp & 3;
   const int half = (warp - 4) >> 2;
@@ -320,19 +318,14 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
 #pragma unroll
     for (int j = 0; j < 4; ++j) pre[j] = r4[j];
   }
-  // row statistics of the folded LayerNorm: partial sums are combined in a fixed order (deterministic)
-  float ln_mean = 0.f, ln_rstd = 1.f;
-  const bool ln = p.ln_part != nullptr;
-  if (ln && row_ok) {
-    float sx = 0.f, sq = 0.f;
-    for (int i = 0; i < p.ln_parts; ++i) {
-      const float2 t = *reinterpret_cast<const float2*>(p.ln_part + ((size_t)i * p.M + row) * 2);
-      sx += t.x;
-      sq += t.y;
-    }
-    const float inv_d = 1.0f / (float)p.ln_dim;
-    ln_mean = sx * inv_d;
-    ln_rstd = rsqrtf(fmaxf(sq * inv_d - ln_mean * ln_mean, 0.f) + 1e-5f);
+  // row statistics of the folded LayerNorm: (μ·rstd, rstd) of this tile's row were fetched while the
+  // previous tile was processed; the next tile's are requested now
+  const bool ln = p.ln_stats != nullptr;
+  const float ln_mr = ln_st.x, ln_rstd = ln_st.y;
+  float2 ln_next = make_float2(0.f, 1.f);
+  if (ln && next_m0 >= 0) {
+    const int nrow = next_m0 + q * 32 + lane;
+    if (nrow < p.M) ln_next = *reinterpret_cast<const float2*>(p.ln_stats + (size_t)nrow * 2);
   }
   float st_sum = 0.f, st_sq = 0.f;
   wait_acc();
@@ -362,11 +355,11 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
       const float4* s4 = reinterpret_cast<const float4*>(p.col_sum + col0);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 ss = __ldg(s4 + j);
-        f[4 * j + 0] = (f[4 * j + 0] - ln_mean * ss.x) * ln_rstd;
-        f[4 * j + 1] = (f[4 * j + 1] - ln_mean * ss.y) * ln_rstd;
-        f[4 * j + 2] = (f[4 * j + 2] - ln_mean * ss.z) * ln_rstd;
-        f[4 * j + 3] = (f[4 * j + 3] - ln_mean * ss.w) * ln_rstd;
+        const float4 ss = __ldg(s4 + j);  // rstd·(acc − μ·s_n) = acc·rstd − (μ·rstd)·s_n
+        f[4 * j + 0] = fmaf(f[4 * j + 0], ln_rstd, -ln_mr * ss.x);
+        f[4 * j + 1] = fmaf(f[4 * j + 1], ln_rstd, -ln_mr * ss.y);
+        f[4 * j + 2] = fmaf(f[4 * j + 2], ln_rstd, -ln_mr * ss.z);
+        f[4 * j + 3] = fmaf(f[4 * j + 3], ln_rstd, -ln_mr * ss.w);
       }
     }
     if (p.bias != nullptr) {
@@ -447,6 +440,7 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
   if (p.stats_out != nullptr && row_ok)
     *reinterpret_cast<float2*>(p.stats_out + ((size_t)(n0 >> 7) * p.M + row) * 2) =
         make_float2(st_sum, st_sq);
+  ln_st = ln_next;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -573,17 +567,24 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps, both CTAs) =====================
     int it = 0;
+    float2 ln_st = make_float2(0.f, 1.f);
+    if (p.ln_stats != nullptr && cluster_id < num_tiles) {
+      const int r = (cluster_id / n_tiles) * 2 * kBM + rank * kBM + (warp & 3) * 32 + lane;
+      if (r < p.M) ln_st = *reinterpret_cast<const float2*>(p.ln_stats + (size_t)r * 2);
+    }
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int m0 = (tile / n_tiles) * 2 * kBM + rank * kBM;
       const int n0 = (tile % n_tiles) * BN;
+      const int next = tile + num_clusters;
+      const int next_m0 = next < num_tiles ? (next / n_tiles) * 2 * kBM + rank * kBM : -1;
       if (p.out_f32)
         gemm_epilogue_tile<BN>(p, tmem_base + as * BN, m0, n0, warp, lane,
                                [&]() { mbar_wait(&tfull_bar[as], aphase); });
       else
         gemm_epilogue_tile_tma(p, &tmC, smem_slabs + (warp - 4) * 8192, tmem_base + as * BN, m0, n0,
-                               warp, lane, [&]() { mbar_wait(&tfull_bar[as], aphase); });
+                               warp, lane, ln_st, next_m0, [&]() { mbar_wait(&tfull_bar[as], aphase); });
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);

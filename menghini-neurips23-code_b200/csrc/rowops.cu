@@ -194,10 +194,14 @@ vit_assemble_lnpre_kernel(const __half* __restrict__ patch, const float* __restr
     }
     *reinterpret_cast<uint4*>(x + (size_t)warp * D + col) = u;
   }
-  // (Σ, Σ²) of the stored row: the statistics of the first block's folded ln_1
+  // (μ·rstd, rstd) of the stored row: the statistics of the first block's folded ln_1
   st_sum = warp_sum(st_sum);
   st_sq = warp_sum(st_sq);
-  if (stats != nullptr && lane == 0) *reinterpret_cast<float2*>(stats + (size_t)warp * 2) = make_float2(st_sum, st_sq);
+  if (stats != nullptr && lane == 0) {
+    const float m2 = st_sum * (1.0f / D);
+    const float r2 = rsqrtf(fmaxf(st_sq * (1.0f / D) - m2 * m2, 0.f) + eps);
+    *reinterpret_cast<float2*>(stats + (size_t)warp * 2) = make_float2(m2 * r2, r2);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -251,7 +255,11 @@ text_assemble_kernel(const int32_t* __restrict__ ids, int ld_ids, const __half* 
   }
   st_sum = warp_sum(st_sum);
   st_sq = warp_sum(st_sq);
-  if (stats != nullptr && lane == 0) *reinterpret_cast<float2*>(stats + (size_t)warp * 2) = make_float2(st_sum, st_sq);
+  if (stats != nullptr && lane == 0) {
+    const float m2 = st_sum * (1.0f / D);
+    const float r2 = rsqrtf(fmaxf(st_sq * (1.0f / D) - m2 * m2, 0.f) + 1e-5f);
+    *reinterpret_cast<float2*>(stats + (size_t)warp * 2) = make_float2(m2 * r2, r2);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -448,6 +456,24 @@ scale_f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, 
   }
 }
 
+// Combines the per-128-column partial (Σ, Σ²) pairs the residual GEMMs emit, in a fixed order, into
+// the (μ·rstd, rstd) pair per row that the LayerNorm-folded GEMM epilogue consumes.
+__global__ void __launch_bounds__(256)
+ln_finalize_kernel(const float* __restrict__ parts, int nparts, int M, float inv_d, float eps,
+                   float* __restrict__ out) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= M) return;
+  float sx = 0.f, sq = 0.f;
+  for (int i = 0; i < nparts; ++i) {
+    const float2 t = *reinterpret_cast<const float2*>(parts + ((size_t)i * M + row) * 2);
+    sx += t.x;
+    sq += t.y;
+  }
+  const float mean = sx * inv_d;
+  const float rstd = rsqrtf(fmaxf(sq * inv_d - mean * mean, 0.f) + eps);
+  *reinterpret_cast<float2*>(out + (size_t)row * 2) = make_float2(mean * rstd, rstd);
+}
+
 inline int warps_grid(long long rows) { return (int)((rows * 32 + 255) / 256); }
 
 }  // namespace
@@ -555,6 +581,14 @@ int gb_launch_scale_f32_to_f16(gb_ctx* c, const float* in, void* out, size_t n, 
   if (n == 0) return GB_OK;
   const size_t threads = (n + 3) / 4;
   scale_f32_to_f16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(in, (__half*)out, n, scale);
+  GB_LAUNCH_CHECK(c);
+  return GB_OK;
+}
+
+int gb_launch_ln_finalize(gb_ctx* c, const float* parts, int nparts, int M, int D, float* out,
+                          cudaStream_t st) {
+  if (M <= 0) return GB_OK;
+  ln_finalize_kernel<<<(M + 255) / 256, 256, 0, st>>>(parts, nparts, M, 1.0f / D, 1e-5f, out);
   GB_LAUNCH_CHECK(c);
   return GB_OK;
 }

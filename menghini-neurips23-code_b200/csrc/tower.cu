@@ -31,6 +31,8 @@ int gb_launch_vit_assemble(gb_ctx* c, const void* patch, const float* cls, const
 int gb_launch_text_assemble(gb_ctx* c, const int32_t* ids, int ld_ids, const void* tok_emb,
                             const float* pos, const float* prefix, int P, void* x, int C, int Lt,
                             cudaStream_t st, float* stats);
+int gb_launch_ln_finalize(gb_ctx* c, const float* parts, int nparts, int M, int D, float* out,
+                          cudaStream_t st);
 int gb_launch_l2norm512(gb_ctx* c, const float* x, void* y16, float* y32, int rows, cudaStream_t st);
 int gb_launch_prefix_grad(gb_ctx* c, const void* dx, int L, int S, int P, int D, const float* prefix,
                           const float* gamma, int ln_pre, float inv_scale, float* dprefix,
@@ -86,13 +88,14 @@ struct Tape {
 // place; with a tape layer l reads tape.x0(l) and leaves its output in tape.x0(l+1) / x_final.
 // When the block table carries LayerNorm-folded weights (s_qkv / s_fc non-null) ln_1 and ln_2 are not
 // separate passes: the in-proj / c_fc GEMMs read the raw residual stream and apply the row statistics
-// in their epilogue, and the two residual GEMMs emit the (Σ, Σ²) partials of the rows they write.
-// st_a / st_b: [D/128][M][2] floats each; st_a holds the statistics of x on entry (1 part).
+// in their epilogue, and the two residual GEMMs emit the (Σ, Σ²) partials of the rows they write,
+// which a tiny kernel turns into (μ·rstd, rstd) per row.
+// st_fin: [M][2] (μ·rstd, rstd) of the current residual stream (valid for x on entry);
+// st_part: [D/128][M][2] scratch for the partial sums.
 int run_blocks(gb_ctx* c, const gb_tower* t, int S, int L, int causal, void* x, const Tape* tape,
-               void* h, void* qkv_ws, void* a, void* g, float* st_a, float* st_b, cudaStream_t st) {
+               void* h, void* qkv_ws, void* a, void* g, float* st_fin, float* st_part, cudaStream_t st) {
   const int D = t->width, M = S * L;
   int rc;
-  int parts_in = 1;  // partial-sum pairs describing the rows of the current residual stream
   for (int l = 0; l < t->layers; ++l) {
     const gb_block_weights& w = t->blocks[l];
     void* x0 = tape ? tape->x0(l) : x;
@@ -100,18 +103,19 @@ int run_blocks(gb_ctx* c, const gb_tower* t, int S, int L, int causal, void* x, 
     void* x2 = tape ? (l + 1 < t->layers ? tape->x0(l + 1) : tape->x_final(t->layers)) : x;
     void* qkv = tape ? tape->qkv(l) : qkv_ws;
     const bool fold = w.s_qkv != nullptr && w.s_fc != nullptr;
+    gb_gemm_ln emit; emit.stats_out = st_part;
     if (fold) {
-      gb_gemm_ln ln1; ln1.ln_part = st_a; ln1.ln_parts = parts_in; ln1.col_sum = w.s_qkv;
+      gb_gemm_ln ln1; ln1.ln_stats = st_fin; ln1.col_sum = w.s_qkv;
       if ((rc = gb_launch_gemm(c, x0, D, w.w_qkv, D, w.b_qkv, nullptr, 0, qkv, 3 * D, M, 3 * D, D, 0, 0, st, nullptr, &ln1))) return rc;
     } else {
       if ((rc = gb_launch_layernorm(c, x0, D, nullptr, 1, w.ln1_g, w.ln1_b, h, D, M, D, 0, st))) return rc;
       if ((rc = gb_launch_gemm(c, h, D, w.w_qkv, D, w.b_qkv, nullptr, 0, qkv, 3 * D, M, 3 * D, D, 0, 0, st))) return rc;
     }
     if ((rc = gb_launch_attn_fwd(c, qkv, a, S, L, D, causal, st))) return rc;
-    gb_gemm_ln so; so.stats_out = fold ? st_b : nullptr;
-    if ((rc = gb_launch_gemm(c, a, D, w.w_o, D, w.b_o, x0, D, x1, D, M, D, D, 0, 0, st, nullptr, fold ? &so : nullptr))) return rc;
+    if ((rc = gb_launch_gemm(c, a, D, w.w_o, D, w.b_o, x0, D, x1, D, M, D, D, 0, 0, st, nullptr, fold ? &emit : nullptr))) return rc;
     if (fold) {
-      gb_gemm_ln ln2; ln2.ln_part = st_b; ln2.ln_parts = D / 128; ln2.col_sum = w.s_fc;
+      if ((rc = gb_launch_ln_finalize(c, st_part, D / 128, M, D, st_fin, st))) return rc;
+      gb_gemm_ln ln2; ln2.ln_stats = st_fin; ln2.col_sum = w.s_fc;
       if ((rc = gb_launch_gemm(c, x1, D, w.w_fc, D, w.b_fc, nullptr, 0, g, 4 * D, M, 4 * D, D, 1, 0, st,
                                tape ? tape->f(l) : nullptr, &ln2))) return rc;
     } else {
@@ -119,9 +123,9 @@ int run_blocks(gb_ctx* c, const gb_tower* t, int S, int L, int causal, void* x, 
       if ((rc = gb_launch_gemm(c, h, D, w.w_fc, D, w.b_fc, nullptr, 0, g, 4 * D, M, 4 * D, D, 1, 0, st,
                                tape ? tape->f(l) : nullptr))) return rc;
     }
-    gb_gemm_ln sp; sp.stats_out = fold ? st_a : nullptr;
-    if ((rc = gb_launch_gemm(c, g, 4 * D, w.w_proj, 4 * D, w.b_proj, x1, D, x2, D, M, D, 4 * D, 0, 0, st, nullptr, fold ? &sp : nullptr))) return rc;
-    parts_in = D / 128;
+    const bool more = fold && l + 1 < t->layers;
+    if ((rc = gb_launch_gemm(c, g, 4 * D, w.w_proj, 4 * D, w.b_proj, x1, D, x2, D, M, D, 4 * D, 0, 0, st, nullptr, more ? &emit : nullptr))) return rc;
+    if (more && (rc = gb_launch_ln_finalize(c, st_part, D / 128, M, D, st_fin, st))) return rc;
   }
   return GB_OK;
 }

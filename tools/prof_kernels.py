@@ -61,3 +61,24 @@ if what in ("attn", "all"):
         qkv = torch.randn(B * L, 3 * D, device="cuda").half()
         ms = timeit(lambda: ctx.attention_fwd(qkv, B, L, D, causal))
         print(f"attn fwd B={B} L={L}: {ms*1e3:.1f} us  ({B*L*D*2*4/ms/1e6:.0f} GB/s algorithmic)", flush=True)
+
+if what in ("vit", "all"):
+    eng_mod = importlib.import_module(PKG + ".engine")
+    synthetic = importlib.import_module(PKG + ".synthetic")
+    sd = synthetic.synthetic_state_dict(1234)
+    img = torch.randn(1024, 3, 224, 224, device="cuda")
+    for fold in (False, True, False, True):
+        eng = eng_mod.Engine(sd, "cuda:0", fold_ln=fold)
+        ms = timeit(lambda: eng.vit_forward(img, None, want_feat=True, want_featn=True), n=10, warm=3)
+        ctx.profile_begin()
+        eng.vit_forward(img, None, want_feat=True, want_featn=True)
+        recs = ctx.profile_launches()
+        ctx.profile_end()
+        shapes = {}
+        for kind, m, n, k, lms, work in recs:
+            if kind == 0:
+                e = shapes.setdefault((m, n, k), [0, 0.0])
+                e[0] += 1; e[1] += lms
+        print(f"vit_forward B=1024 fold_ln={fold}: {ms:.3f} ms  ({1024/ms*1e3:.0f} img/s)  " +
+              "  ".join(f"{s}: {v[1]/v[0]*1e3:.0f}us" for s, v in sorted(shapes.items())), flush=True)
+        del eng
