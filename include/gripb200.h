@@ -40,6 +40,9 @@ const char* gb_last_error(gb_ctx* ctx);
 /* number of kernels launched through this ctx so far (bench.py's gpu_launches) */
 uint64_t gb_launch_count(gb_ctx* ctx);
 const char* gb_version(void);
+/* Cap the persistent GEMM grids at `sms` SMs (0 = all).  Leaves a few SMs free for small kernels of a
+ * second stream (e.g. the text tower running beside the image tower). */
+int gb_set_sm_limit(gb_ctx* ctx, int sms);
 
 /* Per-launch CUDA-event timing of the two roofline kernels, for bench.py: between _begin and _end
  * every tcgen05 GEMM launch (kind 0, work = 2*M*N*K FLOP) and every similarity/softmax/argmax launch

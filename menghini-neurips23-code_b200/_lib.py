@@ -57,6 +57,7 @@ _SIGNATURES = {
     "gb_last_error": (c_char_p, [P]),
     "gb_launch_count": (c_uint64, [P]),
     "gb_version": (c_char_p, []),
+    "gb_set_sm_limit": (c_int, [P, c_int]),
     "gb_profile_begin": (c_int, [P]),
     "gb_profile_end": (c_int, [P, POINTER(ProfileStats), c_int]),
     "gb_profile_launches": (c_int, [P, POINTER(ProfileLaunch), c_int]),
@@ -151,6 +152,10 @@ class Context:
     @property
     def launches(self) -> int:
         return int(self.lib.gb_launch_count(self.h))
+
+    def set_sm_limit(self, sms: int):
+        """Persistent GEMM grids use at most `sms` SMs (0 = all)."""
+        self.check(self.lib.gb_set_sm_limit(self.h, int(sms)), "gb_set_sm_limit")
 
     def profile_begin(self):
         self.check(self.lib.gb_profile_begin(self.h), "gb_profile_begin")

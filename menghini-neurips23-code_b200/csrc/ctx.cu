@@ -37,7 +37,8 @@ void gb_tower_free(gb_tower* t);
 extern "C" int gb_destroy(gb_ctx* c) {
   if (!c) return GB_ERR_ARG;
   cudaSetDevice(c->device);
-  if (c->ws) cudaFree(c->ws);
+  for (int i = 0; i < gb_ctx::kWsCount; ++i)
+    if (c->ws[i]) cudaFree(c->ws[i]);
   gb_tower_free(c->vit);
   gb_tower_free(c->text);
   delete c;
@@ -47,14 +48,20 @@ extern "C" int gb_destroy(gb_ctx* c) {
 extern "C" const char* gb_last_error(gb_ctx* c) { return c ? c->err.c_str() : "null ctx"; }
 extern "C" uint64_t gb_launch_count(gb_ctx* c) { return c ? c->launches : 0; }
 
-int gb_ws_reserve(gb_ctx* c, size_t bytes) {
-  if (bytes <= c->ws_bytes) return GB_OK;
+int gb_ws_reserve(gb_ctx* c, int slot, size_t bytes) {
+  if (bytes <= c->ws_bytes[slot]) return GB_OK;
   GB_CUDA(c, cudaDeviceSynchronize());
-  if (c->ws) GB_CUDA(c, cudaFree(c->ws));
-  c->ws = nullptr;
-  c->ws_bytes = 0;
-  GB_CUDA(c, cudaMalloc(&c->ws, bytes));
-  c->ws_bytes = bytes;
+  if (c->ws[slot]) GB_CUDA(c, cudaFree(c->ws[slot]));
+  c->ws[slot] = nullptr;
+  c->ws_bytes[slot] = 0;
+  GB_CUDA(c, cudaMalloc(&c->ws[slot], bytes));
+  c->ws_bytes[slot] = bytes;
+  return GB_OK;
+}
+
+extern "C" int gb_set_sm_limit(gb_ctx* c, int sms) {
+  if (!c || sms < 0) return GB_ERR_ARG;
+  c->sm_limit = sms;
   return GB_OK;
 }
 

@@ -25,8 +25,12 @@ struct gb_ctx {
   PFN_encodeTiled encode_tiled = nullptr;
   uint64_t launches = 0;  // kernels launched through this ctx (bench.py reports it)
   // workspace owned by the ctx (grown on demand, never inside a timed region after warm-up)
-  void* ws = nullptr;
-  size_t ws_bytes = 0;
+  // One scratch arena per independent call family, so that the image tower, the text tower and the
+  // pool scan may be in flight on different streams at the same time.
+  enum { kWsVit = 0, kWsText = 1, kWsScan = 2, kWsCount = 3 };
+  void* ws[kWsCount] = {nullptr, nullptr, nullptr};
+  size_t ws_bytes[kWsCount] = {0, 0, 0};
+  int sm_limit = 0;  // > 0: persistent GEMM grids use at most this many SMs (rounded down to pairs)
   gb_tower* vit = nullptr;
   gb_tower* text = nullptr;
   // optional per-launch timing of the two roofline kernels (bench.py): kind 0 = tcgen05 GEMM (work =
@@ -93,4 +97,5 @@ struct gb_gemm_ln {
 int gb_launch_gemm(gb_ctx* c, const void* A, int lda, const void* W, int ldw, const float* bias,
                    const void* resid, int ldr, void* out, int ldo, int M, int N, int K, int act,
                    int out_f32, cudaStream_t st, void* aux = nullptr, const struct gb_gemm_ln* ln = nullptr);
-int gb_ws_reserve(gb_ctx* c, size_t bytes);
+int gb_ws_reserve(gb_ctx* c, int slot, size_t bytes);
+inline int gb_gemm_sms(const gb_ctx* c) { return (c->sm_limit > 0 && c->sm_limit < c->num_sms) ? c->sm_limit : c->num_sms; }

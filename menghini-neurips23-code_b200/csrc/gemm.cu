@@ -17,7 +17,8 @@ static int launch_gemm_bn(gb_ctx* c, const CUtensorMap& tmA, const CUtensorMap& 
   }
   const int m_tiles = (p.M + kBM - 1) / kBM;
   const int tiles = m_tiles * (p.N / BN);
-  const int grid = tiles < c->num_sms ? tiles : c->num_sms;
+  const int sms = gb_gemm_sms(c);
+  const int grid = tiles < sms ? tiles : sms;
   {
     gb_prof_scope prof(c, st, 0, 2.0 * p.M * p.N * p.K, p.M, p.N, p.K);
     gemm_f16_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
@@ -37,7 +38,7 @@ static int launch_gemm_2cta(gb_ctx* c, const CUtensorMap& tmA, const CUtensorMap
   }
   const int m_pairs = (p.M + 2 * kBM - 1) / (2 * kBM);
   const int tiles = m_pairs * (p.N / Cfg::BN);
-  const int max_clusters = c->num_sms / 2;
+  const int max_clusters = gb_gemm_sms(c) / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   {
     gb_prof_scope prof(c, st, 0, 2.0 * p.M * p.N * p.K, p.M, p.N, p.K);

@@ -711,9 +711,9 @@ extern "C" int gb_leaderboard_update(gb_ctx* c, void* state, int C, int k, const
     return launch_replay(c, state, C, k, probs, 0, pred, rank, nullptr, row_begin, row_end, idx0, st);
   // chunked: filter against the bounds left by the previous chunk, then replay the survivors
   const LbView v = lb_view(state, C, k);
-  int rc = gb_ws_reserve(c, ((size_t)(row_end + 31) / 32) * 4 + 256);
+  int rc = gb_ws_reserve(c, gb_ctx::kWsScan, ((size_t)(row_end + 31) / 32) * 4 + 256);
   if (rc) return rc;
-  uint32_t* flags = reinterpret_cast<uint32_t*>(c->ws);
+  uint32_t* flags = reinterpret_cast<uint32_t*>(c->ws[gb_ctx::kWsScan]);
   int chunk = 4096;
   for (int r0 = row_begin; r0 < row_end;) {
     const int r1 = min(r0 + chunk, row_end);
@@ -754,10 +754,10 @@ extern "C" int gb_pseudolabel_scan(gb_ctx* c, void* state, const void* F, const 
   const int chunk_cap = 1 << 18;
   const size_t flag_bytes = (((size_t)N + 127) / 128) * 16 + 256;
   const size_t cand_bytes = probs ? 0 : (size_t)(N < chunk_cap ? ((N + 127) & ~127) : chunk_cap) * C * 4;
-  int rc = gb_ws_reserve(c, flag_bytes + cand_bytes);
+  int rc = gb_ws_reserve(c, gb_ctx::kWsScan, flag_bytes + cand_bytes);
   if (rc) return rc;
-  uint32_t* flags = reinterpret_cast<uint32_t*>(c->ws);
-  float* cand = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(c->ws) + flag_bytes);
+  uint32_t* flags = reinterpret_cast<uint32_t*>(c->ws[gb_ctx::kWsScan]);
+  float* cand = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(c->ws[gb_ctx::kWsScan]) + flag_bytes);
   int chunk = 4096;
   for (int r0 = 0; r0 < N;) {
     const int r1 = min(r0 + chunk, N);

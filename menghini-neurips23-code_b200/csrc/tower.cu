@@ -226,9 +226,9 @@ extern "C" int gb_vit_forward(gb_ctx* c, const void* img, int img_f32, const flo
     b.take(M * (D / 128) * 8); b.take(M * (D / 128) * 8);
     need = b.off;
   }
-  int rc = gb_ws_reserve(c, need);
+  int rc = gb_ws_reserve(c, gb_ctx::kWsVit, need);
   if (rc) return rc;
-  Bump b(c->ws);
+  Bump b(c->ws[gb_ctx::kWsVit]);
   void* x_ws = b.take(h2(M, D));
   void* h = b.take(h2(M, D));
   void* qkv = b.take(h2(M, 3 * D));
@@ -274,9 +274,9 @@ extern "C" int gb_vit_backward_prefix(gb_ctx* c, const float* dfeat, const float
     b.take(h2(B, 512)); b.take(h2(B, D));
     need = b.off;
   }
-  int rc = gb_ws_reserve(c, need);
+  int rc = gb_ws_reserve(c, gb_ctx::kWsVit, need);
   if (rc) return rc;
-  Bump b(c->ws);
+  Bump b(c->ws[gb_ctx::kWsVit]);
   void* dx = b.take(h2(M, D));
   void* dh = b.take(h2(M, D));
   void* dqkv = b.take(h2(M, 3 * D));
@@ -316,9 +316,9 @@ extern "C" int gb_text_forward(gb_ctx* c, const int32_t* ids, int ld_ids, const 
     b.take(M * (D / 128) * 8); b.take(M * (D / 128) * 8);
     need = b.off;
   }
-  int rc = gb_ws_reserve(c, need);
+  int rc = gb_ws_reserve(c, gb_ctx::kWsText, need);
   if (rc) return rc;
-  Bump b(c->ws);
+  Bump b(c->ws[gb_ctx::kWsText]);
   void* x_ws = b.take(h2(M, D));
   void* h = b.take(h2(M, D));
   void* qkv = b.take(h2(M, 3 * D));
@@ -364,9 +364,9 @@ extern "C" int gb_text_backward_prefix(gb_ctx* c, const float* dfeat, const int3
     b.take(h2(C, 512)); b.take(h2(C, D)); b.take((size_t)C * 4);
     need = b.off;
   }
-  int rc = gb_ws_reserve(c, need);
+  int rc = gb_ws_reserve(c, gb_ctx::kWsText, need);
   if (rc) return rc;
-  Bump b(c->ws);
+  Bump b(c->ws[gb_ctx::kWsText]);
   void* dx = b.take(h2(M, D));
   void* dh = b.take(h2(M, D));
   void* dqkv = b.take(h2(M, 3 * D));
