@@ -234,12 +234,15 @@ def run_b200(a, rank, local_rank, world):
     # Nothing is reordered across a true dependency: prefix(i) → text(i) → loss(i) ← image(i).
     overlap = not a.no_overlap
     main_stream = torch.cuda.current_stream()
-    side = torch.cuda.Stream(device=dev) if overlap else main_stream
+    side_stream = torch.cuda.Stream(device=dev)
+    mode = {"overlap": overlap}
     if overlap and a.sm_limit > 0:
         ctx.set_sm_limit(a.sm_limit)
 
     def step(img, labels):
         s = state["step"]
+        overlap = mode["overlap"]
+        side = side_stream if overlap else main_stream
         with torch.no_grad():
             feat, featn, _ = eng.vit_forward(img, None, want_feat=True, want_featn=True)
         if overlap:
@@ -277,8 +280,7 @@ def run_b200(a, rank, local_rank, world):
         return loss
 
     def join():
-        if overlap:
-            main_stream.wait_stream(side)
+        main_stream.wait_stream(side_stream)
 
     def timed(fn, steps):
         if world > 1:
@@ -311,11 +313,18 @@ def run_b200(a, rank, local_rank, world):
     # ---- roofline: per-launch CUDA-event timing (on the launching stream) of every tcgen05 GEMM and sim
     # launch in 3 more steps of the same loop; the dominant kernel launch = the GEMM shape with the
     # largest total time
+    # (issued on ONE stream with the SM cap lifted, so a launch's event pair times that kernel alone)
+    join()
+    mode["overlap"] = False
+    ctx.set_sm_limit(0)
     ctx.profile_begin()
     for i in range(3):
         step(dev_img[i % 2], dev_lab[i % 2])
     launches_rec = ctx.profile_launches()
     (g_n, g_ms, g_flop), (s_n, s_ms, s_bytes) = ctx.profile_end()
+    mode["overlap"] = overlap
+    if overlap and a.sm_limit > 0:
+        ctx.set_sm_limit(a.sm_limit)
     pk = peaks()
     by_shape = {}
     for kind, gm, gn, gk, lms, work in launches_rec:
@@ -373,6 +382,8 @@ def run_b200(a, rank, local_rank, world):
             dev_img[b].copy_(host[b], non_blocking=True)
             dev_lab[b].copy_(host_labels[b], non_blocking=True)
             copied[b].record(copy_stream)
+
+    side = side_stream if overlap else main_stream
 
     def e2e_step(i):
         b = i % 2
