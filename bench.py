@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true",
                     help="run the text chain on the image tower's stream instead of beside it")
-    ap.add_argument("--sm-limit", type=int, default=140,
+    ap.add_argument("--sm-limit", type=int, default=144,
                     help="SMs the persistent image-tower GEMMs may use while the text chain runs beside them")
     return ap.parse_args()
 
