@@ -109,8 +109,9 @@ __device__ __forceinline__ void scores_softmax(const __half* Qs, const __half* K
       const int col = c0 + e;
       const bool oka = col < L && !(causal && col > ra);
       const bool okb = col < L && !(causal && col > rb);
-      s[nt][e] = oka ? s[nt][e] * 0.125f : -INFINITY;
-      s[nt][2 + e] = okb ? s[nt][2 + e] * 0.125f : -INFINITY;
+      // scores in log2 units: (q·k / 8)·log2(e), so the soft-max needs a bare ex2
+      s[nt][e] = oka ? s[nt][e] * 0.18033688011112042f : -INFINITY;
+      s[nt][2 + e] = okb ? s[nt][2 + e] * 0.18033688011112042f : -INFINITY;
       m0 = fmaxf(m0, s[nt][e]);
       m1 = fmaxf(m1, s[nt][2 + e]);
     }
@@ -124,8 +125,8 @@ __device__ __forceinline__ void scores_softmax(const __half* Qs, const __half* K
   for (int nt = 0; nt < NT; ++nt) {
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      s[nt][e] = __expf(s[nt][e] - m0);       // col 0 is never masked → m finite
-      s[nt][2 + e] = __expf(s[nt][2 + e] - m1);
+      s[nt][e] = fast_exp2(s[nt][e] - m0);       // col 0 is never masked → m finite
+      s[nt][2 + e] = fast_exp2(s[nt][2 + e] - m1);
       l0 += s[nt][e];
       l1 += s[nt][2 + e];
     }

@@ -443,6 +443,14 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
   ln_st = ln_next;
 }
 
+// Out-of-line copy of the direct-store epilogue for the CTA-pair kernel's rare fp32-output case (the
+// final feature projections), so that its register appetite does not constrain the fp16 hot path.
+__device__ __noinline__ void gemm_epilogue_tile_direct_256(const GemmParams& p, uint32_t tmem_acc,
+                                                           int m0, int n_base, int warp, int lane,
+                                                           uint64_t* bar, uint32_t phase) {
+  gemm_epilogue_tile<256>(p, tmem_acc, m0, n_base, warp, lane, [&]() { mbar_wait(bar, phase); });
+}
+
 // -------------------------------------------------------------------------------------------------
 // CTA-pair variant (cta_group::2), N % 256 == 0: a 2-CTA cluster computes 256 x 256 output tiles.
 // CTA r of the pair stages rows [256·mp + 128·r, +128) of A and rows [n0 + 128·r, +128) of W per
@@ -580,8 +588,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
       const int next = tile + num_clusters;
       const int next_m0 = next < num_tiles ? (next / n_tiles) * 2 * kBM + rank * kBM : -1;
       if (p.out_f32)
-        gemm_epilogue_tile<BN>(p, tmem_base + as * BN, m0, n0, warp, lane,
-                               [&]() { mbar_wait(&tfull_bar[as], aphase); });
+        gemm_epilogue_tile_direct_256(p, tmem_base + as * BN, m0, n0, warp, lane, &tfull_bar[as], aphase);
       else
         gemm_epilogue_tile_tma(p, &tmC, smem_slabs + (warp - 4) * 8192, tmem_base + as * BN, m0, n0,
                                warp, lane, ln_st, next_m0, [&]() { mbar_wait(&tfull_bar[as], aphase); });
