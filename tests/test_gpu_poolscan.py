@@ -201,3 +201,35 @@ def test_large_pool_properties(eng_mod, sim):
     lb3 = eng_mod.Leaderboard(C, k, "cuda:0")
     lb3.update(probs, pred, rank, prefilter=False)
     assert lb3.result() == lb.result()
+
+
+def test_grip_schedule_with_learned_prompts(pkg):
+    """GRIP refresh (methods/semi_supervised_learning/pseudo_iterative.py:62-75,113-125 schedule;
+    assign_pseudo_labels of textual_fpl.py:195-283): k grows from N/(10·C) towards N/C over the iterations
+    and the class decision is argmax(LOGITS) (mode 1).  utils.scan_features against the oracle replay of
+    the device probabilities at every k, including the k == 10000000 "label everything" branch."""
+    U = importlib.import_module("menghini-neurips23-code_b200.utils")
+    ctx = pkg.Context.get(0)
+
+    class _Eng:  # scan_features only needs these three members of an Engine
+        device = torch.device("cuda", 0)
+        logit_scale_exp = 100.0
+
+        def sim_softmax_argmax(self, F, T, scale=None, mode=0, want_probs=False):
+            return _Sim(pkg, None)(F, T, 100.0 if scale is None else scale, mode=mode, probs=want_probs)
+
+    N, C = 9000, 18  # RESICS45 TRZSL: 18 unseen classes
+    f, t = synth.pool(N, C, peaked=0.08)
+    F, T = f.half().cuda(), t.half().cuda()
+    paths = [f"img_{i:06d}.jpg" for i in np.random.RandomState(5).permutation(N)]
+    class_ids = [40 - 2 * j for j in range(C)]
+    pred, _, probs = _Sim(pkg, None)(F, T, 100.0, mode=1)
+    rank = U.path_ranks(paths).numpy()
+    num_iter = 10
+    for it in (1, 4, 10):
+        k = int(it * (N // num_iter) / C)
+        idx, lab = U.scan_features(_Eng(), F, T, k, paths, class_ids, mode=1)
+        w_idx, w_lab = leaderboard_ref.leaderboard(probs.cpu().numpy(), pred.cpu().numpy(), k, rank, class_ids)
+        assert idx == w_idx and lab == w_lab, k
+    idx, lab = U.scan_features(_Eng(), F, T, leaderboard_ref.ALL_UNLABELED_K, paths, class_ids, mode=1)
+    assert idx == list(range(N)) and lab == [class_ids[j] for j in pred.cpu().tolist()]
