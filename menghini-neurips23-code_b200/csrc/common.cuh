@@ -282,15 +282,28 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+// 1/x on the SFU, flush-to-zero, no range fix-up (callers keep x in [1, inf])
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// 16-byte store to a shared-memory address (a generic-pointer store would compile to ST.E + a
+// run-time address-space check)
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
 __device__ __forceinline__ float quick_gelu(float x) {
   // x * sigmoid(1.702 x)   (openai/CLIP QuickGELU) = x / (1 + 2^(−1.702·log2(e)·x)); ex2.approx +
   // rcp.approx: ≈1e-7 relative, far below the fp16 rounding of the stored activation; branch-free
-  return __fdividef(x, 1.0f + fast_exp2(-2.4554669595930157f * x));
+  return x * fast_rcp(1.0f + fast_exp2(-2.4554669595930157f * x));  // 2^t = inf → rcp = 0 → −0
 }
 
 __device__ __forceinline__ float quick_gelu_grad(float x) {
   // d/dx [x·σ(1.702x)] = σ + 1.702·x·σ·(1−σ)
-  const float s = __fdividef(1.0f, 1.0f + fast_exp2(-2.4554669595930157f * x));
+  const float s = fast_rcp(1.0f + fast_exp2(-2.4554669595930157f * x));
   return s + 1.702f * x * s * (1.0f - s);
 }
 

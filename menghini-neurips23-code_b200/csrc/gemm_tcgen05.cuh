@@ -342,6 +342,7 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
       for (int j = 0; j < 4; ++j) pre_next[j] = r4[j];
     }
     uint8_t* slab = slabs + ((c >> 1) & 1) * 4096;
+    const uint32_t slab_s = smem_u32(slab);
     if ((c & 1) == 0) {
       // the store that last used this slab (previous tile) must be done reading it
       if (lane == 0) tma_store_wait_read<1>();
@@ -424,7 +425,7 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
         }
       }
       const int chunk = (c & 1) * 4 + j;
-      *reinterpret_cast<uint4*>(slab + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = o;
+      sts128(slab_s + lane * 128 + ((chunk ^ (lane & 7)) << 4), o);
     }
     if (c & 1) {
       fence_proxy_async();  // generic-proxy writes → visible to the TMA engine
