@@ -8,8 +8,9 @@ Weights: there is no network in this environment, so `load` takes them from (in 
 `state_dict=` argument, the file named by $GRIPB200_CLIP_WEIGHTS (a torch-saved state_dict in
 openai/CLIP layout, e.g. `torch.jit.load('ViT-B-32.pt').state_dict()`), or — when
 $GRIPB200_SYNTHETIC_SEED is set — seeded random-init weights of the ViT-B/32 architecture.
-Tokeniser: the BPE vocabulary file is third-party data that is not redistributable here; when
-$GRIPB200_BPE_VOCAB is absent a deterministic word-hash tokenizer with the same framing
+Tokeniser: `clip.tokenize` is openai/CLIP's byte-pair tokenizer (simple_tokenizer.py) when
+$GRIPB200_BPE_VOCAB names its vocabulary file `bpe_simple_vocab_16e6.txt.gz` (third-party data, not
+available offline); without it a deterministic word-hash tokenizer with the same framing
 ([SOT] … [EOT], zero padded, EOT = arg-max id) is used and says so once.
 """
 from __future__ import annotations
@@ -84,8 +85,9 @@ def tokenize(texts, context_length: int = 77, truncate: bool = False):
     global _warned
     if isinstance(texts, str):
         texts = [texts]
-    if os.environ.get("GRIPB200_BPE_VOCAB"):
-        raise GripB200Error("BPE vocabulary loading is not wired in this build")
+    vocab = os.environ.get("GRIPB200_BPE_VOCAB")
+    if vocab:
+        return _tokenize_bpe(texts, context_length, truncate, vocab)
     if not _warned:
         warnings.warn("clip.tokenize: BPE vocabulary unavailable offline, using the word-hash tokenizer")
         _warned = True
@@ -97,6 +99,29 @@ def tokenize(texts, context_length: int = 77, truncate: bool = False):
                 raise RuntimeError(f"Input {text} is too long for context length {context_length}")
             toks = toks[:context_length]
             toks[-1] = EOT
+        out[i, :len(toks)] = torch.tensor(toks)
+    return out
+
+
+_bpe = {}
+
+
+def _tokenize_bpe(texts, context_length, truncate, vocab_path):
+    """openai/CLIP clip.tokenize: [SOT] + BPE(text) + [EOT], zero padded to context_length."""
+    from .simple_tokenizer import SimpleTokenizer
+
+    tok = _bpe.get(vocab_path)
+    if tok is None:
+        tok = _bpe[vocab_path] = SimpleTokenizer(vocab_path)
+    sot, eot = tok.encoder["<|startoftext|>"], tok.encoder["<|endoftext|>"]
+    out = torch.zeros(len(texts), context_length, dtype=torch.long)
+    for i, text in enumerate(texts):
+        toks = [sot] + tok.encode(text) + [eot]
+        if len(toks) > context_length:
+            if not truncate:
+                raise RuntimeError(f"Input {text} is too long for context length {context_length}")
+            toks = toks[:context_length]
+            toks[-1] = eot
         out[i, :len(toks)] = torch.tensor(toks)
     return out
 

@@ -1,0 +1,51 @@
+"""One-call installation on the reference's import seam.
+
+    import importlib; importlib.import_module("menghini-neurips23-code_b200.dropin").install()
+
+After install(), code written against the reference resolves
+    import clip / from clip import clip / clip.model.Transformer      → the B200 `clip` stand-in
+    from models import CustomTextEncoder, …, UPTModel                  → the B200 classes
+    utils.pseudolabel_top_k / utils.clip_pseudolabels.compute_pseudo_labels
+                                                                        → the fused pool scan
+The reference's own `utils` package is only patched when it is importable (it pulls pandas / scipy /
+accelerate); otherwise a minimal `utils` exposing the hot function is registered.
+"""
+from __future__ import annotations
+
+import importlib
+import sys
+import types
+
+_PKG = __name__.rsplit(".", 1)[0]
+
+
+def install(patch_reference_utils: bool = True):
+    clip = importlib.import_module(_PKG + ".clip")
+    models = importlib.import_module(_PKG + ".models")
+    utils_b200 = importlib.import_module(_PKG + ".utils")
+    sys.modules["clip"] = clip
+    sys.modules["clip.clip"] = clip
+    sys.modules["clip.model"] = importlib.import_module(_PKG + ".clip.model")
+    sys.modules["models"] = models
+    ref_utils = None
+    if patch_reference_utils:
+        try:
+            ref_utils = importlib.import_module("utils")
+            if getattr(ref_utils, "__name__", "") != "utils" or not hasattr(ref_utils, "pseudolabel_top_k"):
+                ref_utils = None
+        except Exception:
+            ref_utils = None
+    if ref_utils is not None:
+        ref_utils.pseudolabel_top_k = utils_b200.pseudolabel_top_k
+        sub = sys.modules.get("utils.clip_pseudolabels")
+        if sub is not None:
+            sub.pseudolabel_top_k = utils_b200.pseudolabel_top_k
+            sub.compute_pseudo_labels = utils_b200.compute_pseudo_labels
+    else:
+        shim = types.ModuleType("utils")
+        shim.pseudolabel_top_k = utils_b200.pseudolabel_top_k
+        shim.compute_pseudo_labels = utils_b200.compute_pseudo_labels
+        shim.clip_pseudolabels = importlib.import_module(_PKG + ".utils.clip_pseudolabels")
+        sys.modules["utils"] = shim
+        sys.modules["utils.clip_pseudolabels"] = shim.clip_pseudolabels
+    return {"clip": clip, "models": models, "utils": sys.modules["utils"]}

@@ -58,3 +58,28 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "oracle" not in src.replace("test oracle", ""), os.path.join(dp, f)
+
+
+def test_dropin_install_registers_the_reference_import_seam():
+    """`import clip`, `from clip import clip`, `clip.model.Transformer`, `from models import …` and
+    `utils.pseudolabel_top_k` resolve to the B200 implementations (run in a subprocess: it edits
+    sys.modules)."""
+    import sys
+
+    code = (
+        "import importlib, sys; sys.path.insert(0, %r)\n"
+        "importlib.import_module('menghini-neurips23-code_b200.dropin').install(patch_reference_utils=False)\n"
+        "import clip\n"
+        "from clip import clip as c2\n"
+        "from models import (CustomImageEncoder, CustomTextEncoder, ImageEncoder, TextEncoder,\n"
+        "                    ImagePrefixModel, TextPrefixModel, UPTModel)\n"
+        "from utils import pseudolabel_top_k\n"
+        "import utils.clip_pseudolabels as cp\n"
+        "assert c2 is clip and hasattr(clip, 'load') and hasattr(clip, 'tokenize')\n"
+        "t = clip.model.Transformer(width=128, layers=1, heads=1)\n"
+        "import torch; assert t(torch.zeros(2, 4, 128)).shape == (2, 4, 128)\n"
+        "assert 'menghini' in CustomTextEncoder.__module__ and 'menghini' in pseudolabel_top_k.__module__\n"
+        "assert cp.compute_pseudo_labels.__module__ == pseudolabel_top_k.__module__\n"
+        "print('ok')\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]

@@ -1,0 +1,91 @@
+"""The restated openai/CLIP byte-pair tokenizer against Hugging Face's independent CLIP BPE
+(Rust `tokenizers` backend) on a synthetic merge table — the real vocabulary file is not available
+offline — plus the clip.tokenize framing with a vocabulary file."""
+import gzip
+import importlib
+import random
+
+import pytest
+import torch
+
+
+def _toy_merges(seed=0, n=400):
+    """Merge table learnt greedily from a toy corpus, in the tokenizer's own symbol alphabet."""
+    words = ("a photo of annual crop land forest herbaceous vegetation highway road industrial buildings "
+             "pasture permanent residential river sea lake airplane airport baseball diamond beach bridge "
+             "chaparral church cloud desert freeway golf course harbor island meadow mountain palace "
+             "railway runway stadium terrace wetland boeing airbus x satellite centered the").split()
+    rnd = random.Random(seed)
+    corpus = {}
+    for w in words:
+        corpus[tuple(w[:-1]) + (w[-1] + "</w>",)] = rnd.randint(1, 20)
+    merges = []
+    for _ in range(n):
+        counts = {}
+        for sym, f in corpus.items():
+            for a, b in zip(sym, sym[1:]):
+                counts[(a, b)] = counts.get((a, b), 0) + f
+        if not counts:
+            break
+        best = max(sorted(counts), key=lambda p: counts[p])
+        merges.append(best)
+        new = {}
+        for sym, f in corpus.items():
+            out, i = [], 0
+            while i < len(sym):
+                if i + 1 < len(sym) and (sym[i], sym[i + 1]) == best:
+                    out.append(sym[i] + sym[i + 1]); i += 2
+                else:
+                    out.append(sym[i]); i += 1
+            new[tuple(out)] = f
+        corpus = new
+    return merges
+
+
+@pytest.fixture(scope="module")
+def toks():
+    st = importlib.import_module("menghini-neurips23-code_b200.clip.simple_tokenizer")
+    merges = _toy_merges()
+    mine = st.SimpleTokenizer(merges=merges)
+    from transformers import CLIPTokenizer
+    hf = CLIPTokenizer(vocab=dict(mine.encoder), merges=[tuple(m) for m in merges])
+    return mine, hf
+
+
+TEXTS = ["a photo of a forest", "X X X X annual crop land", "a photo of a {}sea lake", "Highway or Road",
+         "permanent crop land 7", "baseball-diamond", "it's a river's bridge", "unseenword zzz", "airport 42"]
+
+
+def test_bpe_matches_huggingface_clip_bpe(toks):
+    mine, hf = toks
+    for t in TEXTS:
+        want = hf(t, add_special_tokens=False)["input_ids"]
+        assert mine.encode(t) == want, t
+
+
+def test_decode_round_trip(toks):
+    mine, _ = toks
+    for t in ("a photo of a forest", "annual crop land"):
+        assert mine.decode(mine.encode(t)).strip() == t
+
+
+def test_clip_tokenize_with_vocab_file(toks, tmp_path, monkeypatch):
+    mine, _ = toks
+    # a file in bpe_simple_vocab_16e6.txt.gz format: header line, then one merge per line
+    merges = list(mine.bpe_ranks)
+    path = tmp_path / "bpe_toy.txt.gz"
+    with gzip.open(path, "wt", encoding="utf-8") as f:
+        f.write("#version: toy\n" + "\n".join(" ".join(m) for m in merges) + "\n")
+    clip = importlib.import_module("menghini-neurips23-code_b200.clip")
+    monkeypatch.setenv("GRIPB200_BPE_VOCAB", str(path))
+    ids = clip.tokenize(["X X annual crop land", "sea"])
+    sot, eot = mine.encoder["<|startoftext|>"], mine.encoder["<|endoftext|>"]
+    assert ids.shape == (2, 77) and ids.dtype == torch.long
+    assert ids[0, 0] == sot and ids[1, 0] == sot
+    n0 = len(mine.encode("X X annual crop land"))
+    assert ids[0, 1:1 + n0].tolist() == mine.encode("X X annual crop land")
+    assert ids[0, 1 + n0] == eot and ids[0, 2 + n0:].sum() == 0
+    assert ids.argmax(-1).tolist() == [1 + n0, 1 + len(mine.encode("sea"))]  # EOT has the highest id
+    with pytest.raises(RuntimeError):
+        clip.tokenize(" ".join(["land"] * 100))
+    assert clip.tokenize(" ".join(["land"] * 100), truncate=True)[0, -1] == eot
