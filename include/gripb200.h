@@ -170,7 +170,9 @@ int gb_text_backward_prefix(gb_ctx* ctx, const float* dfeat, const int32_t* eot,
 
 /* logits = scale * F T^T, probs = softmax(logits), pred = argmax: CLIP.forward + softmax + argmax of
  * utils/clip_pseudolabels.py:59-65 for all N images in one HBM pass.
- *   F fp16 [N,512], T fp16 [C,512], both with unit rows; C <= 128.
+ *   F fp16 [N,512], T fp16 [C,512], both with unit rows; C <= 512.  Up to 128 classes the prototypes stay
+ *   resident in shared memory and F is read once; wider class sets (SUN397, CUB-200) run in chunks of 128
+ *   classes with one extra pass over F per chunk and phase (partial statistics, merge, probabilities).
  *   mode 0: pred = argmax(probs) (clip_pseudolabels.py:63); 1: argmax(logits) (textual_fpl.py:228)
  *   pred int32 [N]; p_pred fp32 [N] = probs[i,pred[i]]; probs fp32 [N,C] or NULL. */
 int gb_sim_softmax_argmax(gb_ctx* ctx, const void* F, const void* T, float scale, int N, int C,

@@ -64,6 +64,15 @@ struct SimParams {
   int32_t* pred;   // [N]
   float* p_pred;   // [N]
   float* probs;    // [N, C] or nullptr: every row written
+  // class-chunked operation for C > 128 (phase 0 = single launch, everything above):
+  //   phase 1: this launch covers classes [class0, class0+C) and writes per-row partials
+  //            part[row] = (max, Σ 2^(l−max), arg-max (global class index, as int bits), −)
+  //   phase 2: row_stat[row] = (global max, 1/Σ) is given; writes probs[row, class0..] (ld = ldp) and
+  //            first_eq[row] = first global class of this chunk whose probability equals the row maximum
+  int phase, class0, ldp;
+  float4* part;
+  const float2* row_stat;
+  int32_t* first_eq;
   const float* lb;    // [C] leaderboard lower bounds or nullptr (no filtering)
   uint32_t* flags;    // bit i%32 of flags[i/32]: row i may still change a board (only with lb)
   float* cand_rows;   // [(tile_end-tile_begin)*128, C]: prob rows of flagged rows (only with lb)
@@ -229,7 +238,19 @@ sim_softmax_argmax_kernel(const __grid_constant__ CUtensorMap tmF,
           }
         }
       }
-      const float inv = __frcp_rn(sum);
+      if (p.phase == 1) {  // partial statistics of this class chunk
+        if (row_ok) p.part[row] = make_float4(mx, sum, __int_as_float(p.class0 + am), 0.f);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[grp]);
+        continue;
+      }
+      float inv = __frcp_rn(sum);
+      if (p.phase == 2 && row_ok) {  // global soft-max statistics from the merge kernel
+        const float2 st = p.row_stat[row];
+        mx = st.x;
+        inv = st.y;
+      }
       const float pmax = inv;  // rn(1·inv)
       int pred = am;
       if (p.mode == 0) {
@@ -240,8 +261,9 @@ sim_softmax_argmax_kernel(const __grid_constant__ CUtensorMap tmF,
       loose = loose && row_ok;
       const uint32_t loose_mask = __ballot_sync(0xffffffffu, loose);
       bool survive = false;
-      if (want_rows || loose_mask != 0) {
-        float* dst = want_rows ? p.probs + (size_t)row * C
+      int first_eq = 0x7fffffff;
+      if (want_rows || loose_mask != 0 || p.phase == 2) {
+        float* dst = want_rows ? p.probs + (size_t)row * p.ldp + p.class0
                                : p.cand_rows + (size_t)(row - p.tile_begin * kSimBM) * C;
         const bool store = row_ok && (want_rows || loose);
         tmem_ld_32x16(taddr, v[0]);
@@ -256,11 +278,19 @@ sim_softmax_argmax_kernel(const __grid_constant__ CUtensorMap tmF,
               if (col < C) {
                 const float pj = __fmul_rn(sim_exp(v[c & 1][j], p.scale2, mx), inv);
                 if (filt && pj > s_lb[col]) survive = true;
+                if (p.phase == 2 && pj == pmax) first_eq = min(first_eq, p.class0 + col);
                 if (store) dst[col] = pj;
               }
             }
           }
         }
+      }
+      if (p.phase == 2) {
+        if (row_ok) p.first_eq[row] = first_eq;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[grp]);
+        continue;
       }
       if (filt) {
         const uint32_t ballot = __ballot_sync(0xffffffffu, survive && row_ok);
@@ -360,7 +390,8 @@ lb_filter_kernel(const float* __restrict__ probs, int C, int row_begin, int row_
 // [row_begin,row_end), in index order.  One CTA: warp 0 owns the state machine (lane l handles
 // boards l, l+32, …), warps 1-7 stage the flagged rows' probabilities into a shared-memory ring.
 constexpr int kLbThreads = 256;
-constexpr int kLbBatch = 64;  // rows per ring slot
+constexpr int kLbBatchMax = 64;  // rows per ring slot (32 when C > 256, to bound shared memory)
+inline __host__ __device__ int lb_batch(int C) { return C <= 256 ? kLbBatchMax : 32; }
 
 struct LbReplayParams {
   void* state;
@@ -380,6 +411,7 @@ __device__ void lb_admit(const LbView& v, int j, float pj, int idx, const int32_
 __global__ void __launch_bounds__(kLbThreads, 1) lb_replay_kernel(const LbReplayParams p) {
   extern __shared__ uint8_t lb_smem[];
   const int C = p.C, k = p.k;
+  const int kLbBatch = lb_batch(C);
   float* ring = reinterpret_cast<float*>(lb_smem);                          // [2][kLbBatch][C]
   int32_t* ring_idx = reinterpret_cast<int32_t*>(ring + 2 * kLbBatch * C);  // [2][kLbBatch]
   int32_t* ring_pred = ring_idx + 2 * kLbBatch;                             // [2][kLbBatch]
@@ -598,18 +630,63 @@ __global__ void lb_export_kernel(void* base, int C, int k, int32_t* out_idx, int
   }
 }
 
+// Merge of the per-chunk partials (fixed chunk order → deterministic): global max M, Σ = Σ_c Σ_c·2^(m_c−M),
+// arg-max = arg-max of the first chunk that attains M.
+__global__ void __launch_bounds__(256)
+sim_merge_kernel(const float4* __restrict__ part, int chunks, int N, float2* __restrict__ row_stat,
+                 int32_t* __restrict__ pred, float* __restrict__ p_pred) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= N) return;
+  float M = -INFINITY;
+  int am = 0;
+  for (int c = 0; c < chunks; ++c) {
+    const float4 t = part[(size_t)c * N + row];
+    if (t.x > M) { M = t.x; am = __float_as_int(t.z); }
+  }
+  float S = 0.f;
+  for (int c = 0; c < chunks; ++c) {
+    const float4 t = part[(size_t)c * N + row];
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fsub_rn(t.x, M)));
+    S = __fmaf_rn(t.y, e, S);
+  }
+  const float inv = __frcp_rn(S);
+  row_stat[row] = make_float2(M, inv);
+  pred[row] = am;
+  p_pred[row] = inv;
+}
+
+// mode 0 (arg-max over the probabilities): first class, over all chunks, whose probability equals the max.
+__global__ void __launch_bounds__(256)
+sim_first_eq_kernel(const int32_t* __restrict__ first_eq, int chunks, int N, int32_t* __restrict__ pred) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= N) return;
+  int best = 0x7fffffff;
+  for (int c = 0; c < chunks; ++c) best = min(best, first_eq[(size_t)c * N + row]);
+  if (best != 0x7fffffff) pred[row] = best;
+}
+
 size_t sim_smem_bytes(int BN) {
   return (size_t)kSimKBlocks * BN * 128 + (size_t)kSimStages * kSimABytes + 1024 + 512 +
          (size_t)BN * 4;
 }
-constexpr int kLbMaxC = 256;
+constexpr int kLbMaxC = 512;
 size_t lb_replay_smem_bytes(int C) {
+  const int kLbBatch = lb_batch(C);
   return (size_t)2 * kLbBatch * C * 4 + (size_t)(4 * kLbBatch + 2) * 4 + (size_t)2 * C * 4 + 16;
 }
 
+struct SimChunk {  // class-chunk phase of a launch (see SimParams)
+  int phase = 0, class0 = 0, ldp = 0;
+  float4* part = nullptr;
+  const float2* row_stat = nullptr;
+  int32_t* first_eq = nullptr;
+};
+
 int launch_sim(gb_ctx* c, const void* F, const void* T, float scale, int N, int C, int mode,
                int row_begin, int row_end, int32_t* pred, float* p_pred, float* probs,
-               const float* lb, uint32_t* flags, float* cand_rows, cudaStream_t st) {
+               const float* lb, uint32_t* flags, float* cand_rows, cudaStream_t st,
+               const SimChunk* ck = nullptr) {
   const int BN = (C + 15) & ~15;
   if (C < 1 || BN > 128)
     return gb_fail(c, GB_ERR_ARG, "sim: C=%d unsupported (1..128 classes per launch)", C);
@@ -637,6 +714,11 @@ int launch_sim(gb_ctx* c, const void* F, const void* T, float scale, int N, int 
   p.scale2 = scale * 1.4426950408889634f; p.mode = mode;
   p.pred = pred; p.p_pred = p_pred; p.probs = probs;
   p.lb = lb; p.flags = flags; p.cand_rows = cand_rows;
+  p.phase = 0; p.class0 = 0; p.ldp = C; p.part = nullptr; p.row_stat = nullptr; p.first_eq = nullptr;
+  if (ck) {
+    p.phase = ck->phase; p.class0 = ck->class0; p.ldp = ck->ldp;
+    p.part = ck->part; p.row_stat = ck->row_stat; p.first_eq = ck->first_eq;
+  }
   const int tiles = p.tile_end - p.tile_begin;
   if (tiles <= 0) return GB_OK;
   const int grid = tiles < c->num_sms ? tiles : c->num_sms;
@@ -650,6 +732,49 @@ int launch_sim(gb_ctx* c, const void* F, const void* T, float scale, int N, int 
   return GB_OK;
 }
 
+constexpr int kSimMaxC = 512;
+inline size_t sim_chunked_ws_bytes(int N, int C) {
+  const size_t chunks = (C + 127) / 128;
+  return chunks * N * 16 + (size_t)N * 8 + chunks * N * 4 + 1024;
+}
+
+// C > 128: the prototypes do not fit beside the feature ring, so the classes are processed in chunks of
+// 128 (one pass over F per chunk and phase): partial soft-max statistics per chunk → merge → (when the
+// probabilities or the arg-max over them are wanted) a second pass per chunk with the global statistics.
+// `ws` must hold sim_chunked_ws_bytes(N, C) bytes.
+int sim_chunked(gb_ctx* c, const void* F, const void* T, float scale, int N, int C, int mode,
+                int32_t* pred, float* p_pred, float* probs, void* ws, cudaStream_t st) {
+  const int chunks = (C + 127) / 128;
+  uint8_t* w = reinterpret_cast<uint8_t*>(ws);
+  float4* part = reinterpret_cast<float4*>(w);
+  float2* row_stat = reinterpret_cast<float2*>(w + (size_t)chunks * N * 16);
+  int32_t* first_eq = reinterpret_cast<int32_t*>(w + (size_t)chunks * N * 16 + (size_t)N * 8);
+  int rc;
+  for (int ch = 0; ch < chunks; ++ch) {
+    SimChunk ck;
+    ck.phase = 1; ck.class0 = ch * 128; ck.ldp = C; ck.part = part + (size_t)ch * N;
+    const int cc = C - ch * 128 < 128 ? C - ch * 128 : 128;
+    const __half* Tc = reinterpret_cast<const __half*>(T) + (size_t)ch * 128 * kSimK;
+    if ((rc = launch_sim(c, F, Tc, scale, N, cc, 1, 0, N, pred, p_pred, nullptr, nullptr, nullptr, nullptr, st, &ck))) return rc;
+  }
+  sim_merge_kernel<<<(N + 255) / 256, 256, 0, st>>>(part, chunks, N, row_stat, pred, p_pred);
+  GB_LAUNCH_CHECK(c);
+  if (probs == nullptr && mode == 1) return GB_OK;
+  for (int ch = 0; ch < chunks; ++ch) {
+    SimChunk ck;
+    ck.phase = 2; ck.class0 = ch * 128; ck.ldp = C; ck.row_stat = row_stat;
+    ck.first_eq = first_eq + (size_t)ch * N;
+    const int cc = C - ch * 128 < 128 ? C - ch * 128 : 128;
+    const __half* Tc = reinterpret_cast<const __half*>(T) + (size_t)ch * 128 * kSimK;
+    if ((rc = launch_sim(c, F, Tc, scale, N, cc, 1, 0, N, pred, p_pred, probs, nullptr, nullptr, nullptr, st, &ck))) return rc;
+  }
+  if (mode == 0) {
+    sim_first_eq_kernel<<<(N + 255) / 256, 256, 0, st>>>(first_eq, chunks, N, pred);
+    GB_LAUNCH_CHECK(c);
+  }
+  return GB_OK;
+}
+
 int launch_replay(gb_ctx* c, void* state, int C, int k, const float* rows, int rows_row0,
                   const int32_t* pred, const int32_t* rank, const uint32_t* flags, int row_begin,
                   int row_end, int idx0, cudaStream_t st) {
@@ -658,7 +783,7 @@ int launch_replay(gb_ctx* c, void* state, int C, int k, const float* rows, int r
   static bool attr_set[16] = {false};
   if (!attr_set[c->device & 15]) {
     GB_CUDA(c, cudaFuncSetAttribute(lb_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)lb_replay_smem_bytes(kLbMaxC)));
+                                    (int)lb_replay_smem_bytes(256)));  // the largest: C = 256 with 64-row slots
     attr_set[c->device & 15] = true;
   }
   LbReplayParams p;
@@ -680,6 +805,13 @@ extern "C" int gb_sim_softmax_argmax(gb_ctx* c, const void* F, const void* T, fl
   if (!c) return GB_ERR_ARG;
   if (N <= 0) return GB_OK;
   if (!F || !T || !pred || !p_pred) return gb_fail(c, GB_ERR_ARG, "sim: null pointer");
+  if (C > 128) {
+    if (C > kSimMaxC) return gb_fail(c, GB_ERR_ARG, "sim: C=%d unsupported (1..%d classes)", C, kSimMaxC);
+    int rc = gb_ws_reserve(c, gb_ctx::kWsScan, sim_chunked_ws_bytes(N, C));
+    if (rc) return rc;
+    return sim_chunked(c, F, T, scale, N, C, mode, pred, p_pred, probs, c->ws[gb_ctx::kWsScan],
+                       (cudaStream_t)stream);
+  }
   return launch_sim(c, F, T, scale, N, C, mode, 0, N, pred, p_pred, probs, nullptr, nullptr,
                     nullptr, (cudaStream_t)stream);
 }
@@ -692,7 +824,7 @@ extern "C" size_t gb_leaderboard_state_bytes(int C, int k) {
 extern "C" int gb_leaderboard_init(gb_ctx* c, void* state, int C, int k, void* stream) {
   if (!c) return GB_ERR_ARG;
   if (!state || C <= 0 || C > kLbMaxC || k <= 0)
-    return gb_fail(c, GB_ERR_ARG, "leaderboard_init: bad arguments (C=%d in 1..256, k=%d > 0)", C, k);
+    return gb_fail(c, GB_ERR_ARG, "leaderboard_init: bad arguments (C=%d in 1..512, k=%d > 0)", C, k);
   lb_init_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(state, C, k);
   GB_LAUNCH_CHECK(c);
   return GB_OK;
@@ -751,6 +883,20 @@ extern "C" int gb_pseudolabel_scan(gb_ctx* c, void* state, const void* F, const 
     return gb_fail(c, GB_ERR_ARG, "pseudolabel_scan: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   const LbView v = lb_view(state, C, k);
+  if (C > 128) {
+    // wide class sets: chunked similarity into a full probability matrix, then the standalone
+    // pre-filter + replay.  Scratch layout: [flags | chunk partials | probabilities (if not given)].
+    if (C > kSimMaxC) return gb_fail(c, GB_ERR_ARG, "pseudolabel_scan: C=%d unsupported (1..%d)", C, kSimMaxC);
+    const size_t flag_b = ((((size_t)N + 31) / 32) * 4 + 256 + 255) & ~size_t(255);
+    const size_t part_b = (sim_chunked_ws_bytes(N, C) + 255) & ~size_t(255);
+    const size_t prob_b = probs ? 0 : (size_t)N * C * 4;
+    int rc = gb_ws_reserve(c, gb_ctx::kWsScan, flag_b + part_b + prob_b);
+    if (rc) return rc;
+    uint8_t* w = reinterpret_cast<uint8_t*>(c->ws[gb_ctx::kWsScan]);
+    float* pr = probs ? probs : reinterpret_cast<float*>(w + flag_b + part_b);
+    if ((rc = sim_chunked(c, F, T, scale, N, C, mode, pred, p_pred, pr, w + flag_b, st))) return rc;
+    return gb_leaderboard_update(c, state, C, k, pr, pred, rank, 0, N, idx0, 1, stream);
+  }
   const int chunk_cap = 1 << 18;
   const size_t flag_bytes = (((size_t)N + 127) / 128) * 16 + 256;
   const size_t cand_bytes = probs ? 0 : (size_t)(N < chunk_cap ? ((N + 127) & ~127) : chunk_cap) * C * 4;

@@ -43,7 +43,8 @@ def sim(pkg, eng_mod):
 
 
 @pytest.mark.parametrize("N,C", [(1, 1), (5, 10), (128, 16), (129, 45), (1000, 100), (4097, 102),
-                                 (300, 128), (777, 7), (20000, 18)])
+                                 (300, 128), (777, 7), (20000, 18),
+                                 (300, 129), (2000, 200), (1500, 397), (515, 512)])  # class-chunked path
 def test_sim_softmax_argmax_matches_oracle(sim, N, C):
     f, t = synth.pool(N, C, peaked=0.05 if N % 2 else 0.3)
     F, T = f.half().cuda(), t.half().cuda()
@@ -83,7 +84,7 @@ def test_sim_mode1_argmax_logits(sim):
 
 def test_sim_rejects_too_many_classes(sim, pkg):
     F = torch.zeros(10, 512, device="cuda", dtype=torch.float16)
-    T = torch.zeros(129, 512, device="cuda", dtype=torch.float16)
+    T = torch.zeros(513, 512, device="cuda", dtype=torch.float16)
     with pytest.raises(pkg.GripB200Error):
         sim(F, T, 100.0)
 
@@ -112,7 +113,7 @@ def test_leaderboard_golden_bit_exact(eng_mod, golden_dir, prefilter):
 
 @pytest.mark.parametrize("N,C,k,peaked", [(5000, 10, 16, 0.3), (20000, 45, 16, 0.1), (30000, 100, 16, 0.0),
                                           (4000, 7, 64, 0.2), (3000, 5, 600, 0.3), (2000, 3, 1, 0.5),
-                                          (10000, 102, 4, 0.05)])
+                                          (10000, 102, 4, 0.05), (6000, 200, 8, 0.1), (3000, 397, 3, 0.1)])
 def test_leaderboard_random_matches_oracle(eng_mod, sim, N, C, k, peaked):
     f, t = synth.pool(N, C, peaked=peaked)
     F, T = f.half().cuda(), t.half().cuda()
