@@ -110,8 +110,10 @@ def run_reference(a, rank):
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "images/s",
             "n_gpus": a.gpus, "steps": done, "warmup": min(a.warmup, 1), "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": workload_name(a, a.cpu_batch),
-                                            "note": "reference CPU path (oracle port), bounded sample"},
+            "data": "synthetic", "config": {"workload": workload_name(a, a.batch),
+                                            "note": f"reference CPU path (oracle port of the same step), each step "
+                                                    f"a bounded sample of {a.cpu_batch} images (the reference's "
+                                                    f"BATCH_SIZE) on all host cores"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
