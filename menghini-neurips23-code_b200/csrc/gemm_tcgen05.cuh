@@ -39,8 +39,10 @@ struct GemmParams {
   // so A is the raw residual stream and the row statistics are applied in the epilogue.
   const float* ln_stats;  // [M][2] = (μ·rstd, rstd) of each row of A, or nullptr
   const float* col_sum;   // s_n, [N]
-  // partial (Σ, Σ²) of every OUTPUT row over this warp's 128 columns, [N/128][M][2], or nullptr: the
-  // statistics the next LayerNorm needs, produced where the rows are written.
+  // shifted partial sums of every OUTPUT row over this warp's 128 columns, [N/128][M] float4 =
+  // (x0, Σ(x−x0), Σ(x−x0)², −) with x0 the segment's first stored value, or nullptr: the statistics the
+  // next LayerNorm needs, produced where the rows are written.  The shift keeps the later variance
+  // computation free of the E[x²]−μ² cancellation when a row's mean dwarfs its spread.
   float* stats_out;
 };
 
@@ -327,7 +329,7 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
     const int nrow = next_m0 + q * 32 + lane;
     if (nrow < p.M) ln_next = *reinterpret_cast<const float2*>(p.ln_stats + (size_t)nrow * 2);
   }
-  float st_sum = 0.f, st_sq = 0.f;
+  float st_sum = 0.f, st_sq = 0.f, st_x0 = 0.f;
   wait_acc();
   tc_fence_after();
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + half * (BN / 2);
@@ -420,8 +422,10 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
         h[t] = __floats2half2_rn(f[8 * j + 2 * t], f[8 * j + 2 * t + 1]);
         if (p.stats_out != nullptr) {  // statistics of the values as stored (fp16-rounded)
           const float2 r = __half22float2(h[t]);
-          st_sum += r.x + r.y;
-          st_sq += r.x * r.x + r.y * r.y;
+          if (c == 0 && j == 0 && t == 0) st_x0 = r.x;
+          const float d0 = r.x - st_x0, d1 = r.y - st_x0;
+          st_sum += d0 + d1;
+          st_sq = fmaf(d0, d0, fmaf(d1, d1, st_sq));
         }
       }
       const int chunk = (c & 1) * 4 + j;
@@ -439,8 +443,8 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
     for (int j = 0; j < 4; ++j) pre[j] = pre_next[j];
   }
   if (p.stats_out != nullptr && row_ok)
-    *reinterpret_cast<float2*>(p.stats_out + ((size_t)(n0 >> 7) * p.M + row) * 2) =
-        make_float2(st_sum, st_sq);
+    *reinterpret_cast<float4*>(p.stats_out + ((size_t)(n0 >> 7) * p.M + row) * 4) =
+        make_float4(st_x0, st_sum, st_sq, 0.f);
   ln_st = ln_next;
 }
 

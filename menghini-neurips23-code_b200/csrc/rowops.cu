@@ -189,18 +189,19 @@ vit_assemble_lnpre_kernel(const __half* __restrict__ patch, const float* __restr
       const float o1 = (f[v * 8 + 2 * t + 1] - mean) * rstd * __ldg(gamma + c0 + 1) + __ldg(beta + c0 + 1);
       h[t] = __floats2half2_rn(o0, o1);
       const float2 r = __half22float2(h[t]);
+      f[v * 8 + 2 * t] = r.x;  // keep the stored (rounded) values for the statistics below
+      f[v * 8 + 2 * t + 1] = r.y;
       st_sum += r.x + r.y;
-      st_sq += r.x * r.x + r.y * r.y;
     }
     *reinterpret_cast<uint4*>(x + (size_t)warp * D + col) = u;
   }
-  // (μ·rstd, rstd) of the stored row: the statistics of the first block's folded ln_1
-  st_sum = warp_sum(st_sum);
-  st_sq = warp_sum(st_sq);
-  if (stats != nullptr && lane == 0) {
-    const float m2 = st_sum * (1.0f / D);
-    const float r2 = rsqrtf(fmaxf(st_sq * (1.0f / D) - m2 * m2, 0.f) + eps);
-    *reinterpret_cast<float2*>(stats + (size_t)warp * 2) = make_float2(m2 * r2, r2);
+  // (μ·rstd, rstd) of the stored row, two-pass: the statistics of the first block's folded ln_1
+  if (stats != nullptr) {
+    const float m2 = warp_sum(st_sum) * (1.0f / D);
+#pragma unroll
+    for (int i = 0; i < V * 8; ++i) { const float d = f[i] - m2; st_sq = fmaf(d, d, st_sq); }
+    const float r2 = rsqrtf(warp_sum(st_sq) * (1.0f / D) + eps);
+    if (lane == 0) *reinterpret_cast<float2*>(stats + (size_t)warp * 2) = make_float2(m2 * r2, r2);
   }
 }
 
@@ -216,6 +217,7 @@ text_assemble_kernel(const int32_t* __restrict__ ids, int ld_ids, const __half* 
                      __half* __restrict__ x, int C, int ctx_len, float* __restrict__ stats) {
   constexpr int D = 512, V = 2;
   float st_sum = 0.f, st_sq = 0.f;
+  float kept[V * 8];  // the stored (rounded) row, for the two-pass statistics
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= C * ctx_len) return;
@@ -248,17 +250,18 @@ text_assemble_kernel(const int32_t* __restrict__ ids, int ld_ids, const __half* 
     for (int t = 0; t < 4; ++t) {
       h[t] = __floats2half2_rn(a[2 * t], a[2 * t + 1]);
       const float2 r = __half22float2(h[t]);
+      kept[v * 8 + 2 * t] = r.x;
+      kept[v * 8 + 2 * t + 1] = r.y;
       st_sum += r.x + r.y;
-      st_sq += r.x * r.x + r.y * r.y;
     }
     *reinterpret_cast<uint4*>(x + (size_t)warp * D + col) = o;
   }
-  st_sum = warp_sum(st_sum);
-  st_sq = warp_sum(st_sq);
-  if (stats != nullptr && lane == 0) {
-    const float m2 = st_sum * (1.0f / D);
-    const float r2 = rsqrtf(fmaxf(st_sq * (1.0f / D) - m2 * m2, 0.f) + 1e-5f);
-    *reinterpret_cast<float2*>(stats + (size_t)warp * 2) = make_float2(m2 * r2, r2);
+  if (stats != nullptr) {  // (μ·rstd, rstd) of the stored row, two-pass
+    const float m2 = warp_sum(st_sum) * (1.0f / D);
+#pragma unroll
+    for (int i = 0; i < V * 8; ++i) { const float d = kept[i] - m2; st_sq = fmaf(d, d, st_sq); }
+    const float r2 = rsqrtf(warp_sum(st_sq) * (1.0f / D) + 1e-5f);
+    if (lane == 0) *reinterpret_cast<float2*>(stats + (size_t)warp * 2) = make_float2(m2 * r2, r2);
   }
 }
 
@@ -456,21 +459,27 @@ scale_f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, 
   }
 }
 
-// Combines the per-128-column partial (Σ, Σ²) pairs the residual GEMMs emit, in a fixed order, into
-// the (μ·rstd, rstd) pair per row that the LayerNorm-folded GEMM epilogue consumes.
+// Combines the per-128-column shifted partials (x0, Σ(x−x0), Σ(x−x0)²) the residual GEMMs emit into the
+// (μ·rstd, rstd) pair per row that the LayerNorm-folded GEMM epilogue consumes: per segment mean and
+// centred second moment, then Chan's pairwise update in a fixed segment order (deterministic, and free of
+// the E[x²]−μ² cancellation).
 __global__ void __launch_bounds__(256)
-ln_finalize_kernel(const float* __restrict__ parts, int nparts, int M, float inv_d, float eps,
+ln_finalize_kernel(const float4* __restrict__ parts, int nparts, int M, float seg_n, float eps,
                    float* __restrict__ out) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= M) return;
-  float sx = 0.f, sq = 0.f;
+  float n = 0.f, mean = 0.f, m2 = 0.f;
   for (int i = 0; i < nparts; ++i) {
-    const float2 t = *reinterpret_cast<const float2*>(parts + ((size_t)i * M + row) * 2);
-    sx += t.x;
-    sq += t.y;
+    const float4 t = parts[(size_t)i * M + row];
+    const float mp = t.x + t.y / seg_n;            // segment mean
+    const float m2p = t.z - t.y * t.y / seg_n;     // Σ (x − segment mean)²
+    const float nn = n + seg_n;
+    const float delta = mp - mean;
+    mean += delta * (seg_n / nn);
+    m2 += m2p + delta * delta * (n * seg_n / nn);
+    n = nn;
   }
-  const float mean = sx * inv_d;
-  const float rstd = rsqrtf(fmaxf(sq * inv_d - mean * mean, 0.f) + eps);
+  const float rstd = rsqrtf(fmaxf(m2 / n, 0.f) + eps);
   *reinterpret_cast<float2*>(out + (size_t)row * 2) = make_float2(mean * rstd, rstd);
 }
 
@@ -588,7 +597,8 @@ int gb_launch_scale_f32_to_f16(gb_ctx* c, const float* in, void* out, size_t n, 
 int gb_launch_ln_finalize(gb_ctx* c, const float* parts, int nparts, int M, int D, float* out,
                           cudaStream_t st) {
   if (M <= 0) return GB_OK;
-  ln_finalize_kernel<<<(M + 255) / 256, 256, 0, st>>>(parts, nparts, M, 1.0f / D, 1e-5f, out);
+  ln_finalize_kernel<<<(M + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(parts), nparts, M,
+                                                     (float)(D / nparts), 1e-5f, out);
   GB_LAUNCH_CHECK(c);
   return GB_OK;
 }

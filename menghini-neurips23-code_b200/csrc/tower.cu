@@ -91,7 +91,7 @@ struct Tape {
 // in their epilogue, and the two residual GEMMs emit the (Σ, Σ²) partials of the rows they write,
 // which a tiny kernel turns into (μ·rstd, rstd) per row.
 // st_fin: [M][2] (μ·rstd, rstd) of the current residual stream (valid for x on entry);
-// st_part: [D/128][M][2] scratch for the partial sums.
+// st_part: [D/128][M] float4 scratch for the shifted partial sums.
 int run_blocks(gb_ctx* c, const gb_tower* t, int S, int L, int causal, void* x, const Tape* tape,
                void* h, void* qkv_ws, void* a, void* g, float* st_fin, float* st_part, cudaStream_t st) {
   const int D = t->width, M = S * L;
@@ -223,7 +223,7 @@ extern "C" int gb_vit_forward(gb_ctx* c, const void* img, int img_f32, const flo
     Bump b(nullptr);
     b.take(h2(M, D)); b.take(h2(M, D)); b.take(h2(M, 3 * D)); b.take(h2(M, D));
     b.take(h2(M > (size_t)B * 49 ? M : (size_t)B * 49, 4 * D)); b.take(h2(B, D)); b.take((size_t)B * 512 * 4);
-    b.take(M * (D / 128) * 8); b.take(M * (D / 128) * 8);
+    b.take(M * 8); b.take(M * (D / 128) * 16);
     need = b.off;
   }
   int rc = gb_ws_reserve(c, gb_ctx::kWsVit, need);
@@ -236,8 +236,8 @@ extern "C" int gb_vit_forward(gb_ctx* c, const void* img, int img_f32, const flo
   void* g = b.take(h2(M > (size_t)B * 49 ? M : (size_t)B * 49, 4 * D));
   void* cls_ln = b.take(h2(B, D));
   float* feat_ws = reinterpret_cast<float*>(b.take((size_t)B * 512 * 4));
-  float* st_a = reinterpret_cast<float*>(b.take(M * (D / 128) * 8));
-  float* st_b = reinterpret_cast<float*>(b.take(M * (D / 128) * 8));
+  float* st_a = reinterpret_cast<float*>(b.take(M * 8));                 // (μ·rstd, rstd) per row
+  float* st_b = reinterpret_cast<float*>(b.take(M * (D / 128) * 16));    // shifted partials per 128 columns
   Tape tape{reinterpret_cast<uint8_t*>(tape_mem), M, (size_t)D};
   void* x = tape_mem ? tape.x0(0) : x_ws;
   const gb_vit_weights& w = t->vit;
@@ -313,7 +313,7 @@ extern "C" int gb_text_forward(gb_ctx* c, const int32_t* ids, int ld_ids, const 
     Bump b(nullptr);
     b.take(h2(M, D)); b.take(h2(M, D)); b.take(h2(M, 3 * D)); b.take(h2(M, D)); b.take(h2(M, 4 * D));
     b.take(h2(C, D)); b.take((size_t)C * 512 * 4); b.take((size_t)C * 4);
-    b.take(M * (D / 128) * 8); b.take(M * (D / 128) * 8);
+    b.take(M * 8); b.take(M * (D / 128) * 16);
     need = b.off;
   }
   int rc = gb_ws_reserve(c, gb_ctx::kWsText, need);
@@ -327,8 +327,8 @@ extern "C" int gb_text_forward(gb_ctx* c, const int32_t* ids, int ld_ids, const 
   void* eot_ln = b.take(h2(C, D));
   float* feat_ws = reinterpret_cast<float*>(b.take((size_t)C * 512 * 4));
   int32_t* rows = reinterpret_cast<int32_t*>(b.take((size_t)C * 4));
-  float* st_a = reinterpret_cast<float*>(b.take(M * (D / 128) * 8));
-  float* st_b = reinterpret_cast<float*>(b.take(M * (D / 128) * 8));
+  float* st_a = reinterpret_cast<float*>(b.take(M * 8));                 // (μ·rstd, rstd) per row
+  float* st_b = reinterpret_cast<float*>(b.take(M * (D / 128) * 16));    // shifted partials per 128 columns
   Tape tape{reinterpret_cast<uint8_t*>(tape_mem), M, (size_t)D};
   void* x = tape_mem ? tape.x0(0) : x_ws;
   // token embedding, prefix overwrite of rows 1..P, + positional embedding: models/clip_encoders.py:63-74
