@@ -333,6 +333,7 @@ struct LbView {
   int32_t* ei;
   float* sp;
   int32_t* si;
+  int32_t* sr;  // ranks of the k+1 items during the one-time sort (shared-memory boards only)
 };
 
 __host__ __device__ inline size_t lb_bytes(int C, int k) {
@@ -350,6 +351,7 @@ __host__ __device__ inline LbView lb_view(void* base, int C, int k) {
   v.ei = reinterpret_cast<int32_t*>(v.ep + (size_t)C * k);
   v.sp = reinterpret_cast<float*>(v.ei + (size_t)C * k);
   v.si = reinterpret_cast<int32_t*>(v.sp + k + 1);
+  v.sr = nullptr;
   return v;
 }
 
@@ -389,6 +391,7 @@ lb_filter_kernel(const float* __restrict__ probs, int C, int row_begin, int row_
 // Exact sequential replay (utils/clip_pseudolabels.py:72-101) of the flagged rows of
 // [row_begin,row_end), in index order.  One CTA: warp 0 owns the state machine (lane l handles
 // boards l, l+32, …), warps 1-7 stage the flagged rows' probabilities into a shared-memory ring.
+constexpr size_t kLbSmemEntries = 8192;  // boards of up to C·k entries (64 KB) are held in shared memory
 constexpr int kLbThreads = 256;
 constexpr int kLbBatchMax = 64;  // rows per ring slot (32 when C > 256, to bound shared memory)
 inline __host__ __device__ int lb_batch(int C) { return C <= 256 ? kLbBatchMax : 32; }
@@ -419,12 +422,26 @@ __global__ void __launch_bounds__(kLbThreads, 1) lb_replay_kernel(const LbReplay
   float* s_last = reinterpret_cast<float*>(ring_n + 2);                     // [C]
   int32_t* s_cnt = reinterpret_cast<int32_t*>(s_last + C);                  // [C]
 
-  const LbView v = lb_view(p.state, C, k);
+  const LbView g = lb_view(p.state, C, k);  // the state in global memory
+  // Boards small enough (C·k ≤ kLbSmemEntries) live in shared memory for the duration of the launch:
+  // an admission then costs a few hundred cycles instead of several global-memory round trips.
+  LbView v = g;
+  const bool in_smem = (size_t)C * k <= kLbSmemEntries;
+  if (in_smem) {
+    v.ep = reinterpret_cast<float*>(s_cnt + C);
+    v.ei = reinterpret_cast<int32_t*>(v.ep + (size_t)C * k);
+    v.srt = v.ei + (size_t)C * k;
+    v.sp = reinterpret_cast<float*>(v.srt + C);
+    v.si = reinterpret_cast<int32_t*>(v.sp + k + 1);
+    v.sr = v.si + k + 1;
+    for (int i = threadIdx.x; i < C * k; i += kLbThreads) { v.ep[i] = g.ep[i]; v.ei[i] = g.ei[i]; }
+    for (int j = threadIdx.x; j < C; j += kLbThreads) v.srt[j] = g.srt[j];
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int j = threadIdx.x; j < C; j += kLbThreads) {
-    const int c = v.cnt[j];
+    const int c = g.cnt[j];
     s_cnt[j] = c;
-    s_last[j] = c > 0 ? v.ep[(size_t)j * k + c - 1] : 0.f;
+    s_last[j] = c > 0 ? g.ep[(size_t)j * k + c - 1] : 0.f;
   }
   __syncthreads();
 
@@ -534,10 +551,14 @@ __global__ void __launch_bounds__(kLbThreads, 1) lb_replay_kernel(const LbReplay
     slot ^= 1;
   }
   __syncthreads();
+  if (in_smem) {  // boards back to the caller-owned state
+    for (int i = threadIdx.x; i < C * k; i += kLbThreads) { g.ep[i] = v.ep[i]; g.ei[i] = v.ei[i]; }
+    for (int j = threadIdx.x; j < C; j += kLbThreads) g.srt[j] = v.srt[j];
+  }
   // publish counters and the pre-filter lower bounds
   for (int j = threadIdx.x; j < C; j += kLbThreads) {
     const int c = s_cnt[j];
-    v.cnt[j] = c;
+    g.cnt[j] = c;
     float lbv = -INFINITY;
     if (c >= k) {
       if (v.srt[j]) {
@@ -547,7 +568,7 @@ __global__ void __launch_bounds__(kLbThreads, 1) lb_replay_kernel(const LbReplay
         for (int e = 0; e < k; ++e) lbv = fminf(lbv, v.ep[(size_t)j * k + e]);
       }
     }
-    v.lb[j] = lbv;
+    g.lb[j] = lbv;
   }
 }
 
@@ -589,27 +610,30 @@ __device__ void lb_admit(const LbView& v, int j, float pj, int idx, const int32_
     if (lane == 0) { ep[pos] = pj; ei[pos] = idx; }
     __syncwarp();
   } else {
-    // full stable sort of k+1 items by rank counting into scratch, keep the first k
-    for (int a0 = 0; a0 <= k; a0 += 32) {
-      const int a = a0 + lane;
-      if (a <= k) {
-        const float pa = a < k ? ep[a] : pj;
-        const int ia = a < k ? ei[a] : idx;
-        const int64_t ra = rank ? (int64_t)rank[ia] : (int64_t)ia;
-        int before = 0;
-        for (int b = 0; b <= k; ++b) {
-          if (b == a) continue;
-          const float pb = b < k ? ep[b] : pj;
-          const int ib = b < k ? ei[b] : idx;
-          const int64_t rb = rank ? (int64_t)rank[ib] : (int64_t)ib;
-          if (lb_before(pb, rb, pa, ra) || (pb == pa && rb == ra && b < a)) ++before;
-        }
-        v.sp[before] = pa;
-        v.si[before] = ia;
-      }
+    // full stable sort of k+1 items by rank counting, keep the first k.  Items (and, with shared-memory
+    // boards, their path ranks) are first copied to scratch so that the counting loop touches no
+    // dependent global loads and the result can be written straight into the board.
+    for (int a = lane; a <= k; a += 32) {
+      const float pa = a < k ? ep[a] : pj;
+      const int ia = a < k ? ei[a] : idx;
+      v.sp[a] = pa;
+      v.si[a] = ia;
+      if (v.sr) v.sr[a] = rank ? rank[ia] : ia;
     }
     __syncwarp();
-    for (int e = lane; e < k; e += 32) { ep[e] = v.sp[e]; ei[e] = v.si[e]; }
+    for (int a = lane; a <= k; a += 32) {
+      const float pa = v.sp[a];
+      const int ia = v.si[a];
+      const int64_t ra = v.sr ? (int64_t)v.sr[a] : (rank ? (int64_t)rank[ia] : (int64_t)ia);
+      int before = 0;
+      for (int b = 0; b <= k; ++b) {
+        if (b == a) continue;
+        const float pb = v.sp[b];
+        const int64_t rb = v.sr ? (int64_t)v.sr[b] : (rank ? (int64_t)rank[v.si[b]] : (int64_t)v.si[b]);
+        if (lb_before(pb, rb, pa, ra) || (pb == pa && rb == ra && b < a)) ++before;
+      }
+      if (before < k) { ep[before] = pa; ei[before] = ia; }
+    }
     if (lane == 0) v.srt[j] = 1;
     __syncwarp();
   }
@@ -671,9 +695,11 @@ size_t sim_smem_bytes(int BN) {
          (size_t)BN * 4;
 }
 constexpr int kLbMaxC = 512;
-size_t lb_replay_smem_bytes(int C) {
+size_t lb_replay_smem_bytes(int C, int k) {
   const int kLbBatch = lb_batch(C);
-  return (size_t)2 * kLbBatch * C * 4 + (size_t)(4 * kLbBatch + 2) * 4 + (size_t)2 * C * 4 + 16;
+  size_t b = (size_t)2 * kLbBatch * C * 4 + (size_t)(4 * kLbBatch + 2) * 4 + (size_t)2 * C * 4 + 16;
+  if ((size_t)C * k <= kLbSmemEntries) b += (size_t)C * k * 8 + (size_t)C * 4 + ((size_t)k + 1) * 12 + 16;
+  return b;
 }
 
 struct SimChunk {  // class-chunk phase of a launch (see SimParams)
@@ -779,11 +805,11 @@ int launch_replay(gb_ctx* c, void* state, int C, int k, const float* rows, int r
                   const int32_t* pred, const int32_t* rank, const uint32_t* flags, int row_begin,
                   int row_end, int idx0, cudaStream_t st) {
   if (row_end <= row_begin) return GB_OK;
-  const size_t smem = lb_replay_smem_bytes(C);
+  const size_t smem = lb_replay_smem_bytes(C, k);
   static bool attr_set[16] = {false};
   if (!attr_set[c->device & 15]) {
     GB_CUDA(c, cudaFuncSetAttribute(lb_replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)lb_replay_smem_bytes(256)));  // the largest: C = 256 with 64-row slots
+                                    200 * 1024));  // ring ≤ 128 KB + boards ≤ 64 KB
     attr_set[c->device & 15] = true;
   }
   LbReplayParams p;
