@@ -208,54 +208,59 @@ __global__ void __launch_bounds__(128)
 attn_bwd_kernel(const __half* __restrict__ qkv, const __half* __restrict__ dout,
                 __half* __restrict__ dqkv, int L, int D, int causal) {
   constexpr int Lp = NT * 8;
-  constexpr int ldv = Lp + 8;   // row stride of the [64, Lp] transposed tiles
   constexpr int ldp = Lp + 8;   // row stride of the [Lp, Lp] P / dS tiles
   extern __shared__ __align__(16) uint8_t attn_smem[];
-  __half* Qs = reinterpret_cast<__half*>(attn_smem);   // [Lp, 72]
-  __half* Ks = Qs + Lp * kQKld;                        // [Lp, 72]
-  __half* Vs = Ks + Lp * kQKld;                        // [Lp, 72]   V row-major (B operand of dO·Vᵀ)
-  __half* dOs = Vs + Lp * kQKld;                       // [Lp, 72]
-  __half* Qt = dOs + Lp * kQKld;                       // [64, ldv]  Qᵀ  (B operand of dSᵀ·Q)
-  __half* Kt = Qt + kDh * ldv;                         // [64, ldv]  Kᵀ  (B operand of dS·K)
-  __half* dOt = Kt + kDh * ldv;                        // [64, ldv]  dOᵀ (B operand of Pᵀ·dO)
-  __half* Ps = dOt + kDh * ldv;                        // [Lp, ldp]  P   (row-major: A of … transposed use)
-  __half* dSs = Ps + Lp * ldp;                         // [Lp, ldp]  dS
+  __half* Qs = reinterpret_cast<__half*>(attn_smem);   // [Lp, 72] row-major, like K, V, dO
+  __half* Ks = Qs + Lp * kQKld;
+  __half* Vs = Ks + Lp * kQKld;
+  __half* dOs = Vs + Lp * kQKld;
+  __half* Ps = dOs + Lp * kQKld;                       // [Lp, ldp]  P  (query-major)
+  __half* dSs = Ps + Lp * ldp;                         // [Lp, ldp]  dS (query-major)
   const int h = blockIdx.x, b = blockIdx.y;
   const size_t ld = (size_t)3 * D;
-  for (int i = threadIdx.x; i < Lp * 8; i += blockDim.x) {
-    const int r = i >> 3, ch = i & 7;
-    uint4 q = make_uint4(0, 0, 0, 0), k = q, v = q, d = q;
-    if (r < L) {
-      const __half* src = qkv + ((size_t)b * L + r) * ld + h * kDh + ch * 8;
-      q = *reinterpret_cast<const uint4*>(src);
-      k = *reinterpret_cast<const uint4*>(src + D);
-      v = *reinterpret_cast<const uint4*>(src + 2 * D);
-      d = *reinterpret_cast<const uint4*>(dout + ((size_t)b * L + r) * D + h * kDh + ch * 8);
-    }
-    *reinterpret_cast<uint4*>(Qs + r * kQKld + ch * 8) = q;
-    *reinterpret_cast<uint4*>(Ks + r * kQKld + ch * 8) = k;
-    *reinterpret_cast<uint4*>(Vs + r * kQKld + ch * 8) = v;
-    *reinterpret_cast<uint4*>(dOs + r * kQKld + ch * 8) = d;
-    const __half* qh = reinterpret_cast<const __half*>(&q);
-    const __half* kh = reinterpret_cast<const __half*>(&k);
-    const __half* dh = reinterpret_cast<const __half*>(&d);
+  {
+    // one round trip: every 16-byte chunk of Q, K, V, dO is requested before the first store; all
+    // transposed operands below come from ldmatrix.trans on these row-major tiles
+    constexpr int kIt = (Lp * 8) / 128;
+    uint4 q[kIt], k[kIt], v[kIt], d[kIt];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      Qt[(ch * 8 + e) * ldv + r] = qh[e];
-      Kt[(ch * 8 + e) * ldv + r] = kh[e];
-      dOt[(ch * 8 + e) * ldv + r] = dh[e];
+    for (int it = 0; it < kIt; ++it) {
+      const int i = it * 128 + threadIdx.x;
+      const int r = i >> 3, ch = i & 7;
+      q[it] = k[it] = v[it] = d[it] = make_uint4(0, 0, 0, 0);
+      if (r < L) {
+        const __half* src = qkv + ((size_t)b * L + r) * ld + h * kDh + ch * 8;
+        q[it] = *reinterpret_cast<const uint4*>(src);
+        k[it] = *reinterpret_cast<const uint4*>(src + D);
+        v[it] = *reinterpret_cast<const uint4*>(src + 2 * D);
+        d[it] = *reinterpret_cast<const uint4*>(dout + ((size_t)b * L + r) * D + h * kDh + ch * 8);
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+      const int i = it * 128 + threadIdx.x;
+      const int r = i >> 3, ch = i & 7;
+      *reinterpret_cast<uint4*>(Qs + r * kQKld + ch * 8) = q[it];
+      *reinterpret_cast<uint4*>(Ks + r * kQKld + ch * 8) = k[it];
+      *reinterpret_cast<uint4*>(Vs + r * kQKld + ch * 8) = v[it];
+      *reinterpret_cast<uint4*>(dOs + r * kQKld + ch * 8) = d[it];
     }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
+  // lane-dependent parts of the ldmatrix.x4.trans row addresses
+  const int lm_row = (lane & 7) + ((lane >> 3) & 1) * 8;   // B operand: k rows 0-7 | 8-15
+  const int lm_col = (lane >> 4) * 8;                      //            n block dn | dn+1
+  const int la_row = (lane & 7) + ((lane >> 4) & 1) * 8;   // transposed A operand: k (query) rows
+  const int la_col = ((lane >> 3) & 1) * 8;                //                       m (key) block
   // ---- phase 1: per query-row tile: P, dP, dS (→ smem), dQ (→ global) ---------------------------
   for (int mt = warp; mt * 16 < Lp; mt += 4) {
     const int r0 = mt * 16;
     float s[NT][4];
     float inv0, inv1;
     scores_softmax<NT>(Qs, Ks, r0, L, causal != 0, lane, s, inv0, inv1);
-    // dP = dO · Vᵀ   (A = dO rows, B[k=dh][n=key] = V[key][dh] → V row-major)
+    // dP = dO · Vᵀ   (A = dO rows, B[k=dh][n=key] = V[key][dh] → V row-major is already "col")
     uint32_t a[4][4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
@@ -301,7 +306,7 @@ attn_bwd_kernel(const __half* __restrict__ qkv, const __half* __restrict__ dout,
       *reinterpret_cast<uint32_t*>(dSs + (r0 + g + 8) * ldp + c0) = pack_h2(d2, d3);
       s[nt][0] = d0; s[nt][1] = d1; s[nt][2] = d2; s[nt][3] = d3;
     }
-    // dQ = dS · K / 8   (A = dS from registers, B[k=key][n=dh] = K[key][dh] → Kᵀ tile)
+    // dQ = dS · K / 8   (A = dS from registers, B[k=key][n=dh] = K[key][dh] → ldmatrix.trans on K)
     float o[8][4];
 #pragma unroll
     for (int dn = 0; dn < 8; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.f;
@@ -312,11 +317,13 @@ attn_bwd_kernel(const __half* __restrict__ qkv, const __half* __restrict__ dout,
       af[1] = pack_h2(s[2 * kt][2], s[2 * kt][3]);
       af[2] = pack_h2(s[2 * kt + 1][0], s[2 * kt + 1][1]);
       af[3] = pack_h2(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+      const __half* krow = Ks + (kt * 16 + lm_row) * kQKld + lm_col;
 #pragma unroll
-      for (int dn = 0; dn < 8; ++dn) {
-        const uint32_t b0 = lds32(Kt + (dn * 8 + g) * ldv + kt * 16 + 2 * t);
-        const uint32_t b1 = lds32(Kt + (dn * 8 + g) * ldv + kt * 16 + 8 + 2 * t);
-        mma16816(o[dn], af, b0, b1);
+      for (int dn = 0; dn < 8; dn += 2) {
+        uint32_t bf[4];
+        ldmatrix_x4_trans(bf, krow + dn * 8);
+        mma16816(o[dn], af, bf[0], bf[1]);
+        mma16816(o[dn + 1], af, bf[2], bf[3]);
       }
     }
 #pragma unroll
@@ -332,7 +339,8 @@ attn_bwd_kernel(const __half* __restrict__ qkv, const __half* __restrict__ dout,
   }
   __syncthreads();
   // ---- phase 2: per key-row tile: dK = dSᵀ·Q/8, dV = Pᵀ·dO -------------------------------------
-  // A[m=key][k=query] = dS[query][key] → transposed read of the row-major smem tile (16-bit loads).
+  // A[m=key][k=query] = dS[query][key] (resp. P): the transposed fragments come from
+  // ldmatrix.x4.trans on the query-major tiles; B[k=query][n=dh] = Q / dO rows, also via .trans.
   for (int mt = warp; mt * 16 < L; mt += 4) {
     const int r0 = mt * 16;  // key rows
     float ok[8][4], ov[8][4];
@@ -345,31 +353,19 @@ attn_bwd_kernel(const __half* __restrict__ qkv, const __half* __restrict__ dout,
     for (int kt = 0; kt < NT / 2; ++kt) {
       const int q0 = kt * 16;  // query block
       uint32_t as[4], ap[4];
-      {
-        auto ldT = [&](const __half* M, int key, int qq) -> uint32_t {
-          const __half x = M[(qq)*ldp + key];
-          const __half y = M[(qq + 1) * ldp + key];
-          const __half2 v2 = __halves2half2(x, y);
-          return *reinterpret_cast<const uint32_t*>(&v2);
-        };
-        as[0] = ldT(dSs, r0 + g, q0 + 2 * t);
-        as[1] = ldT(dSs, r0 + g + 8, q0 + 2 * t);
-        as[2] = ldT(dSs, r0 + g, q0 + 8 + 2 * t);
-        as[3] = ldT(dSs, r0 + g + 8, q0 + 8 + 2 * t);
-        ap[0] = ldT(Ps, r0 + g, q0 + 2 * t);
-        ap[1] = ldT(Ps, r0 + g + 8, q0 + 2 * t);
-        ap[2] = ldT(Ps, r0 + g, q0 + 8 + 2 * t);
-        ap[3] = ldT(Ps, r0 + g + 8, q0 + 8 + 2 * t);
-      }
+      ldmatrix_x4_trans(as, dSs + (q0 + la_row) * ldp + r0 + la_col);
+      ldmatrix_x4_trans(ap, Ps + (q0 + la_row) * ldp + r0 + la_col);
+      const __half* qrow = Qs + (q0 + lm_row) * kQKld + lm_col;
+      const __half* drow = dOs + (q0 + lm_row) * kQKld + lm_col;
 #pragma unroll
-      for (int dn = 0; dn < 8; ++dn) {
-        // B[k=query][n=dh] = Q[query][dh] / dO[query][dh] → transposed tiles Qt / dOt
-        const uint32_t bq0 = lds32(Qt + (dn * 8 + g) * ldv + q0 + 2 * t);
-        const uint32_t bq1 = lds32(Qt + (dn * 8 + g) * ldv + q0 + 8 + 2 * t);
-        mma16816(ok[dn], as, bq0, bq1);
-        const uint32_t bd0 = lds32(dOt + (dn * 8 + g) * ldv + q0 + 2 * t);
-        const uint32_t bd1 = lds32(dOt + (dn * 8 + g) * ldv + q0 + 8 + 2 * t);
-        mma16816(ov[dn], ap, bd0, bd1);
+      for (int dn = 0; dn < 8; dn += 2) {
+        uint32_t bq[4], bd[4];
+        ldmatrix_x4_trans(bq, qrow + dn * 8);
+        ldmatrix_x4_trans(bd, drow + dn * 8);
+        mma16816(ok[dn], as, bq[0], bq[1]);
+        mma16816(ok[dn + 1], as, bq[2], bq[3]);
+        mma16816(ov[dn], ap, bd[0], bd[1]);
+        mma16816(ov[dn + 1], ap, bd[2], bd[3]);
       }
     }
     const int ra = r0 + g, rb = r0 + g + 8;
@@ -400,7 +396,7 @@ size_t fwd_smem() {
 template <int NT>
 size_t bwd_smem() {
   constexpr int Lp = NT * 8;
-  return (size_t)(4 * Lp * kQKld + 3 * kDh * (Lp + 8) + 2 * Lp * (Lp + 8)) * 2;
+  return (size_t)(4 * Lp * kQKld + 2 * Lp * (Lp + 8)) * 2;
 }
 
 template <int NT>

@@ -82,3 +82,10 @@ if what in ("vit", "all"):
         print(f"vit_forward B=1024 fold_ln={fold}: {ms:.3f} ms  ({1024/ms*1e3:.0f} img/s)  " +
               "  ".join(f"{s}: {v[1]/v[0]*1e3:.0f}us" for s, v in sorted(shapes.items())), flush=True)
         del eng
+
+if what in ("attnbwd", "all"):
+    for B, L, D, causal in ((512, 66, 768, 0), (1024, 50, 768, 0)):
+        qkv = torch.randn(B * L, 3 * D, device="cuda").half()
+        dout = torch.randn(B * L, D, device="cuda").half()
+        ms = timeit(lambda: ctx.attention_bwd(qkv, dout, B, L, D, causal))
+        print(f"attn bwd B={B} L={L}: {ms*1e3:.1f} us", flush=True)
