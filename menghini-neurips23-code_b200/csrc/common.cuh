@@ -110,6 +110,15 @@ template <int N>
 __device__ __forceinline__ void tma_store_wait_all() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
+// Warp-specialised register budgets: a warpgroup (4 consecutive warps) gives registers back / takes them.
+template <int N>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
 // L2 eviction policies (createpolicy encodings used by CUTLASS' CacheHintSm90).
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
@@ -169,6 +178,25 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
       : "r"(taddr)
       : "memory");
 }
+// 64 consecutive accumulator columns of this warp's 32 TMEM lanes → 64 registers per thread
+__device__ __forceinline__ void tmem_ld_32x64(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -208,6 +236,16 @@ __device__ __forceinline__ void tma_load_2d_2cta(void* dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
       "[%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+// Same, multicast: the box lands at the same smem offset in every CTA of `mask`, and each destination's
+// transaction bytes are signalled on ITS pair leader's barrier (peer bit cleared relative to the destination).
+__device__ __forceinline__ void tma_load_2d_2cta_mc(void* dst, const CUtensorMap* m, uint64_t* bar,
+                                                    int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      ".multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar) & kPeerBitMask), "h"(mask), "r"(c0), "r"(c1)
       : "memory");
 }
 // D[tmem, both CTAs] (+)= A · Bᵀ over the pair: M = 256 (128 rows per CTA), B's N split across CTAs.
@@ -295,10 +333,39 @@ __device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
                "r"(v.w)
                : "memory");
 }
+__device__ __forceinline__ float4 lds128f(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts128f(uint32_t saddr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
 __device__ __forceinline__ float quick_gelu(float x) {
   // x * sigmoid(1.702 x)   (openai/CLIP QuickGELU) = x / (1 + 2^(−1.702·log2(e)·x)); ex2.approx +
   // rcp.approx: ≈1e-7 relative, far below the fp16 rounding of the stored activation; branch-free
   return x * fast_rcp(1.0f + fast_exp2(-2.4554669595930157f * x));  // 2^t = inf → rcp = 0 → −0
+}
+
+// Four QuickGELUs sharing ONE reciprocal: 1/a, 1/b, 1/c, 1/d from r = 1/(abcd) by multiplications.  The
+// GEMM epilogue that applies the activation is bound by the SFU (16 lanes/clk/SM): this form issues
+// 1.25 MUFU per element instead of 2.  The denominators are clamped to 2^30 + 1 so the product of four
+// cannot overflow; the clamp only acts for x < −12.2, where x·σ(1.702x) is below fp16's smallest subnormal.
+__device__ __forceinline__ void quick_gelu4(float& a, float& b, float& c, float& d) {
+  constexpr float k = -2.4554669595930157f;  // −1.702·log2(e)
+  constexpr float kMax = 1073741824.f;       // 2^30
+  const float ea = fminf(fast_exp2(k * a), kMax) + 1.0f;
+  const float eb = fminf(fast_exp2(k * b), kMax) + 1.0f;
+  const float ec = fminf(fast_exp2(k * c), kMax) + 1.0f;
+  const float ed = fminf(fast_exp2(k * d), kMax) + 1.0f;
+  const float pab = ea * eb, pcd = ec * ed;
+  const float r = fast_rcp(pab * pcd);
+  const float rab = r * pcd, rcd = r * pab;  // 1/(ea·eb), 1/(ec·ed)
+  a *= rab * eb;
+  b *= rab * ea;
+  c *= rcd * ed;
+  d *= rcd * ec;
 }
 
 __device__ __forceinline__ float quick_gelu_grad(float x) {

@@ -66,14 +66,16 @@ extern "C" int gb_set_sm_limit(gb_ctx* c, int sms) {
 }
 
 int gb_make_tmap_2d_f16(gb_ctx* c, CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols,
-                        uint64_t ld_elems, uint32_t box_rows) {
+                        uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols) {
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld_elems * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
+  if (box_cols != 64 && box_cols != 32) return gb_fail(c, GB_ERR_ARG, "tensor map: box of %u columns", box_cols);
   CUresult r = c->encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims,
                                strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return gb_fail(c, GB_ERR_CUDA,

@@ -82,9 +82,10 @@ inline int gb_fail(gb_ctx* c, int code, const char* fmt, ...) {
     (c)->launches++;                                                                     \
   } while (0)
 
-// 2-D fp16 row-major tensor map with 128 B swizzle: box = {64 elements, box_rows}.
+// 2-D fp16 row-major tensor map: box = {box_cols elements, box_rows}; 128 B swizzle for 64-column
+// boxes, 64 B swizzle for 32-column boxes.
 int gb_make_tmap_2d_f16(gb_ctx* c, CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols,
-                        uint64_t ld_elems, uint32_t box_rows);
+                        uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols = 64);
 
 // LayerNorm-folding extras of a GEMM launch (see GemmParams): statistics consumed / produced.
 struct gb_gemm_ln {

@@ -5,6 +5,7 @@
 
 using namespace gb;
 
+
 template <int BN>
 static int launch_gemm_bn(gb_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmB,
                           const GemmParams& p, cudaStream_t st) {
@@ -27,22 +28,37 @@ static int launch_gemm_bn(gb_ctx* c, const CUtensorMap& tmA, const CUtensorMap& 
   return GB_OK;
 }
 
+template <int kMode>
 static int launch_gemm_2cta(gb_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                           const CUtensorMap& tmC, const GemmParams& p, cudaStream_t st) {
+                            const CUtensorMap& tmC, const GemmParams& p, cudaStream_t st) {
   using Cfg = Gemm2Cfg;
+  // One pair per cluster.  (The kernel also supports two pairs sharing their W tile through TMA
+  // multicast; measured on B200 at M = 51200, K = 768 / 3072 it gains nothing — the pair kernel is not
+  // bound by L2 bandwidth — and four-CTA clusters strand 16 of the 148 SMs.)
+  constexpr int kPairs = 1;
+  constexpr int kCluster = 2 * kPairs;
+  auto kernel = gemm_f16_tcgen05_2cta_kernel<kPairs, kMode>;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cfg.attrs = attr; cfg.numAttrs = 1;
   static bool attr_set[16] = {false};
   if (!attr_set[c->device & 15]) {
-    GB_CUDA(c, cudaFuncSetAttribute(gemm_f16_tcgen05_2cta_kernel,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    GB_CUDA(c, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set[c->device & 15] = true;
   }
-  const int m_pairs = (p.M + 2 * kBM - 1) / (2 * kBM);
-  const int tiles = m_pairs * (p.N / Cfg::BN);
-  const int max_clusters = gb_gemm_sms(c) / 2;
+  const int m_blocks = (p.M + 2 * kBM * kPairs - 1) / (2 * kBM * kPairs);
+  const int tiles = m_blocks * (p.N / Cfg::BN);
+  const int max_clusters = gb_gemm_sms(c) / kCluster;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  cfg.gridDim = dim3(kCluster * clusters);
   {
     gb_prof_scope prof(c, st, 0, 2.0 * p.M * p.N * p.K, p.M, p.N, p.K);
-    gemm_f16_tcgen05_2cta_kernel<<<2 * clusters, kGemmThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, tmC, p);
+    GB_CUDA(c, cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, tmC, p));
   }
   GB_LAUNCH_CHECK(c);
   return GB_OK;
@@ -64,7 +80,9 @@ int gb_launch_gemm(gb_ctx* c, const void* A, int lda, const void* W, int ldw, co
   // 256-wide tiles halve the per-FLOP shared-memory traffic.  The tile shape is a function of N only:
   // a row's arithmetic must not depend on how many other rows are in the batch (pseudolabels have to
   // be bit-identical however the pool is batched or sharded across GPUs).
-  const bool wide = (N % 256 == 0);
+  // (fp32 outputs — the final feature projections, a few MFLOP — use the single-CTA kernel's direct-store
+  // epilogue; the CTA-pair kernel only has the fp16 TMA-store epilogue)
+  const bool wide = (N % 256 == 0) && !out_f32;
   // wide tiles run on CTA pairs (each CTA stages half of the 256 W rows); otherwise one CTA, BN = 128
   const int BN = 128;
   CUtensorMap tmA, tmB;
@@ -78,7 +96,6 @@ int gb_launch_gemm(gb_ctx* c, const void* A, int lda, const void* W, int ldw, co
   p.bias = bias;
   p.resid = reinterpret_cast<const __half*>(resid); p.ldr = ldr;
   p.act = act; p.out_f32 = out_f32;
-  if (getenv("GB_DEBUG_NOSTORE")) p.out_f32 = 2;  // experiment: skip the epilogue's global stores
   p.aux = reinterpret_cast<__half*>(aux);
   p.ln_stats = nullptr; p.col_sum = nullptr; p.stats_out = nullptr;
   if (ln) {
@@ -92,13 +109,47 @@ int gb_launch_gemm(gb_ctx* c, const void* A, int lda, const void* W, int ldw, co
   if (act == 2 && !aux) return gb_fail(c, GB_ERR_ARG, "gemm: act 2 needs aux");
   if (aux && (out_f32 || (reinterpret_cast<uintptr_t>(aux) & 15))) return gb_fail(c, GB_ERR_ARG, "gemm: aux needs fp16 output layout and 16-byte alignment");
   if (!wide) return launch_gemm_bn<128>(c, tmA, tmB, p, st);
-  // output tensor map for the TMA-store epilogue (fp16 outputs): 64-column x 32-row boxes
-  CUtensorMap tmC = tmA;
-  if (!out_f32) {
-    rc = gb_make_tmap_2d_f16(c, &tmC, out, (uint64_t)M, (uint64_t)N, (uint64_t)ldo, 32);
-    if (rc) return rc;
+  // output tensor map for the TMA-store epilogue: 32-column x 32-row boxes (64 B swizzle)
+  CUtensorMap tmC;
+  rc = gb_make_tmap_2d_f16(c, &tmC, out, (uint64_t)M, (uint64_t)N, (uint64_t)ldo, 32, 32);
+  if (rc) return rc;
+  const bool fold = p.ln_stats != nullptr;
+  if (p.stats_out != nullptr && (fold || act != 0 || !resid))
+    return gb_fail(c, GB_ERR_ARG, "gemm: row statistics are emitted by the residual epilogue only");
+  if (act == 2) {
+    if (fold || resid || bias) return gb_fail(c, GB_ERR_ARG, "gemm: act 2 takes no bias / residual / LayerNorm");
+    return launch_gemm_2cta<kEpiAct2>(c, tmA, tmB, tmC, p, st);
   }
-  return launch_gemm_2cta(c, tmA, tmB, tmC, p, st);
+  if (act == 1) {
+    if (resid) return gb_fail(c, GB_ERR_ARG, "gemm: act 1 with a residual is not supported");
+    return fold ? launch_gemm_2cta<kEpiLnGelu>(c, tmA, tmB, tmC, p, st)
+                : launch_gemm_2cta<kEpiGelu>(c, tmA, tmB, tmC, p, st);
+  }
+  if (resid) {
+    if (fold) return gb_fail(c, GB_ERR_ARG, "gemm: folded LayerNorm with a residual is not supported");
+    return launch_gemm_2cta<kEpiResid>(c, tmA, tmB, tmC, p, st);
+  }
+  return fold ? launch_gemm_2cta<kEpiLn>(c, tmA, tmB, tmC, p, st)
+              : launch_gemm_2cta<kEpiPlain>(c, tmA, tmB, tmC, p, st);
+}
+
+// Debug hook (meaningful only in a -DGB_GEMM_STALLS build): accumulated stall counters of the CTA-pair
+// kernel since the last reset: [0] MMA waits for operands, [1] MMA waits for a drained accumulator,
+// [2] MMA thread total, [3] producer waits for a free slot, [4] epilogue warp 4 waits for the accumulator,
+// [5] epilogue warp 4 total, [7] number of MMA threads that reported.
+extern "C" int gb_debug_gemm_stalls(unsigned long long* out16, int reset) {
+#ifdef GB_GEMM_STALLS
+  if (cudaDeviceSynchronize() != cudaSuccess) return GB_ERR_CUDA;
+  if (out16 && cudaMemcpyFromSymbol(out16, g_gemm_stalls, 128) != cudaSuccess) return GB_ERR_CUDA;
+  if (reset) {
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyToSymbol(g_gemm_stalls, z, 128) != cudaSuccess) return GB_ERR_CUDA;
+  }
+  return GB_OK;
+#else
+  (void)out16; (void)reset;
+  return GB_ERR_ARG;
+#endif
 }
 
 extern "C" int gb_gemm_f16(gb_ctx* c, const void* A, int lda, const void* W, int ldw,

@@ -18,6 +18,22 @@
 
 namespace gb {
 
+// Optional stall accounting of the CTA-pair kernel (build with -DGB_GEMM_STALLS; read back with
+// gb_debug_gemm_stalls): cycles the MMA thread waits for operands / for a drained accumulator, the
+// producer for a free slot, and epilogue warp 4 for a finished accumulator.
+#ifdef GB_GEMM_STALLS
+__device__ unsigned long long g_gemm_stalls[16];
+#define GB_STALL_DECL(v) long long v = 0
+#define GB_STALL_T(t) const long long t = clock64()
+#define GB_STALL_ADD(v, t) v += clock64() - t
+#define GB_STALL_PUT(i, v) atomicAdd(&g_gemm_stalls[i], (unsigned long long)(v))
+#else
+#define GB_STALL_DECL(v)
+#define GB_STALL_T(t)
+#define GB_STALL_ADD(v, t)
+#define GB_STALL_PUT(i, v)
+#endif
+
 constexpr int kBM = 128;   // rows per tile  (UMMA M)
 constexpr int kBK = 64;    // fp16 elements per k-block = one 128 B swizzle atom
 constexpr int kUmmaK = 16;
@@ -132,7 +148,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
         }
       }
     }
-    if (row_ok && p.out_f32 != 2) {
+    if (row_ok) {
       if (p.act != 2 && has_pre) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -293,87 +309,119 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 }
 
 // Epilogue of one 128 x 256 accumulator tile with TMA stores (fp16 output).  Each of the 8 epilogue
-// warps owns 32 rows x 128 columns; it converts 64 columns at a time into a private 32 x 128-byte
-// shared-memory slab (128B-swizzled: quarter-warp accesses are conflict-free) and one lane hands the
-// slab to the TMA engine, which writes whole 128-byte lines and clips rows >= M.  Direct per-thread
-// stores (32 row-strided 16-byte pieces per instruction) were the bottleneck of every K=768 GEMM.
-// Two slabs per warp alternate, so a slab is rewritten only after the store issued two chunks
-// earlier has finished reading it.
-template <typename WaitAcc>
+// warps owns 32 rows x 128 columns.
+//  * A tcgen05.ld issued while the pair's MMAs are running takes ≈1-2 k clocks to deliver, so the warp
+//    pulls its entire 32 x 128 fp32 slice into registers with two back-to-back x64 loads, pays that
+//    latency once per tile, and releases the TMEM accumulator to the MMA thread immediately — the
+//    arithmetic, packing and stores then overlap the next-but-one tile's MMAs.  The epilogue
+//    warpgroups run with 232 registers (setmaxnreg); the TMA / MMA warpgroup gives its registers up.
+//  * The per-column constants (bias, and Σ_k W'[n,k] of a folded LayerNorm) of the warp's 128 columns
+//    are fetched one tile ahead with one coalesced 16-byte load per lane and parked in a warp-private
+//    shared-memory strip; the chunk loop reads them back as broadcasts.  (Read straight from global
+//    memory they cost an L2 round trip per 32-column chunk — the top stall of the epilogue.)
+//  * Output: 32 columns at a time into a private 32 x 64-byte shared-memory half-slab (64B-swizzled:
+//    quarter-warp accesses are conflict-free); one lane hands it to the TMA engine, which writes whole
+//    row segments and clips rows >= M.  Direct per-thread stores (32 row-strided 16-byte pieces per
+//    instruction) were the bottleneck of every K=768 GEMM.  Two half-slabs per warp alternate, so one
+//    is rewritten only after the store issued two chunks earlier has finished reading it.
+// Epilogue flavours of the CTA-pair kernel: one kernel instantiation each, so that an instantiation's
+// (fully unrolled) epilogue stays small — with every flavour behind run-time flags in one kernel the
+// epilogue warps spent 15-25 % of their issue slots waiting for instruction fetches.
+enum : int {
+  kEpiPlain = 0,   // [+ bias]
+  kEpiLn = 1,      // folded LayerNorm [+ bias]
+  kEpiResid = 2,   // [+ bias] + residual [→ row statistics]
+  kEpiGelu = 3,    // [+ bias], QuickGELU [pre-activation → aux]
+  kEpiLnGelu = 4,  // folded LayerNorm [+ bias], QuickGELU [pre-activation → aux]
+  kEpiAct2 = 5,    // × QuickGELU'(aux)   (backward of the activation)
+  kEpiModes = 6
+};
+
+template <int kMode, typename WaitAcc, typename ReleaseAcc>
 __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, const CUtensorMap* tmC,
                                                        uint8_t* slabs, uint32_t tmem_acc, int m0,
                                                        int n_base, int warp, int lane, float2& ln_st,
-                                                       int next_m0, WaitAcc&& wait_acc) {
+                                                       int next_m0, uint32_t consts_s, uint32_t consts_next_s,
+                                                       int next_n_base, WaitAcc&& wait_acc,
+                                                       ReleaseAcc&& release_acc) {
   constexpr int BN = 256;
+  constexpr bool kLn = kMode == kEpiLn || kMode == kEpiLnGelu;
+  constexpr bool kGelu = kMode == kEpiGelu || kMode == kEpiLnGelu;
+  constexpr bool kAct2 = kMode == kEpiAct2;
+  constexpr bool kPre = kMode == kEpiResid || kMode == kEpiAct2;
   const int q = warp & 3;
   const int half = (warp - 4) >> 2;
-  const __half* pre_base = (p.act == 2) ? p.aux : p.resid;
-  const int pre_ld = (p.act == 2) ? p.ldo : p.ldr;
+  const __half* pre_base = kAct2 ? p.aux : p.resid;
+  const int pre_ld = kAct2 ? p.ldo : p.ldr;
   const int n0 = n_base + half * (BN / 2);
   const int row0 = m0 + q * 32;
   const int row = row0 + lane;
   const bool row_ok = row < p.M;
-  const bool has_pre = pre_base != nullptr && row_ok;
-  uint4 pre[4], pre_next[4];
+  const bool has_pre = kPre && pre_base != nullptr && row_ok;
+  // the operand that comes from global memory (residual, or the saved pre-activation for act 2): this
+  // row's 128 columns are requested before the accumulator is even ready
+  uint4 pre[kPre ? 16 : 1];
   if (has_pre) {
     const uint4* r4 = reinterpret_cast<const uint4*>(pre_base + (size_t)row * pre_ld + n0);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) pre[j] = r4[j];
+    for (int j = 0; j < 16; ++j) pre[j] = r4[j];
   }
   // row statistics of the folded LayerNorm: (μ·rstd, rstd) of this tile's row were fetched while the
   // previous tile was processed; the next tile's are requested now
-  const bool ln = p.ln_stats != nullptr;
-  const float ln_mr = ln_st.x, ln_rstd = ln_st.y;
+  const float ln_mr = -ln_st.x, ln_rstd = ln_st.y;
   float2 ln_next = make_float2(0.f, 1.f);
-  if (ln && next_m0 >= 0) {
+  if (kLn && next_m0 >= 0) {
     const int nrow = next_m0 + q * 32 + lane;
     if (nrow < p.M) ln_next = *reinterpret_cast<const float2*>(p.ln_stats + (size_t)nrow * 2);
+  }
+  // next tile's per-column constants: lane l fetches columns 4l … 4l+3 of the warp's 128
+  float4 nb = make_float4(0.f, 0.f, 0.f, 0.f), ns = nb;
+  if (!kAct2 && next_n_base >= 0) {
+    const int nc = next_n_base + half * (BN / 2) + 4 * lane;
+    if (p.bias != nullptr) nb = __ldg(reinterpret_cast<const float4*>(p.bias + nc));
+    if (kLn) ns = __ldg(reinterpret_cast<const float4*>(p.col_sum + nc));
   }
   float st_sum = 0.f, st_sq = 0.f, st_x0 = 0.f;
   wait_acc();
   tc_fence_after();
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + half * (BN / 2);
-#pragma unroll 1
-  for (int c = 0; c < 4; ++c) {  // 32-column chunks; two chunks fill one slab
-    uint32_t v[32];
-    tmem_ld_32x32(taddr + c * 32, v);
-    const int col0 = n0 + c * 32;
-    if (has_pre && c + 1 < 4) {
-      const uint4* r4 = reinterpret_cast<const uint4*>(pre_base + (size_t)row * pre_ld + col0 + 32);
+  uint32_t v[128];
+  tmem_ld_32x64(taddr, v);
+  tmem_ld_32x64(taddr + 64, v + 64);
+  tmem_ld_wait();
+  tc_fence_before();
+  __syncwarp();
+  release_acc();  // the accumulator is in registers: the MMA thread may overwrite it
 #pragma unroll
-      for (int j = 0; j < 4; ++j) pre_next[j] = r4[j];
-    }
-    uint8_t* slab = slabs + ((c >> 1) & 1) * 4096;
+  for (int c = 0; c < 4; ++c) {  // 32-column chunks; two chunks fill one slab
+    const int col0 = n0 + c * 32;
+    uint8_t* slab = slabs + (c & 1) * 2048;
     const uint32_t slab_s = smem_u32(slab);
-    if ((c & 1) == 0) {
-      // the store that last used this slab (previous tile) must be done reading it
-      if (lane == 0) tma_store_wait_read<1>();
-      __syncwarp();
-    }
-    tmem_ld_wait();
+    // the store that last used this half-slab (two chunks ago) must be done reading it
+    if (lane == 0) tma_store_wait_read<1>();
+    __syncwarp();
     float f[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-    if (ln) {
-      const float4* s4 = reinterpret_cast<const float4*>(p.col_sum + col0);
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[32 * c + j]);
+    if constexpr (kLn) {
+      // rstd·(acc − μ·s_n) + b_n = acc·rstd + (b_n − (μ·rstd)·s_n): two FMAs per element
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 ss = __ldg(s4 + j);  // rstd·(acc − μ·s_n) = acc·rstd − (μ·rstd)·s_n
-        f[4 * j + 0] = fmaf(f[4 * j + 0], ln_rstd, -ln_mr * ss.x);
-        f[4 * j + 1] = fmaf(f[4 * j + 1], ln_rstd, -ln_mr * ss.y);
-        f[4 * j + 2] = fmaf(f[4 * j + 2], ln_rstd, -ln_mr * ss.z);
-        f[4 * j + 3] = fmaf(f[4 * j + 3], ln_rstd, -ln_mr * ss.w);
+        const float4 bb = lds128f(consts_s + (c * 32 + 4 * j) * 4);
+        const float4 ss = lds128f(consts_s + 512 + (c * 32 + 4 * j) * 4);
+        f[4 * j + 0] = fmaf(f[4 * j + 0], ln_rstd, fmaf(ln_mr, ss.x, bb.x));
+        f[4 * j + 1] = fmaf(f[4 * j + 1], ln_rstd, fmaf(ln_mr, ss.y, bb.y));
+        f[4 * j + 2] = fmaf(f[4 * j + 2], ln_rstd, fmaf(ln_mr, ss.z, bb.z));
+        f[4 * j + 3] = fmaf(f[4 * j + 3], ln_rstd, fmaf(ln_mr, ss.w, bb.w));
       }
-    }
-    if (p.bias != nullptr) {
-      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+    } else if (!kAct2 && p.bias != nullptr) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 bb = __ldg(b4 + j);
+        const float4 bb = lds128f(consts_s + (c * 32 + 4 * j) * 4);
         f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
       }
     }
-    if (p.act == 1) {
+    if constexpr (kGelu) {
       if (p.aux != nullptr && row_ok) {
         uint4* a4 = reinterpret_cast<uint4*>(p.aux + (size_t)row * p.ldo + col0);
 #pragma unroll
@@ -387,11 +435,11 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
         }
       }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
-    } else if (p.act == 2 && has_pre) {
+      for (int j = 0; j < 8; ++j) quick_gelu4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+    } else if (kAct2 && has_pre) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const __half2* h = reinterpret_cast<const __half2*>(&pre[j]);
+        const __half2* h = reinterpret_cast<const __half2*>(&pre[4 * c + j]);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const float2 x = __half22float2(h[t]);
@@ -400,10 +448,10 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
         }
       }
     }
-    if (p.act != 2 && has_pre) {
+    if (kMode == kEpiResid && has_pre) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const __half2* h = reinterpret_cast<const __half2*>(&pre[j]);
+        const __half2* h = reinterpret_cast<const __half2*>(&pre[4 * c + j]);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const float2 rf = __half22float2(h[t]);
@@ -412,7 +460,7 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
         }
       }
     }
-    // 64 bytes of this thread's row → 16-byte chunks 4·(c&1) … +3 of slab row `lane`
+    // 64 bytes of this thread's row → the four 16-byte pieces of half-slab row `lane`
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       uint4 o;
@@ -420,7 +468,7 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         h[t] = __floats2half2_rn(f[8 * j + 2 * t], f[8 * j + 2 * t + 1]);
-        if (p.stats_out != nullptr) {  // statistics of the values as stored (fp16-rounded)
+        if (kMode == kEpiResid && p.stats_out != nullptr) {  // statistics of the values as stored (fp16-rounded)
           const float2 r = __half22float2(h[t]);
           if (c == 0 && j == 0 && t == 0) st_x0 = r.x;
           const float d0 = r.x - st_x0, d1 = r.y - st_x0;
@@ -428,54 +476,57 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
           st_sq = fmaf(d0, d0, fmaf(d1, d1, st_sq));
         }
       }
-      const int chunk = (c & 1) * 4 + j;
-      sts128(slab_s + lane * 128 + ((chunk ^ (lane & 7)) << 4), o);
+      sts128(slab_s + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), o);
     }
-    if (c & 1) {
-      fence_proxy_async();  // generic-proxy writes → visible to the TMA engine
-      __syncwarp();
-      if (lane == 0) {
-        tma_store_2d(tmC, slab, n0 + (c >> 1) * 64, row0);
-        tma_store_commit();
-      }
+    fence_proxy_async();  // generic-proxy writes → visible to the TMA engine
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tmC, slab, col0, row0);
+      tma_store_commit();
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) pre[j] = pre_next[j];
   }
-  if (p.stats_out != nullptr && row_ok)
+  if (!kAct2 && next_n_base >= 0) {  // park the next tile's constants (all reads of this tile's are done)
+    sts128f(consts_next_s + lane * 16, nb);
+    if (kLn) sts128f(consts_next_s + 512 + lane * 16, ns);
+    __syncwarp();
+  }
+  if (kMode == kEpiResid && p.stats_out != nullptr && row_ok)
     *reinterpret_cast<float4*>(p.stats_out + ((size_t)(n0 >> 7) * p.M + row) * 4) =
         make_float4(st_x0, st_sum, st_sq, 0.f);
   ln_st = ln_next;
 }
 
-// Out-of-line copy of the direct-store epilogue for the CTA-pair kernel's rare fp32-output case (the
-// final feature projections), so that its register appetite does not constrain the fp16 hot path.
-__device__ __noinline__ void gemm_epilogue_tile_direct_256(const GemmParams& p, uint32_t tmem_acc,
-                                                           int m0, int n_base, int warp, int lane,
-                                                           uint64_t* bar, uint32_t phase) {
-  gemm_epilogue_tile<256>(p, tmem_acc, m0, n_base, warp, lane, [&]() { mbar_wait(bar, phase); });
-}
-
 // -------------------------------------------------------------------------------------------------
-// CTA-pair variant (cta_group::2), N % 256 == 0: a 2-CTA cluster computes 256 x 256 output tiles.
-// CTA r of the pair stages rows [256·mp + 128·r, +128) of A and rows [n0 + 128·r, +128) of W per
-// k-block (32 KB per stage instead of 48 KB → 6 stages), both signalling the LEADER's full barrier;
+// CTA-pair variant (cta_group::2), N % 256 == 0: a CTA pair computes 256 x 256 output tiles.
+// CTA h of the pair stages rows [m0 + 128·h, +128) of A and rows [n0 + 128·h, +128) of W per
+// k-block (32 KB per stage instead of 48 KB), both signalling the LEADER's full barrier;
 // the leader's single MMA thread issues 256x256x16 tcgen05.mma.cta_group::2 instructions whose
 // accumulator rows live in each CTA's own TMEM; commits are multicast to both CTAs' barriers; each
 // CTA's 8 epilogue warps drain their own 128 rows and release the accumulator on the leader.
+//
+// kPairs = 2 (cluster of 4): two pairs work on vertically adjacent 256-row tiles of the SAME 256
+// W rows.  At the tensor pipe's rate a pair-only kernel pulls 64 B/clk/SM out of L2 (9.5 KB/clk over
+// 148 SMs, above what the L2 slices deliver), which capped the K=768 GEMMs at 60-70 % tensor
+// activity.  Here CTA (pair p, half h) fetches only 64 of its 128 W rows and TMA-multicasts them to
+// CTA h of both pairs, so a CTA requests 24 KB instead of 32 KB per k-block.  A smem slot is then
+// written by both pairs' producers, hence a slot is free only when BOTH leaders' MMAs have retired
+// (empty barriers count kPairs arrivals; commits are multicast to the whole cluster).
+// Per-row arithmetic is identical for kPairs = 1 and 2 (same k order, same epilogue).
 // -------------------------------------------------------------------------------------------------
 struct Gemm2Cfg {
   static constexpr int BN = 256;
   static constexpr int kStages = 5;
-  static constexpr int kSlabBytes = 8 * 2 * 4096;      // two 32x128 B output slabs per epilogue warp
+  static constexpr int kSlabBytes = 8 * 2 * 2048;      // two 32x64 B output half-slabs per epilogue warp
+  static constexpr int kConstBytes = 8 * 2 * 1024;     // per warp, double-buffered: 128 biases + 128 column sums
   static constexpr int kABytes = kBM * kBK * 2;        // 16 KB: this CTA's 128 rows of A
   static constexpr int kBBytes = (BN / 2) * kBK * 2;   // 16 KB: this CTA's half of the W tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kSlabBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kSlabBytes + kConstBytes + 1024 + 256;
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+template <int kPairs, int kMode>
+__global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
                              const __grid_constant__ CUtensorMap tmB,
                              const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
@@ -489,7 +540,8 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * Cfg::kABytes;
   uint8_t* smem_slabs = smem + kStages * Cfg::kStageBytes;  // 1024-aligned: stage bytes are 32 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_slabs + Cfg::kSlabBytes);
+  uint8_t* smem_consts = smem_slabs + Cfg::kSlabBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_consts + Cfg::kConstBytes);
   uint64_t* full_bar = bars;                      // [kStages]  (used on the leader)
   uint64_t* empty_bar = bars + kStages;           // [kStages]  (each CTA waits on its own)
   uint64_t* tfull_bar = bars + 2 * kStages;       // [2]        (each CTA waits on its own)
@@ -499,14 +551,19 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const bool leader = rank == 0;
+  const uint32_t pair = rank >> 1;   // which 256-row tile of the cluster's row block
+  const uint32_t half = rank & 1;    // which CTA of the MMA pair
+  const bool leader = half == 0;
+  constexpr int kClusterRows = 2 * kBM * kPairs;
+  constexpr uint16_t kAllCtas = (1u << (2 * kPairs)) - 1;
 
-  const int m_pairs = (p.M + 2 * kBM - 1) / (2 * kBM);
+  const int m_blocks = (p.M + kClusterRows - 1) / kClusterRows;
   const int n_tiles = p.N / BN;
-  const int num_tiles = m_pairs * n_tiles;
+  const int num_tiles = m_blocks * n_tiles;
   const int k_blocks = p.K / kBK;
-  const int cluster_id = blockIdx.x >> 1;
-  const int num_clusters = gridDim.x >> 1;
+  const int cluster_id = blockIdx.x / (2 * kPairs);
+  const int num_clusters = gridDim.x / (2 * kPairs);
+  const int row_off = pair * 2 * kBM + half * kBM;  // this CTA's rows inside the cluster's row block
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -516,7 +573,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);   // leader's arrive.expect_tx covering both CTAs' loads
-      mbar_init(&empty_bar[s], 1);  // the leader's multicast commit
+      mbar_init(&empty_bar[s], kPairs);  // every leader's multicast commit
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);    // the leader's multicast commit
@@ -533,22 +590,35 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < 4) reg_dealloc<40>();  // warpgroup 0 (TMA, MMA, TMEM-alloc, idle) hands its registers over
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      GB_STALL_DECL(w_empty);
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m0 = (tile / n_tiles) * 2 * kBM + rank * kBM;
-        const int n0 = (tile % n_tiles) * BN + rank * (BN / 2);
+        const int m0 = (tile / n_tiles) * kClusterRows + row_off;
+        const int n0 = (tile % n_tiles) * BN + half * (BN / 2);
         for (int kb = 0; kb < k_blocks; ++kb) {
+          GB_STALL_T(t_e);
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          GB_STALL_ADD(w_empty, t_e);
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
           tma_load_2d_2cta(smem_a + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * kBK, m0);
-          tma_load_2d_2cta(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBK, n0);
+          if constexpr (kPairs == 1) {
+            tma_load_2d_2cta(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBK, n0);
+          } else {
+            // my 64-row slice of this half's W rows, delivered to CTA `half` of every pair
+            constexpr int kSlice = (BN / 2) / kPairs;
+            tma_load_2d_2cta_mc(smem_b + stage * Cfg::kBBytes + pair * (kSlice * kBK * 2), &tmB,
+                                &full_bar[stage], kb * kBK, n0 + pair * kSlice,
+                                static_cast<uint16_t>(0x5u << half));
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
+      (void)0;
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
@@ -557,50 +627,86 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      GB_STALL_DECL(w_full);
+      GB_STALL_DECL(w_tempty);
+      GB_STALL_T(t_mma0);
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
+        GB_STALL_T(t_te);
         mbar_wait(&tempty_bar[as], aphase ^ 1);
+        GB_STALL_ADD(w_tempty, t_te);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
         for (int kb = 0; kb < k_blocks; ++kb) {
+          GB_STALL_T(t_f);
           mbar_wait(&full_bar[stage], phase);
+          GB_STALL_ADD(w_full, t_f);
           tc_fence_after();
           const uint64_t adesc = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
           const uint64_t bdesc = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k)
             umma_f16_2cta(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          umma_commit_2cta(&empty_bar[stage], 0b11);  // frees the slot in both CTAs
+          umma_commit_2cta(&empty_bar[stage], kAllCtas);  // one of kPairs arrivals in every CTA
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit_2cta(&tfull_bar[as], 0b11);  // accumulator ready in both CTAs
+        umma_commit_2cta(&tfull_bar[as], static_cast<uint16_t>(0b11u << (2 * pair)));  // both CTAs of the pair
       }
+#ifdef GB_GEMM_STALLS
+      GB_STALL_PUT(0, w_full);
+      GB_STALL_PUT(1, w_tempty);
+      GB_STALL_PUT(2, clock64() - t_mma0);
+      GB_STALL_PUT(7, 1);
+#endif
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (8 warps, both CTAs) =====================
+    // ===================== epilogue (8 warps, both CTAs; fp16 output through TMA stores) =====================
+    reg_alloc<232>();
     int it = 0;
+    GB_STALL_DECL(w_tfull);
+    GB_STALL_T(t_epi0);
     float2 ln_st = make_float2(0.f, 1.f);
-    if (p.ln_stats != nullptr && cluster_id < num_tiles) {
-      const int r = (cluster_id / n_tiles) * 2 * kBM + rank * kBM + (warp & 3) * 32 + lane;
+    if ((kMode == kEpiLn || kMode == kEpiLnGelu) && cluster_id < num_tiles) {
+      const int r = (cluster_id / n_tiles) * kClusterRows + row_off + (warp & 3) * 32 + lane;
       if (r < p.M) ln_st = *reinterpret_cast<const float2*>(p.ln_stats + (size_t)r * 2);
+    }
+    const uint32_t consts_s = smem_u32(smem_consts + (warp - 4) * 2048);
+    if (kMode != kEpiAct2 && cluster_id < num_tiles) {  // the first tile's per-column constants
+      const int nc = (cluster_id % n_tiles) * BN + ((warp - 4) >> 2) * (BN / 2) + 4 * lane;
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f), cs = b;
+      if (p.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.bias + nc));
+      if (kMode == kEpiLn || kMode == kEpiLnGelu) cs = __ldg(reinterpret_cast<const float4*>(p.col_sum + nc));
+      sts128f(consts_s + lane * 16, b);
+      sts128f(consts_s + 512 + lane * 16, cs);
+      __syncwarp();
     }
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int m0 = (tile / n_tiles) * 2 * kBM + rank * kBM;
+      const int m0 = (tile / n_tiles) * kClusterRows + row_off;
       const int n0 = (tile % n_tiles) * BN;
       const int next = tile + num_clusters;
-      const int next_m0 = next < num_tiles ? (next / n_tiles) * 2 * kBM + rank * kBM : -1;
-      if (p.out_f32)
-        gemm_epilogue_tile_direct_256(p, tmem_base + as * BN, m0, n0, warp, lane, &tfull_bar[as], aphase);
-      else
-        gemm_epilogue_tile_tma(p, &tmC, smem_slabs + (warp - 4) * 8192, tmem_base + as * BN, m0, n0,
-                               warp, lane, ln_st, next_m0, [&]() { mbar_wait(&tfull_bar[as], aphase); });
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], 0);
+      const int next_m0 = next < num_tiles ? (next / n_tiles) * kClusterRows + row_off : -1;
+      const int next_n0 = next < num_tiles ? (next % n_tiles) * BN : -1;
+      gemm_epilogue_tile_tma<kMode>(
+          p, &tmC, smem_slabs + (warp - 4) * 4096, tmem_base + as * BN, m0, n0, warp, lane, ln_st, next_m0,
+          consts_s + (it & 1) * 1024, consts_s + ((it + 1) & 1) * 1024, next_n0,
+          [&]() {
+            GB_STALL_T(t_tf);
+            mbar_wait(&tfull_bar[as], aphase);
+            GB_STALL_ADD(w_tfull, t_tf);
+          },
+          [&]() {
+            if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], rank & ~1u);
+          });
     }
+#ifdef GB_GEMM_STALLS
+    if (leader && warp == 4 && lane == 0) {
+      GB_STALL_PUT(4, w_tfull);
+      GB_STALL_PUT(5, clock64() - t_epi0);
+    }
+#endif
     if (lane == 0) tma_store_wait_all<0>();  // all output tiles are in global memory before exit
   }
 
