@@ -342,7 +342,7 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
                                                        uint8_t* slabs, uint32_t tmem_acc, int m0,
                                                        int n_base, int warp, int lane, float2& ln_st,
                                                        int next_m0, uint32_t consts_s, uint32_t consts_next_s,
-                                                       int next_n_base, WaitAcc&& wait_acc,
+                                                       int next_n_base, uint4 (&pre_lo)[8], WaitAcc&& wait_acc,
                                                        ReleaseAcc&& release_acc) {
   constexpr int BN = 256;
   constexpr bool kLn = kMode == kEpiLn || kMode == kEpiLnGelu;
@@ -358,13 +358,15 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
   const int row = row0 + lane;
   const bool row_ok = row < p.M;
   const bool has_pre = kPre && pre_base != nullptr && row_ok;
-  // the operand that comes from global memory (residual, or the saved pre-activation for act 2): this
-  // row's 128 columns are requested before the accumulator is even ready
-  uint4 pre[kPre ? 16 : 1];
+  // The operand that comes from global memory (residual, or the saved pre-activation for act 2) is
+  // fetched half a tile ahead: columns 0-63 of this row arrived while the previous tile's second half
+  // was processed (pre_lo, carried across tiles); columns 64-127 are requested now, before the
+  // accumulator is even ready; the next tile's columns 0-63 once this tile's first half is done.
+  uint4 pre_hi[kPre ? 8 : 1];
   if (has_pre) {
-    const uint4* r4 = reinterpret_cast<const uint4*>(pre_base + (size_t)row * pre_ld + n0);
+    const uint4* r4 = reinterpret_cast<const uint4*>(pre_base + (size_t)row * pre_ld + n0 + 64);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) pre[j] = r4[j];
+    for (int j = 0; j < 8; ++j) pre_hi[j] = r4[j];
   }
   // row statistics of the folded LayerNorm: (μ·rstd, rstd) of this tile's row were fetched while the
   // previous tile was processed; the next tile's are requested now
@@ -393,8 +395,22 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
   __syncwarp();
   release_acc();  // the accumulator is in registers: the MMA thread may overwrite it
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {  // 32-column chunks; two chunks fill one slab
+  for (int c = 0; c < 4; ++c) {  // 32-column chunks, one half-slab each
     const int col0 = n0 + c * 32;
+    uint4 pre[kPre ? 4 : 1];
+    if constexpr (kPre) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pre[j] = c < 2 ? pre_lo[4 * c + j] : pre_hi[4 * (c - 2) + j];
+      if (c == 2 && next_m0 >= 0 && pre_base != nullptr) {  // pre_lo is free: the next tile's first half
+        const int nrow = next_m0 + q * 32 + lane;
+        if (nrow < p.M) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(pre_base + (size_t)nrow * pre_ld +
+                                                           next_n_base + half * (BN / 2));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pre_lo[j] = r4[j];
+        }
+      }
+    }
     uint8_t* slab = slabs + (c & 1) * 2048;
     const uint32_t slab_s = smem_u32(slab);
     // the store that last used this half-slab (two chunks ago) must be done reading it
@@ -439,7 +455,7 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
     } else if (kAct2 && has_pre) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const __half2* h = reinterpret_cast<const __half2*>(&pre[4 * c + j]);
+        const __half2* h = reinterpret_cast<const __half2*>(&pre[j]);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const float2 x = __half22float2(h[t]);
@@ -451,7 +467,7 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
     if (kMode == kEpiResid && has_pre) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const __half2* h = reinterpret_cast<const __half2*>(&pre[4 * c + j]);
+        const __half2* h = reinterpret_cast<const __half2*>(&pre[j]);
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const float2 rf = __half22float2(h[t]);
@@ -681,6 +697,18 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
       sts128f(consts_s + 512 + lane * 16, cs);
       __syncwarp();
     }
+    uint4 pre_lo[8];
+    if ((kMode == kEpiResid || kMode == kEpiAct2) && cluster_id < num_tiles) {  // first tile's columns 0-63
+      const __half* pre_base = kMode == kEpiAct2 ? p.aux : p.resid;
+      const int pre_ld = kMode == kEpiAct2 ? p.ldo : p.ldr;
+      const int r = (cluster_id / n_tiles) * kClusterRows + row_off + (warp & 3) * 32 + lane;
+      if (pre_base != nullptr && r < p.M) {
+        const uint4* r4 = reinterpret_cast<const uint4*>(
+            pre_base + (size_t)r * pre_ld + (cluster_id % n_tiles) * BN + ((warp - 4) >> 2) * (BN / 2));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pre_lo[j] = r4[j];
+      }
+    }
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -691,7 +719,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
       const int next_n0 = next < num_tiles ? (next % n_tiles) * BN : -1;
       gemm_epilogue_tile_tma<kMode>(
           p, &tmC, smem_slabs + (warp - 4) * 4096, tmem_base + as * BN, m0, n0, warp, lane, ln_st, next_m0,
-          consts_s + (it & 1) * 1024, consts_s + ((it + 1) & 1) * 1024, next_n0,
+          consts_s + (it & 1) * 1024, consts_s + ((it + 1) & 1) * 1024, next_n0, pre_lo,
           [&]() {
             GB_STALL_T(t_tf);
             mbar_wait(&tfull_bar[as], aphase);
