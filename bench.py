@@ -12,8 +12,11 @@ pseudolabel assignment (k=16) on the same batch:
   3. cosine logits, cross-entropy, backward to the prefix, SGD update   (:98-135)
   4. similarity + softmax + argmax + per-class leaderboard update with the current prompts
                                                            (assign_pseudo_labels, textual_fpl.py:195-283)
-`value` times this with the batch already resident in HBM; `e2e` feeds every step from pinned host
-memory (H2D copy inside the timed region, double buffered) and reads the loss and predictions back.
+Images are raw uint8 pixels (the resized + centre-cropped crop); ToTensor + Normalize run on the device,
+fused into the patch gather, bit-identical to the reference's host transform (tests/test_gpu_towers.py).
+`value` times the step with the batch already resident in HBM; `e2e` feeds every step from pinned host
+memory (H2D copy inside the timed region, double buffered) and reads the loss and predictions back;
+`e2e_f32` is the same with host-normalised fp32 tensors, what the reference's DataLoader hands over.
 """
 from __future__ import annotations
 
@@ -62,9 +65,9 @@ def workload_name(a, batch):
     if getattr(a, "workload", "coop") == "vpt":
         return (f"VPT prompt-tune step (P={a.prefix}, C={a.classes}, ViT-B/32, SGD; forward with tape + "
                 f"prompt-only backward through the image tower) + FPL pseudolabel leaderboard (k={a.k}) on "
-                f"{batch} synthetic 224x224x3 fp32 images per GPU per step")
+                f"{batch} synthetic 224x224x3 uint8 images per GPU per step")
     return (f"CoOp prompt-tune step (P={a.prefix}, C={a.classes}, ViT-B/32, SGD) + FPL pseudolabel "
-            f"leaderboard (k={a.k}) on {batch} synthetic 224x224x3 fp32 images per GPU per step")
+            f"leaderboard (k={a.k}) on {batch} synthetic 224x224x3 uint8 images per GPU per step")
 
 
 # --------------------------------------------------------------------------------------------------
@@ -230,7 +233,8 @@ def run_b200(a, rank, local_rank, world):
     state = {"step": 0, "board": board}
 
     gi = torch.Generator().manual_seed(100 + rank)
-    host = [torch.randn(B, 3, 224, 224, generator=gi).pin_memory() for _ in range(2)]
+    host = [torch.randint(0, 256, (B, 3, 224, 224), generator=gi, dtype=torch.uint8).pin_memory()
+            for _ in range(2)]
     host_labels = [(torch.randint(0, C, (B,), generator=gi)).pin_memory() for _ in range(2)]
     dev_img = [h.to(dev) for h in host]
     dev_lab = [h.to(dev) for h in host_labels]
@@ -432,53 +436,68 @@ def run_b200(a, rank, local_rank, world):
 
     # ---- end-to-end arm: pinned host → device every step, loss + predictions read back ---------
     copy_stream = torch.cuda.Stream(device=dev)
-    copied = [torch.cuda.Event(), torch.cuda.Event()]
-    consumed = [torch.cuda.Event(), torch.cuda.Event()]
-    consumed_side = [torch.cuda.Event(), torch.cuda.Event()]  # labels are read by the side stream
     main = torch.cuda.current_stream()
-
-    def prefetch(i):
-        b = i % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[b])
-            copy_stream.wait_event(consumed_side[b])
-            dev_img[b].copy_(host[b], non_blocking=True)
-            dev_lab[b].copy_(host_labels[b], non_blocking=True)
-            copied[b].record(copy_stream)
-
     side = side_stream if overlap else main_stream
 
-    def e2e_step(i):
-        b = i % 2
-        prefetch(i + 1)               # next batch streams in while this one computes
-        main.wait_event(copied[b])
-        loss = step(dev_img[b], dev_lab[b])
-        consumed[b].record(main)
-        with torch.cuda.stream(side):
-            consumed_side[b].record(side)
-            out_loss.copy_(loss.detach().reshape(1), non_blocking=True)
-            out_pred.copy_(state["pred"], non_blocking=True)
-        # the caller reads loss / predictions every step: with the text chain overlapped the values read
-        # here are those of the previous step (its side-stream work is what we wait for)
-        if overlap:
-            if state.get("prev_done") is not None:
-                state["prev_done"].synchronize()
-            state["prev_done"] = torch.cuda.Event()
-            state["prev_done"].record(side)
-        else:
-            main.synchronize()
+    def run_e2e(host_img, dev_bufs):
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed_side = [torch.cuda.Event(), torch.cuda.Event()]  # labels are read by the side stream
 
-    join()
-    for b in range(2):
-        consumed[b].record(main)
-        consumed_side[b].record(main)
-    prefetch(0)
-    for i in range(a.warmup):
-        e2e_step(i)
-    ms_e2e, _ = timed(lambda i: e2e_step(i + a.warmup), a.steps)
+        def prefetch(i):
+            b = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[b])
+                copy_stream.wait_event(consumed_side[b])
+                dev_bufs[b].copy_(host_img[b], non_blocking=True)
+                dev_lab[b].copy_(host_labels[b], non_blocking=True)
+                copied[b].record(copy_stream)
+
+        def e2e_step(i):
+            b = i % 2
+            prefetch(i + 1)               # next batch streams in while this one computes
+            main.wait_event(copied[b])
+            loss = step(dev_bufs[b], dev_lab[b])
+            consumed[b].record(main)
+            with torch.cuda.stream(side):
+                consumed_side[b].record(side)
+                out_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+                out_pred.copy_(state["pred"], non_blocking=True)
+            # the caller reads loss / predictions every step: with the text chain overlapped the values read
+            # here are those of the previous step (its side-stream work is what we wait for)
+            if overlap:
+                if state.get("prev_done") is not None:
+                    state["prev_done"].synchronize()
+                state["prev_done"] = torch.cuda.Event()
+                state["prev_done"].record(side)
+            else:
+                main.synchronize()
+
+        join()
+        torch.cuda.synchronize()
+        for b in range(2):
+            consumed[b].record(main)
+            consumed_side[b].record(main)
+        prefetch(0)
+        for i in range(a.warmup):
+            e2e_step(i)
+        ms_, _ = timed(lambda i: e2e_step(i + a.warmup), a.steps)
+        torch.cuda.synchronize()
+        return ms_
+
+    ms_e2e = run_e2e(host, dev_img)
     e2e_value = a.steps * B * world / (ms_e2e / 1e3)
-    h2d = B * 3 * 224 * 224 * 4 + B * 8
+    h2d = B * 3 * 224 * 224 + B * 8
     d2h = 4 + B * 4
+    # the same with the fp32 tensors the reference's DataLoader yields (4x the bytes over PCIe)
+    host_f32 = [importlib.import_module(PKG + ".clip").normalize_u8(h).pin_memory() for h in host]
+    dev_f32 = [torch.empty(B, 3, 224, 224, device=dev) for _ in range(2)]
+    ms_e2e_f32 = run_e2e(host_f32, dev_f32)
+    e2e_f32 = {"value": a.steps * B * world / (ms_e2e_f32 / 1e3), "unit": "images/s",
+               "ms_per_step": ms_e2e_f32 / a.steps, "h2d_bytes_per_step": B * 3 * 224 * 224 * 4 + B * 8,
+               "d2h_bytes_per_step": d2h,
+               "note": "host-normalised fp32 tensors (the reference DataLoader's output) instead of uint8 pixels"}
+    del host_f32, dev_f32
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps,
@@ -486,7 +505,10 @@ def run_b200(a, rank, local_rank, world):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f16 (fp32 accumulate)",
                 "data": "synthetic",
                 "config": {"workload": workload_name(a, B), "weights": "random-init ViT-B/32 (seed 1234)",
-                           "l2_policy": "inputs larger than L2 (616 MB image batch per step)",
+                           "l2_policy": "inputs larger than L2 (154 MB uint8 image batch per step + 0.3 GB of weights, "
+                                        "~2 GB of activations)",
+                           "input": "uint8 pixels, ToTensor + Normalize fused into the patch gather on the device "
+                                    "(bit-identical to host-normalised fp32 input)",
                            "parallelism": f"dp{world}: image batch and pool sharded, prefix-grad all-reduce, "
                                           f"ordered leaderboard hand-off" if world > 1 else "single GPU",
                            "streams": (f"image tower on the main stream (GEMM grids capped at {a.sm_limit} SMs), text "
@@ -496,6 +518,7 @@ def run_b200(a, rank, local_rank, world):
                 "clocks": clk.summary(), "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / a.steps,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e_f32": e2e_f32,
                 "roofline": roofline, "roofline_sim": roofline_sim}
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_arm(a, 1000, 1, budget_s=15.0)[0]

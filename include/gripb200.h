@@ -143,10 +143,16 @@ size_t gb_tape_bytes(int samples, int L, int D, int layers);
 /* CustomVisionTransformer.forward (models/clip_encoders.py:123-194) / encode_image when P == 0:
  * conv1 patch embed, CLS + positional embedding, P prefix rows inserted after CLS (no positional
  * embedding), ln_pre, 12 blocks, ln_post(CLS) @ proj.
- *   img    : [B,3,224,224] NCHW, fp32 (img_f32 != 0) or fp16          prefix : fp32 [P,768] or NULL
+ *   img    : [B,3,224,224] NCHW; img_f32 selects the element type: GB_IMG_F16 (0), GB_IMG_F32 (1) —
+ *            already normalised, what the reference's DataLoader yields — or GB_IMG_U8 (2): raw 0..255
+ *            pixels of the resized / centre-cropped image, ToTensor + Normalize(CLIP mean, std) applied
+ *            on the device with torch's own fp32 operation order (bit-identical features, 4x fewer
+ *            host→device bytes)
+ *   prefix : fp32 [P,768] or NULL
  *   feat   : fp32 [B,512] un-normalised (what the reference modules return) or NULL
  *   featn  : fp16 [B,512] L2-normalised rows (input of gb_sim_softmax_argmax) or NULL
  *   tape   : gb_tape_bytes(B, 50+P, 768, 12) bytes or NULL (inference) */
+enum { GB_IMG_F16 = 0, GB_IMG_F32 = 1, GB_IMG_U8 = 2 };
 int gb_vit_forward(gb_ctx* ctx, const void* img, int img_f32, const float* prefix, int B, int P,
                    float* feat, void* featn, void* tape, void* stream);
 /* dprefix fp32 [P,768] = d loss / d prefix given dfeat fp32 [B,512] (autograd through

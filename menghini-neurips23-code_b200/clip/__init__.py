@@ -33,8 +33,10 @@ def available_models():
     return ["ViT-B/32"]
 
 
-def _preprocess():
-    """CLIP's transform: Resize(224, bicubic) → CenterCrop → RGB → ToTensor → Normalize."""
+def _preprocess(raw: bool = False):
+    """CLIP's transform: Resize(224, bicubic) → CenterCrop → RGB → ToTensor → Normalize.
+    raw=True stops after the crop and returns the uint8 [3,224,224] pixels: the image tower applies
+    ToTensor + Normalize on the device (bit-identical features, a quarter of the host→device bytes)."""
     import numpy as np
     from PIL import Image
 
@@ -48,10 +50,24 @@ def _preprocess():
         w, h = img.size
         l, t = (w - 224) // 2, (h - 224) // 2
         img = img.crop((l, t, l + 224, t + 224)).convert("RGB")
-        x = torch.from_numpy(np.asarray(img, dtype=np.uint8).copy()).permute(2, 0, 1).float() / 255.0
-        return (x - mean) / std
+        x = torch.from_numpy(np.asarray(img, dtype=np.uint8).copy()).permute(2, 0, 1)
+        if raw:
+            return x.contiguous()
+        return (x.float() / 255.0 - mean) / std
 
     return transform
+
+
+def preprocess_u8():
+    """The transform of `load()` without its ToTensor/Normalize tail (see `_preprocess`)."""
+    return _preprocess(raw=True)
+
+
+def normalize_u8(x: torch.Tensor) -> torch.Tensor:
+    """Host restatement of what the device does with uint8 pixels [..., 3, 224, 224] (ToTensor + Normalize)."""
+    mean = torch.tensor((0.48145466, 0.4578275, 0.40821073)).view(3, 1, 1)
+    std = torch.tensor((0.26862954, 0.26130258, 0.27577711)).view(3, 1, 1)
+    return (x.float() / 255.0 - mean) / std
 
 
 def load(name="ViT-B/32", device="cuda", jit=False, state_dict=None, download_root=None):

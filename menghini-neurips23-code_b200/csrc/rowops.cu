@@ -118,6 +118,40 @@ im2col_patch32_kernel(const InT* __restrict__ img, __half* __restrict__ out, int
   *reinterpret_cast<uint4*>(dst) = o;
 }
 
+// Same re-index for raw uint8 pixels [B,3,224,224], with the reference's preprocessing tail fused in:
+// torchvision ToTensor (x/255 in fp32) followed by Normalize with CLIP's mean / std ((x − mean)/std,
+// clip.load's `_transform`; used by the reference at data/dataset.py:64-79).  The three fp32 operations
+// are the ones torch performs, in the same order and rounding, so the fp16 operand written here is
+// bit-identical to feeding the host-normalised fp32 tensor — at a quarter of the host→device bytes.
+__global__ void __launch_bounds__(256)
+im2col_patch32_u8_kernel(const uint8_t* __restrict__ img, __half* __restrict__ out, int B) {
+  // one thread per 16 consecutive kx: total = B*3*224*14 groups
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)B * 3 * 224 * 14;
+  if (gid >= total) return;
+  const int x16 = gid % 14;
+  const int y = (gid / 14) % 224;
+  const int c = (gid / (14 * 224)) % 3;
+  const int b = gid / (14 * 224 * 3);
+  const float mean = c == 0 ? 0.48145466f : (c == 1 ? 0.4578275f : 0.40821073f);
+  const float sd = c == 0 ? 0.26862954f : (c == 1 ? 0.26130258f : 0.27577711f);
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(img + (((size_t)b * 3 + c) * 224 + y) * 224 + x16 * 16));
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  uint4 o[2];
+  __half2* h = reinterpret_cast<__half2*>(o);
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const uint32_t word = w[t >> 1] >> ((t & 1) * 16);
+    const float a = __fdiv_rn(__fsub_rn(__fdiv_rn((float)(word & 0xffu), 255.0f), mean), sd);
+    const float d = __fdiv_rn(__fsub_rn(__fdiv_rn((float)((word >> 8) & 0xffu), 255.0f), mean), sd);
+    h[t] = __floats2half2_rn(a, d);
+  }
+  const int py = y >> 5, ky = y & 31, px = (x16 * 16) >> 5, kx = (x16 * 16) & 31;
+  uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)b * 49 + py * 7 + px) * 3072 + c * 1024 + ky * 32 + kx);
+  dst[0] = o[0];
+  dst[1] = o[1];
+}
+
 // ---------------------------------------------------------------------------------------------
 // Vision token assembly fused with ln_pre (D = 768):
 //   row l of image b:  l == 0      → class_embedding + pos[0]
@@ -506,11 +540,14 @@ int gb_launch_layernorm(gb_ctx* c, const void* x, int ldx, const int32_t* row_id
   return GB_OK;
 }
 
-int gb_launch_im2col(gb_ctx* c, const void* img, int img_f32, void* out, int B, cudaStream_t st) {
+int gb_launch_im2col(gb_ctx* c, const void* img, int img_fmt, void* out, int B, cudaStream_t st) {
   if (B <= 0) return GB_OK;
-  const size_t total = (size_t)B * 3 * 224 * 28;
+  if (img_fmt < 0 || img_fmt > GB_IMG_U8) return gb_fail(c, GB_ERR_ARG, "im2col: unknown image format %d", img_fmt);
+  if (reinterpret_cast<uintptr_t>(img) & 15) return gb_fail(c, GB_ERR_ARG, "im2col: image pointer must be 16-byte aligned");
+  const size_t total = (size_t)B * 3 * 224 * (img_fmt == GB_IMG_U8 ? 14 : 28);
   const int grid = (int)((total + 255) / 256);
-  if (img_f32) im2col_patch32_kernel<float><<<grid, 256, 0, st>>>((const float*)img, (__half*)out, B);
+  if (img_fmt == GB_IMG_U8) im2col_patch32_u8_kernel<<<grid, 256, 0, st>>>((const uint8_t*)img, (__half*)out, B);
+  else if (img_fmt == GB_IMG_F32) im2col_patch32_kernel<float><<<grid, 256, 0, st>>>((const float*)img, (__half*)out, B);
   else im2col_patch32_kernel<__half><<<grid, 256, 0, st>>>((const __half*)img, (__half*)out, B);
   GB_LAUNCH_CHECK(c);
   return GB_OK;

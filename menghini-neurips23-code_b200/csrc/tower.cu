@@ -24,7 +24,7 @@ int gb_launch_layernorm(gb_ctx* c, const void* x, int ldx, const int32_t* row_id
 int gb_launch_layernorm_bwd(gb_ctx* c, const void* dy, int lddy, const void* x, int ldx,
                             const int32_t* row_idx, int in_row_mul, const float* gamma, void* dx,
                             int lddx, int rows, int D, int accumulate, cudaStream_t st);
-int gb_launch_im2col(gb_ctx* c, const void* img, int img_f32, void* out, int B, cudaStream_t st);
+int gb_launch_im2col(gb_ctx* c, const void* img, int img_fmt, void* out, int B, cudaStream_t st);
 int gb_launch_vit_assemble(gb_ctx* c, const void* patch, const float* cls, const float* pos,
                            const float* prefix, int P, const float* gamma, const float* beta,
                            void* x, int B, cudaStream_t st, float* stats);

@@ -145,15 +145,19 @@ class Engine:
 
     def vit_forward(self, img: torch.Tensor, prefix: Optional[torch.Tensor] = None,
                     want_feat=True, want_featn=False, tape: bool = False):
-        """img [B,3,224,224] fp32/fp16 on this device; prefix fp32 [P,768] or None.
+        """img [B,3,224,224] on this device: fp32 / fp16 already normalised (what the reference's
+        DataLoader yields), or uint8 raw pixels of the resized + centre-cropped image — ToTensor and
+        Normalize(CLIP mean, std) then run on the device, fused into the patch gather, with torch's own
+        fp32 operation order (bit-identical features).  prefix fp32 [P,768] or None.
         Returns (feat fp32 [B,512] | None, featn fp16 [B,512] | None, tape | None)."""
         if img.device != self.device:
             raise GripB200Error(f"image batch is on {img.device}, engine on {self.device}")
         if img.dim() != 4 or tuple(img.shape[1:]) != (3, 224, 224):
             raise GripB200Error(f"expected [B,3,224,224] images, got {tuple(img.shape)}")
-        if img.dtype not in (torch.float32, torch.float16):
+        if img.dtype not in (torch.float32, torch.float16, torch.uint8):
             img = img.float()
         img = img.contiguous()
+        fmt = {torch.float16: 0, torch.float32: 1, torch.uint8: 2}[img.dtype]
         B = img.shape[0]
         P = 0
         if prefix is not None:
@@ -165,7 +169,7 @@ class Engine:
         if tape:
             tp = torch.empty(self.tape_bytes(B, 50 + P, V_WIDTH), device=self.device, dtype=torch.uint8)
         self._bind()
-        rc = self.lib.gb_vit_forward(self.ctx.h, ptr(img), int(img.dtype == torch.float32),
+        rc = self.lib.gb_vit_forward(self.ctx.h, ptr(img), fmt,
                                      ptr(prefix) if P else None, B, P, ptr(feat), ptr(featn), ptr(tp),
                                      stream_ptr())
         self.ctx.check(rc, "gb_vit_forward")

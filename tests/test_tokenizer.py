@@ -89,3 +89,21 @@ def test_clip_tokenize_with_vocab_file(toks, tmp_path, monkeypatch):
     with pytest.raises(RuntimeError):
         clip.tokenize(" ".join(["land"] * 100))
     assert clip.tokenize(" ".join(["land"] * 100), truncate=True)[0, -1] == eot
+
+
+def test_preprocess_u8_is_the_transform_without_its_normalisation_tail():
+    """clip.preprocess_u8() stops after resize + centre crop; normalize_u8 (the host restatement of what the
+    device applies to uint8 pixels) then reproduces clip.load's transform bit for bit."""
+    import importlib
+
+    import numpy as np
+    import torch
+    from PIL import Image
+
+    clip = importlib.import_module("menghini-neurips23-code_b200.clip")
+    rng = np.random.RandomState(0)
+    img = Image.fromarray(rng.randint(0, 256, (300, 260, 3), dtype=np.uint8))
+    full = clip._preprocess()(img)
+    raw = clip.preprocess_u8()(img)
+    assert raw.dtype == torch.uint8 and tuple(raw.shape) == (3, 224, 224)
+    assert torch.equal(clip.normalize_u8(raw), full)
