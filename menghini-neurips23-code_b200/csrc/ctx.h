@@ -90,6 +90,8 @@ int gb_make_tmap_2d_f16(gb_ctx* c, CUtensorMap* out, const void* ptr, uint64_t r
 // LayerNorm-folding extras of a GEMM launch (see GemmParams): statistics consumed / produced.
 struct gb_gemm_ln {
   const float* ln_stats = nullptr;  // [M][2] (μ·rstd, rstd) of A's rows → fold LayerNorm into this GEMM
+  const float* ln_parts = nullptr;  // … or [nparts][M] float4 partials as a GEMM's stats_out left them
+  int nparts = 0;                   //   (merged in the epilogue; K / nparts columns per segment)
   const float* col_sum = nullptr;   // [N]
   float* stats_out = nullptr;      // [N/128][M][2] partial statistics of the output rows
 };

@@ -98,12 +98,20 @@ int gb_launch_gemm(gb_ctx* c, const void* A, int lda, const void* W, int ldw, co
   p.act = act; p.out_f32 = out_f32;
   p.aux = reinterpret_cast<__half*>(aux);
   p.ln_stats = nullptr; p.col_sum = nullptr; p.stats_out = nullptr;
+  p.ln_parts = nullptr; p.ln_nparts = 0; p.ln_seg_n = 1.f;
   if (ln) {
     if (out_f32 || N % 256 != 0)
       return gb_fail(c, GB_ERR_ARG, "gemm: LayerNorm folding needs fp16 output and N %% 256 == 0");
-    if ((ln->ln_stats != nullptr) != (ln->col_sum != nullptr))
+    const bool fold_in = ln->ln_stats != nullptr || ln->ln_parts != nullptr;
+    if (fold_in != (ln->col_sum != nullptr) || (ln->ln_stats && ln->ln_parts) ||
+        (ln->ln_parts && (ln->nparts < 1 || ln->nparts > 6 || K % ln->nparts != 0)))
       return gb_fail(c, GB_ERR_ARG, "gemm: inconsistent LayerNorm folding arguments");
     p.ln_stats = ln->ln_stats; p.col_sum = ln->col_sum;
+    if (ln->ln_parts) {
+      p.ln_parts = reinterpret_cast<const float4*>(ln->ln_parts);
+      p.ln_nparts = ln->nparts;
+      p.ln_seg_n = (float)(K / ln->nparts);
+    }
     p.stats_out = ln->stats_out;
   }
   if (act == 2 && !aux) return gb_fail(c, GB_ERR_ARG, "gemm: act 2 needs aux");
@@ -113,7 +121,7 @@ int gb_launch_gemm(gb_ctx* c, const void* A, int lda, const void* W, int ldw, co
   CUtensorMap tmC;
   rc = gb_make_tmap_2d_f16(c, &tmC, out, (uint64_t)M, (uint64_t)N, (uint64_t)ldo, 32, 32);
   if (rc) return rc;
-  const bool fold = p.ln_stats != nullptr;
+  const bool fold = p.ln_stats != nullptr || p.ln_parts != nullptr;
   if (p.stats_out != nullptr && (fold || act != 0 || !resid))
     return gb_fail(c, GB_ERR_ARG, "gemm: row statistics are emitted by the residual epilogue only");
   if (act == 2) {

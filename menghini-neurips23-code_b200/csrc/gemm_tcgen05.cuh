@@ -55,6 +55,11 @@ struct GemmParams {
   // so A is the raw residual stream and the row statistics are applied in the epilogue.
   const float* ln_stats;  // [M][2] = (μ·rstd, rstd) of each row of A, or nullptr
   const float* col_sum;   // s_n, [N]
+  // … or the row statistics still in the form the producing GEMM left them (its stats_out): the
+  // epilogue merges the ln_nparts segments of a row itself, one tile ahead (no finalize launch)
+  const float4* ln_parts;  // [ln_nparts][M] (x0, Σ(x−x0), Σ(x−x0)², −), or nullptr
+  int ln_nparts;           // ≤ 6
+  float ln_seg_n;          // columns per segment
   // shifted partial sums of every OUTPUT row over this warp's 128 columns, [N/128][M] float4 =
   // (x0, Σ(x−x0), Σ(x−x0)², −) with x0 the segment's first stored value, or nullptr: the statistics the
   // next LayerNorm needs, produced where the rows are written.  The shift keeps the later variance
@@ -324,6 +329,33 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 //    row segments and clips rows >= M.  Direct per-thread stores (32 row-strided 16-byte pieces per
 //    instruction) were the bottleneck of every K=768 GEMM.  Two half-slabs per warp alternate, so one
 //    is rewritten only after the store issued two chunks earlier has finished reading it.
+// (μ·rstd, rstd) of one row from its per-segment shifted partials (x0, Σ(x−x0), Σ(x−x0)²): per segment
+// mean and centred second moment, then Chan's pairwise update in a fixed segment order (deterministic,
+// free of the E[x²]−μ² cancellation; same arithmetic as ln_finalize_kernel in rowops.cu).
+__device__ __forceinline__ float2 ln_merge_parts(const float4 (&lp)[6], int nparts, float seg_n) {
+  float n = 0.f, mean = 0.f, m2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    if (i < nparts) {
+      const float4 t = lp[i];
+      const float mp = t.x + t.y / seg_n;
+      const float m2p = t.z - t.y * t.y / seg_n;
+      const float nn = n + seg_n;
+      const float delta = mp - mean;
+      mean += delta * (seg_n / nn);
+      m2 += m2p + delta * delta * (n * seg_n / nn);
+      n = nn;
+    }
+  }
+  const float rstd = rsqrtf(fmaxf(m2 / n, 0.f) + 1e-5f);
+  return make_float2(mean * rstd, rstd);
+}
+__device__ __forceinline__ void ln_load_parts(const GemmParams& p, int row, float4 (&lp)[6]) {
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+    if (i < p.ln_nparts) lp[i] = __ldg(p.ln_parts + (size_t)i * p.M + row);
+}
+
 // Epilogue flavours of the CTA-pair kernel: one kernel instantiation each, so that an instantiation's
 // (fully unrolled) epilogue stays small — with every flavour behind run-time flags in one kernel the
 // epilogue warps spent 15-25 % of their issue slots waiting for instruction fetches.
@@ -372,10 +404,11 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
   // previous tile was processed; the next tile's are requested now
   const float ln_mr = -ln_st.x, ln_rstd = ln_st.y;
   float2 ln_next = make_float2(0.f, 1.f);
-  if (kLn && next_m0 >= 0) {
-    const int nrow = next_m0 + q * 32 + lane;
-    if (nrow < p.M) ln_next = *reinterpret_cast<const float2*>(p.ln_stats + (size_t)nrow * 2);
-  }
+  const int ln_nrow = next_m0 + q * 32 + lane;
+  const bool ln_parts_next = kLn && p.ln_parts != nullptr && next_m0 >= 0 && ln_nrow < p.M;
+  float4 lp[kLn ? 6 : 1];
+  if (kLn && p.ln_parts == nullptr && next_m0 >= 0 && ln_nrow < p.M)
+    ln_next = *reinterpret_cast<const float2*>(p.ln_stats + (size_t)ln_nrow * 2);
   // next tile's per-column constants: lane l fetches columns 4l … 4l+3 of the warp's 128
   float4 nb = make_float4(0.f, 0.f, 0.f, 0.f), ns = nb;
   if (!kAct2 && next_n_base >= 0) {
@@ -397,6 +430,9 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
 #pragma unroll
   for (int c = 0; c < 4; ++c) {  // 32-column chunks, one half-slab each
     const int col0 = n0 + c * 32;
+    if constexpr (kLn) {  // half of v is dead by now: room for the next tile's statistics partials
+      if (c == 2 && ln_parts_next) ln_load_parts(p, ln_nrow, lp);
+    }
     uint4 pre[kPre ? 4 : 1];
     if constexpr (kPre) {
 #pragma unroll
@@ -509,6 +545,9 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
   if (kMode == kEpiResid && p.stats_out != nullptr && row_ok)
     *reinterpret_cast<float4*>(p.stats_out + ((size_t)(n0 >> 7) * p.M + row) * 4) =
         make_float4(st_x0, st_sum, st_sq, 0.f);
+  if constexpr (kLn) {
+    if (ln_parts_next) ln_next = ln_merge_parts(lp, p.ln_nparts, p.ln_seg_n);
+  }
   ln_st = ln_next;
 }
 
@@ -529,6 +568,20 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
 // (empty barriers count kPairs arrivals; commits are multicast to the whole cluster).
 // Per-row arithmetic is identical for kPairs = 1 and 2 (same k order, same epilogue).
 // -------------------------------------------------------------------------------------------------
+// (row block, column tile) of a persistent CTA's tile sequence tile = first, first + step, …, advanced
+// incrementally: one integer division pair at start-up instead of two per tile on the critical path.
+struct TileWalk {
+  int mi, ni, dm, dn, n_tiles;
+  __device__ __forceinline__ TileWalk(int first, int step, int n_tiles_) : n_tiles(n_tiles_) {
+    mi = first / n_tiles; ni = first % n_tiles;
+    dm = step / n_tiles; dn = step % n_tiles;
+  }
+  __device__ __forceinline__ void next() {
+    mi += dm; ni += dn;
+    if (ni >= n_tiles) { ni -= n_tiles; ++mi; }
+  }
+};
+
 struct Gemm2Cfg {
   static constexpr int BN = 256;
   static constexpr int kStages = 5;
@@ -613,9 +666,10 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
       int stage = 0;
       uint32_t phase = 0;
       GB_STALL_DECL(w_empty);
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m0 = (tile / n_tiles) * kClusterRows + row_off;
-        const int n0 = (tile % n_tiles) * BN + half * (BN / 2);
+      TileWalk tw(cluster_id, num_clusters, n_tiles);
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, tw.next()) {
+        const int m0 = tw.mi * kClusterRows + row_off;
+        const int n0 = tw.ni * BN + half * (BN / 2);
         for (int kb = 0; kb < k_blocks; ++kb) {
           GB_STALL_T(t_e);
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -683,9 +737,17 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
     GB_STALL_DECL(w_tfull);
     GB_STALL_T(t_epi0);
     float2 ln_st = make_float2(0.f, 1.f);
-    if ((kMode == kEpiLn || kMode == kEpiLnGelu) && cluster_id < num_tiles) {
+    if constexpr (kMode == kEpiLn || kMode == kEpiLnGelu) {
       const int r = (cluster_id / n_tiles) * kClusterRows + row_off + (warp & 3) * 32 + lane;
-      if (r < p.M) ln_st = *reinterpret_cast<const float2*>(p.ln_stats + (size_t)r * 2);
+      if (cluster_id < num_tiles && r < p.M) {
+        if (p.ln_parts != nullptr) {
+          float4 lp[6];
+          ln_load_parts(p, r, lp);
+          ln_st = ln_merge_parts(lp, p.ln_nparts, p.ln_seg_n);
+        } else {
+          ln_st = *reinterpret_cast<const float2*>(p.ln_stats + (size_t)r * 2);
+        }
+      }
     }
     const uint32_t consts_s = smem_u32(smem_consts + (warp - 4) * 2048);
     if (kMode != kEpiAct2 && cluster_id < num_tiles) {  // the first tile's per-column constants
@@ -709,14 +771,16 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
         for (int j = 0; j < 8; ++j) pre_lo[j] = r4[j];
       }
     }
+    TileWalk tw(cluster_id, num_clusters, n_tiles);
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int m0 = (tile / n_tiles) * kClusterRows + row_off;
-      const int n0 = (tile % n_tiles) * BN;
-      const int next = tile + num_clusters;
-      const int next_m0 = next < num_tiles ? (next / n_tiles) * kClusterRows + row_off : -1;
-      const int next_n0 = next < num_tiles ? (next % n_tiles) * BN : -1;
+      const int m0 = tw.mi * kClusterRows + row_off;
+      const int n0 = tw.ni * BN;
+      tw.next();
+      const bool more = tile + num_clusters < num_tiles;
+      const int next_m0 = more ? tw.mi * kClusterRows + row_off : -1;
+      const int next_n0 = more ? tw.ni * BN : -1;
       gemm_epilogue_tile_tma<kMode>(
           p, &tmC, smem_slabs + (warp - 4) * 4096, tmem_base + as * BN, m0, n0, warp, lane, ln_st, next_m0,
           consts_s + (it & 1) * 1024, consts_s + ((it + 1) & 1) * 1024, next_n0, pre_lo,

@@ -105,7 +105,10 @@ int run_blocks(gb_ctx* c, const gb_tower* t, int S, int L, int causal, void* x, 
     const bool fold = w.s_qkv != nullptr && w.s_fc != nullptr;
     gb_gemm_ln emit; emit.stats_out = st_part;
     if (fold) {
-      gb_gemm_ln ln1; ln1.ln_stats = st_fin; ln1.col_sum = w.s_qkv;
+      // layer 0 reads the statistics the assemble kernel finalized; later layers merge the partials the
+      // previous c_proj GEMM emitted in their own epilogue
+      gb_gemm_ln ln1; ln1.col_sum = w.s_qkv;
+      if (l == 0) ln1.ln_stats = st_fin; else { ln1.ln_parts = st_part; ln1.nparts = D / 128; }
       if ((rc = gb_launch_gemm(c, x0, D, w.w_qkv, D, w.b_qkv, nullptr, 0, qkv, 3 * D, M, 3 * D, D, 0, 0, st, nullptr, &ln1))) return rc;
     } else {
       if ((rc = gb_launch_layernorm(c, x0, D, nullptr, 1, w.ln1_g, w.ln1_b, h, D, M, D, 0, st))) return rc;
@@ -114,8 +117,7 @@ int run_blocks(gb_ctx* c, const gb_tower* t, int S, int L, int causal, void* x, 
     if ((rc = gb_launch_attn_fwd(c, qkv, a, S, L, D, causal, st))) return rc;
     if ((rc = gb_launch_gemm(c, a, D, w.w_o, D, w.b_o, x0, D, x1, D, M, D, D, 0, 0, st, nullptr, fold ? &emit : nullptr))) return rc;
     if (fold) {
-      if ((rc = gb_launch_ln_finalize(c, st_part, D / 128, M, D, st_fin, st))) return rc;
-      gb_gemm_ln ln2; ln2.ln_stats = st_fin; ln2.col_sum = w.s_fc;
+      gb_gemm_ln ln2; ln2.ln_parts = st_part; ln2.nparts = D / 128; ln2.col_sum = w.s_fc;
       if ((rc = gb_launch_gemm(c, x1, D, w.w_fc, D, w.b_fc, nullptr, 0, g, 4 * D, M, 4 * D, D, 1, 0, st,
                                tape ? tape->f(l) : nullptr, &ln2))) return rc;
     } else {
@@ -125,7 +127,6 @@ int run_blocks(gb_ctx* c, const gb_tower* t, int S, int L, int causal, void* x, 
     }
     const bool more = fold && l + 1 < t->layers;
     if ((rc = gb_launch_gemm(c, g, 4 * D, w.w_proj, 4 * D, w.b_proj, x1, D, x2, D, M, D, 4 * D, 0, 0, st, nullptr, more ? &emit : nullptr))) return rc;
-    if (more && (rc = gb_launch_ln_finalize(c, st_part, D / 128, M, D, st_fin, st))) return rc;
   }
   return GB_OK;
 }

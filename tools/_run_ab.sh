@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
 echo "=== tests"
-timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-echo "=== bench"
-timeout 400 python bench.py > gpurun_out/s3t_bench.json 2>gpurun_out/s3t_bench.err; tail -3 gpurun_out/s3t_bench.err; cat gpurun_out/s3t_bench.json | cut -c1-300
+timeout 200 python -m pytest tests/test_gpu_ops.py tests/test_gpu_towers.py -m gpu -x -q 2>&1 | tail -2
+timeout 120 python tools/gpu_sustained_gemm.py 1.0 ours 2>&1 | tail -12
+timeout 120 python tools/gpu_power_diag.py 3 2>&1 | tail -10
