@@ -405,10 +405,11 @@ def run_b200(a, rank, local_rank, world):
         Np, Cp = 1 << 20, 100
         F = torch.nn.functional.normalize(torch.randn(Np, 512, device=dev), dim=1).half()
         T = torch.nn.functional.normalize(torch.randn(Cp, 512, device=dev), dim=1).half()
-        for _ in range(3):
+        for _ in range(20):  # long enough for the clocks to settle after the GEMM-heavy steps
             eng.sim_softmax_argmax(F, T, 100.0)
+        torch.cuda.synchronize()
         ctx.profile_begin()
-        for _ in range(10):
+        for _ in range(20):
             eng.sim_softmax_argmax(F, T, 100.0)
         (_, _, _), (n1, ms1, by1) = ctx.profile_end()
         gbs = by1 / (ms1 * 1e-3) / 1e9

@@ -331,7 +331,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 //    is rewritten only after the store issued two chunks earlier has finished reading it.
 // (μ·rstd, rstd) of one row from its per-segment shifted partials (x0, Σ(x−x0), Σ(x−x0)²): per segment
 // mean and centred second moment, then Chan's pairwise update in a fixed segment order (deterministic,
-// free of the E[x²]−μ² cancellation; same arithmetic as ln_finalize_kernel in rowops.cu).
+// free of the E[x²]−μ² cancellation).
 __device__ __forceinline__ float2 ln_merge_parts(const float4 (&lp)[6], int nparts, float seg_n) {
   float n = 0.f, mean = 0.f, m2 = 0.f;
 #pragma unroll

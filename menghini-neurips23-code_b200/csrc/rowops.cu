@@ -493,30 +493,6 @@ scale_f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, 
   }
 }
 
-// Combines the per-128-column shifted partials (x0, Σ(x−x0), Σ(x−x0)²) the residual GEMMs emit into the
-// (μ·rstd, rstd) pair per row that the LayerNorm-folded GEMM epilogue consumes: per segment mean and
-// centred second moment, then Chan's pairwise update in a fixed segment order (deterministic, and free of
-// the E[x²]−μ² cancellation).
-__global__ void __launch_bounds__(256)
-ln_finalize_kernel(const float4* __restrict__ parts, int nparts, int M, float seg_n, float eps,
-                   float* __restrict__ out) {
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= M) return;
-  float n = 0.f, mean = 0.f, m2 = 0.f;
-  for (int i = 0; i < nparts; ++i) {
-    const float4 t = parts[(size_t)i * M + row];
-    const float mp = t.x + t.y / seg_n;            // segment mean
-    const float m2p = t.z - t.y * t.y / seg_n;     // Σ (x − segment mean)²
-    const float nn = n + seg_n;
-    const float delta = mp - mean;
-    mean += delta * (seg_n / nn);
-    m2 += m2p + delta * delta * (n * seg_n / nn);
-    n = nn;
-  }
-  const float rstd = rsqrtf(fmaxf(m2 / n, 0.f) + eps);
-  *reinterpret_cast<float2*>(out + (size_t)row * 2) = make_float2(mean * rstd, rstd);
-}
-
 inline int warps_grid(long long rows) { return (int)((rows * 32 + 255) / 256); }
 
 }  // namespace
@@ -627,15 +603,6 @@ int gb_launch_scale_f32_to_f16(gb_ctx* c, const float* in, void* out, size_t n, 
   if (n == 0) return GB_OK;
   const size_t threads = (n + 3) / 4;
   scale_f32_to_f16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(in, (__half*)out, n, scale);
-  GB_LAUNCH_CHECK(c);
-  return GB_OK;
-}
-
-int gb_launch_ln_finalize(gb_ctx* c, const float* parts, int nparts, int M, int D, float* out,
-                          cudaStream_t st) {
-  if (M <= 0) return GB_OK;
-  ln_finalize_kernel<<<(M + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(parts), nparts, M,
-                                                     (float)(D / nparts), 1e-5f, out);
   GB_LAUNCH_CHECK(c);
   return GB_OK;
 }

@@ -31,8 +31,6 @@ int gb_launch_vit_assemble(gb_ctx* c, const void* patch, const float* cls, const
 int gb_launch_text_assemble(gb_ctx* c, const int32_t* ids, int ld_ids, const void* tok_emb,
                             const float* pos, const float* prefix, int P, void* x, int C, int Lt,
                             cudaStream_t st, float* stats);
-int gb_launch_ln_finalize(gb_ctx* c, const float* parts, int nparts, int M, int D, float* out,
-                          cudaStream_t st);
 int gb_launch_l2norm512(gb_ctx* c, const float* x, void* y16, float* y32, int rows, cudaStream_t st);
 int gb_launch_prefix_grad(gb_ctx* c, const void* dx, int L, int S, int P, int D, const float* prefix,
                           const float* gamma, int ln_pre, float inv_scale, float* dprefix,
