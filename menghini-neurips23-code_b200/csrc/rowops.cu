@@ -123,8 +123,19 @@ im2col_patch32_kernel(const InT* __restrict__ img, __half* __restrict__ out, int
 // clip.load's `_transform`; used by the reference at data/dataset.py:64-79).  The three fp32 operations
 // are the ones torch performs, in the same order and rounding, so the fp16 operand written here is
 // bit-identical to feeding the host-normalised fp32 tensor — at a quarter of the host→device bytes.
+// A pixel has 256 possible values per channel, so each block first tabulates the 3 x 256 results (with
+// exactly those IEEE operations) in shared memory and then only looks pixels up — the per-pixel
+// divisions made the kernel ALU-bound at a third of the HBM rate.
 __global__ void __launch_bounds__(256)
 im2col_patch32_u8_kernel(const uint8_t* __restrict__ img, __half* __restrict__ out, int B) {
+  __shared__ __half lut[3 * 256];
+  for (int i = threadIdx.x; i < 3 * 256; i += 256) {
+    const int c = i >> 8;
+    const float mean = c == 0 ? 0.48145466f : (c == 1 ? 0.4578275f : 0.40821073f);
+    const float sd = c == 0 ? 0.26862954f : (c == 1 ? 0.26130258f : 0.27577711f);
+    lut[i] = __float2half_rn(__fdiv_rn(__fsub_rn(__fdiv_rn((float)(i & 255), 255.0f), mean), sd));
+  }
+  __syncthreads();
   // one thread per 16 consecutive kx: total = B*3*224*14 groups
   const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)B * 3 * 224 * 14;
@@ -133,19 +144,13 @@ im2col_patch32_u8_kernel(const uint8_t* __restrict__ img, __half* __restrict__ o
   const int y = (gid / 14) % 224;
   const int c = (gid / (14 * 224)) % 3;
   const int b = gid / (14 * 224 * 3);
-  const float mean = c == 0 ? 0.48145466f : (c == 1 ? 0.4578275f : 0.40821073f);
-  const float sd = c == 0 ? 0.26862954f : (c == 1 ? 0.26130258f : 0.27577711f);
   const uint4 u = __ldg(reinterpret_cast<const uint4*>(img + (((size_t)b * 3 + c) * 224 + y) * 224 + x16 * 16));
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  const __half* l = lut + c * 256;
   uint4 o[2];
-  __half2* h = reinterpret_cast<__half2*>(o);
+  __half* h = reinterpret_cast<__half*>(o);
 #pragma unroll
-  for (int t = 0; t < 8; ++t) {
-    const uint32_t word = w[t >> 1] >> ((t & 1) * 16);
-    const float a = __fdiv_rn(__fsub_rn(__fdiv_rn((float)(word & 0xffu), 255.0f), mean), sd);
-    const float d = __fdiv_rn(__fsub_rn(__fdiv_rn((float)((word >> 8) & 0xffu), 255.0f), mean), sd);
-    h[t] = __floats2half2_rn(a, d);
-  }
+  for (int t = 0; t < 16; ++t) h[t] = l[(w[t >> 2] >> ((t & 3) * 8)) & 0xffu];
   const int py = y >> 5, ky = y & 31, px = (x16 * 16) >> 5, kx = (x16 * 16) & 31;
   uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)b * 49 + py * 7 + px) * 3072 + c * 1024 + ky * 32 + kx);
   dst[0] = o[0];
