@@ -529,6 +529,9 @@ def run_b200(a, rank, local_rank, world):
 
 
 def main():
+    # NCCL's banner ("NCCL version …", printed on stdout at NCCL_DEBUG=VERSION) would precede the one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
