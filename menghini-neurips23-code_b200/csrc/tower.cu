@@ -90,10 +90,19 @@ struct Tape {
 // which a tiny kernel turns into (μ·rstd, rstd) per row.
 // st_fin: [M][2] (μ·rstd, rstd) of the current residual stream (valid for x on entry);
 // st_part: [D/128][M] float4 scratch for the shifted partial sums.
+// first_rows != nullptr (inference only, no tape): the caller needs just row 0 of every sample from the last
+// block (the image tower's CLS token, models/clip_encoders.py:189-192).  Everything after that block's
+// attention — out-proj + residual, ln_2, c_fc, QuickGELU, c_proj + residual — is row-wise, so it runs on
+// those S rows only (read in place through a row stride of L·D) and leaves them compact in first_rows
+// [S, 6·D halves: x1 | x2 | 4·D of MLP scratch].  Per-row arithmetic is unchanged, so the features are
+// bit-identical to the dense evaluation; the reference computes and discards the other rows
+// (5.6 % of the tower's FLOPs at L = 50).
 int run_blocks(gb_ctx* c, const gb_tower* t, int S, int L, int causal, void* x, const Tape* tape,
-               void* h, void* qkv_ws, void* a, void* g, float* st_fin, float* st_part, cudaStream_t st) {
+               void* h, void* qkv_ws, void* a, void* g, float* st_fin, float* st_part, cudaStream_t st,
+               void* first_rows = nullptr) {
   const int D = t->width, M = S * L;
   int rc;
+  if (first_rows && tape) return gb_fail(c, GB_ERR_ARG, "run_blocks: first_rows is an inference-only path");
   for (int l = 0; l < t->layers; ++l) {
     const gb_block_weights& w = t->blocks[l];
     void* x0 = tape ? tape->x0(l) : x;
@@ -113,6 +122,22 @@ int run_blocks(gb_ctx* c, const gb_tower* t, int S, int L, int causal, void* x, 
       if ((rc = gb_launch_gemm(c, h, D, w.w_qkv, D, w.b_qkv, nullptr, 0, qkv, 3 * D, M, 3 * D, D, 0, 0, st))) return rc;
     }
     if ((rc = gb_launch_attn_fwd(c, qkv, a, S, L, D, causal, st))) return rc;
+    if (first_rows && l + 1 == t->layers) {
+      uint8_t* xc1 = reinterpret_cast<uint8_t*>(first_rows);
+      uint8_t* xc2 = xc1 + h2(S, D);
+      uint8_t* gc = xc2 + h2(S, D);
+      const int ldr = L * D;  // row 0 of sample s sits at row s·L of the [M, D] buffers
+      if ((rc = gb_launch_gemm(c, a, ldr, w.w_o, D, w.b_o, x0, ldr, xc1, D, S, D, D, 0, 0, st, nullptr, fold ? &emit : nullptr))) return rc;
+      if (fold) {
+        gb_gemm_ln ln2; ln2.ln_parts = st_part; ln2.nparts = D / 128; ln2.col_sum = w.s_fc;
+        if ((rc = gb_launch_gemm(c, xc1, D, w.w_fc, D, w.b_fc, nullptr, 0, gc, 4 * D, S, 4 * D, D, 1, 0, st, nullptr, &ln2))) return rc;
+      } else {
+        if ((rc = gb_launch_layernorm(c, xc1, D, nullptr, 1, w.ln2_g, w.ln2_b, h, D, S, D, 0, st))) return rc;
+        if ((rc = gb_launch_gemm(c, h, D, w.w_fc, D, w.b_fc, nullptr, 0, gc, 4 * D, S, 4 * D, D, 1, 0, st))) return rc;
+      }
+      if ((rc = gb_launch_gemm(c, gc, 4 * D, w.w_proj, 4 * D, w.b_proj, xc1, D, xc2, D, S, D, 4 * D, 0, 0, st))) return rc;
+      break;
+    }
     if ((rc = gb_launch_gemm(c, a, D, w.w_o, D, w.b_o, x0, D, x1, D, M, D, D, 0, 0, st, nullptr, fold ? &emit : nullptr))) return rc;
     if (fold) {
       gb_gemm_ln ln2; ln2.ln_parts = st_part; ln2.nparts = D / 128; ln2.col_sum = w.s_fc;
@@ -222,7 +247,7 @@ extern "C" int gb_vit_forward(gb_ctx* c, const void* img, int img_f32, const flo
     Bump b(nullptr);
     b.take(h2(M, D)); b.take(h2(M, D)); b.take(h2(M, 3 * D)); b.take(h2(M, D));
     b.take(h2(M > (size_t)B * 49 ? M : (size_t)B * 49, 4 * D)); b.take(h2(B, D)); b.take((size_t)B * 512 * 4);
-    b.take(M * 8); b.take(M * (D / 128) * 16);
+    b.take(M * 8); b.take(M * (D / 128) * 16); b.take(h2(B, 6 * D));
     need = b.off;
   }
   int rc = gb_ws_reserve(c, gb_ctx::kWsVit, need);
@@ -237,6 +262,7 @@ extern "C" int gb_vit_forward(gb_ctx* c, const void* img, int img_f32, const flo
   float* feat_ws = reinterpret_cast<float*>(b.take((size_t)B * 512 * 4));
   float* st_a = reinterpret_cast<float*>(b.take(M * 8));                 // (μ·rstd, rstd) per row
   float* st_b = reinterpret_cast<float*>(b.take(M * (D / 128) * 16));    // shifted partials per 128 columns
+  void* cls_rows = b.take(h2(B, 6 * D));                                 // last block on the CLS rows only
   Tape tape{reinterpret_cast<uint8_t*>(tape_mem), M, (size_t)D};
   void* x = tape_mem ? tape.x0(0) : x_ws;
   const gb_vit_weights& w = t->vit;
@@ -245,10 +271,16 @@ extern "C" int gb_vit_forward(gb_ctx* c, const void* img, int img_f32, const flo
   if ((rc = gb_launch_gemm(c, g, 3072, w.conv_w, 3072, nullptr, nullptr, 0, a, D, B * 49, D, 3072, 0, 0, st))) return rc;
   // CLS + pos-emb, prefix rows, ln_pre: :135-157
   if ((rc = gb_launch_vit_assemble(c, a, w.cls, w.pos, prefix, P, w.ln_pre_g, w.ln_pre_b, x, B, st, st_a))) return rc;
-  if ((rc = run_blocks(c, t, B, L, 0, x, tape_mem ? &tape : nullptr, h, qkv, a, g, st_a, st_b, st))) return rc;
-  const void* xf = tape_mem ? tape.x_final(t->layers) : x;
+  // without a tape only the CLS rows of the last block are evaluated past its attention (see run_blocks)
+  if ((rc = run_blocks(c, t, B, L, 0, x, tape_mem ? &tape : nullptr, h, qkv, a, g, st_a, st_b, st,
+                       tape_mem ? nullptr : cls_rows))) return rc;
   // ln_post(x[:,0,:]) @ proj: :189-192
-  if ((rc = gb_launch_layernorm(c, xf, D, nullptr, L, w.ln_post_g, w.ln_post_b, cls_ln, D, B, D, 0, st))) return rc;
+  if (tape_mem) {
+    if ((rc = gb_launch_layernorm(c, tape.x_final(t->layers), D, nullptr, L, w.ln_post_g, w.ln_post_b, cls_ln, D, B, D, 0, st))) return rc;
+  } else {
+    const uint8_t* xc2 = reinterpret_cast<const uint8_t*>(cls_rows) + h2(B, D);
+    if ((rc = gb_launch_layernorm(c, xc2, D, nullptr, 1, w.ln_post_g, w.ln_post_b, cls_ln, D, B, D, 0, st))) return rc;
+  }
   float* fo = feat ? feat : feat_ws;
   if ((rc = gb_launch_gemm(c, cls_ln, D, w.proj_t, D, nullptr, nullptr, 0, fo, 512, B, 512, D, 0, 1, st))) return rc;
   if (featn && (rc = gb_launch_l2norm512(c, fo, featn, nullptr, B, st))) return rc;

@@ -140,6 +140,21 @@ class Engine:
             self.ctx._bound_engine = weakref.ref(self)
 
     # ---- towers -------------------------------------------------------------------------------
+    @staticmethod
+    def wave_aligned_batch(max_batch: int, L: int = 50, sms: int = 148, width: int = V_WIDTH) -> int:
+        """Largest batch ≤ max_batch whose tower GEMMs fill whole waves of the persistent CTA pairs.
+
+        The GEMMs tile M = batch·L rows into 256-row blocks and N ∈ {D, 3D, 4D} into 256-column tiles, one
+        tile per CTA pair and wave; a last, partly filled wave costs a full tile time (at batch 1024, L = 50
+        on 72 pairs the two N = 768 GEMMs run 9 waves for 8.3 waves of work).  Pool scans are free to pick
+        their chunk size, so they pick one that divides evenly."""
+        pairs = max(1, sms // 2)
+        n_tiles = width // 256
+        for b in range(max_batch, 0, -1):
+            if (-(-(b * L) // 256) * n_tiles) % pairs == 0:
+                return b
+        return max_batch
+
     def tape_bytes(self, samples, L, D, layers=12) -> int:
         return int(self.lib.gb_tape_bytes(samples, L, D, layers))
 
