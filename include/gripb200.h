@@ -208,6 +208,24 @@ int gb_pseudolabel_scan(gb_ctx* ctx, void* state, const void* F, const void* T, 
                         int C, int k, int mode, int idx0, const int32_t* rank, int32_t* pred,
                         float* p_pred, float* probs, void* stream);
 
+/* ---- prompt-tuning step glue on the device --------------------------------------
+ * Cosine-logit cross-entropy of the reference's training loops and its gradient w.r.t. the text features
+ * (methods/semi_supervised_learning/textual_prompt.py:93-109: normalise both sides, logits =
+ * logit_scale.exp()·I·Tᵀ, nn.CrossEntropyLoss), in three launches and without a host round trip.
+ *   imfn16 : fp16 [B,512] unit image features (gb_vit_forward's featn)     text : fp32 [C,512] UN-normalised
+ *   labels : int32 [B]                      coef : fp32 [B] per-sample weights or NULL (= 1/B, mean reduction;
+ *            the FPL variants' balance_param split, textual_fpl.py:123-165, is balance/|group| per sample)
+ *   dtext  : fp32 [C,512] = d loss / d text (through the normalisation)   loss : fp32 [1] or NULL
+ *   pred   : int32 [B] arg-max class per row or NULL                      deterministic (fixed summation order) */
+int gb_ce_text_grad(gb_ctx* ctx, const void* imfn16, const float* text, const int32_t* labels,
+                    const float* coef, float logit_scale_exp, int B, int C, float* dtext, float* loss,
+                    int32_t* pred, void* stream);
+/* torch.optim.SGD step (dampening 0, no Nesterov): g += wd·p; buf = first ? g : mu·buf + g; p -= lr·(mu ? buf : g). */
+int gb_sgd_step(gb_ctx* ctx, float* param, const float* grad, float* momentum_buf, long long n, float lr,
+                float momentum, float weight_decay, int first_step, void* stream);
+/* Learning rate of utils/schedulers.py:36-65 (WarmupCosineSchedule, cycles 0.5) at `step`. */
+double gb_warmup_cosine_lr(double base_lr, int warmup_steps, int t_total, int step);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,9 +27,9 @@ struct gb_ctx {
   // workspace owned by the ctx (grown on demand, never inside a timed region after warm-up)
   // One scratch arena per independent call family, so that the image tower, the text tower and the
   // pool scan may be in flight on different streams at the same time.
-  enum { kWsVit = 0, kWsText = 1, kWsScan = 2, kWsCount = 3 };
-  void* ws[kWsCount] = {nullptr, nullptr, nullptr};
-  size_t ws_bytes[kWsCount] = {0, 0, 0};
+  enum { kWsVit = 0, kWsText = 1, kWsScan = 2, kWsTrain = 3, kWsCount = 4 };
+  void* ws[kWsCount] = {nullptr, nullptr, nullptr, nullptr};
+  size_t ws_bytes[kWsCount] = {0, 0, 0, 0};
   int sm_limit = 0;  // > 0: persistent GEMM grids use at most this many SMs (rounded down to pairs)
   gb_tower* vit = nullptr;
   gb_tower* text = nullptr;

@@ -1,0 +1,198 @@
+// Prompt-tuning step glue on the device: the cosine-logit cross-entropy of the reference's
+// training loops and the SGD update of the prompt parameters, without host round trips.
+//
+// Reference: methods/semi_supervised_learning/textual_prompt.py:93-135 — L2-normalise text and image
+// features, logits = logit_scale.exp()·I·Tᵀ, nn.CrossEntropyLoss, backward, optimizer.step(); the FPL
+// variants weight two groups of samples differently (balance_param, textual_fpl.py:123-165), which is a
+// per-sample coefficient here.  The learning-rate rule is utils/schedulers.py:36-65 (WarmupCosineSchedule).
+#include <math.h>
+
+#include "common.cuh"
+#include "ctx.h"
+
+using namespace gb;
+
+namespace {
+
+// One warp per image row: logits against the C normalised prompts, log-softmax, this row's loss term and
+// d loss / d logits.  tn = T / |T| is recomputed from T by every warp's lanes on the fly (C·512 floats,
+// L2-resident); all sums run in a fixed order (deterministic).
+//   loss_i = −coef_i · log softmax(z_i)[y_i],   dz_ij = coef_i · (softmax(z_i)_j − [j == y_i])
+__global__ void __launch_bounds__(256)
+ce_rows_kernel(const __half* __restrict__ imfn, const float* __restrict__ tn, const int32_t* __restrict__ labels,
+               const float* __restrict__ coef, float coef_all, float scale, int B, int C,
+               float* __restrict__ dlogits, float* __restrict__ loss_rows, int32_t* __restrict__ pred) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  // this row's features: lane holds 16 of the 512 values (two 16-byte pieces)
+  float f[16];
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(imfn + (size_t)row * 512);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const uint4 u = src[p * 32 + lane];
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 a = __half22float2(h[t]);
+        f[p * 8 + 2 * t] = a.x;
+        f[p * 8 + 2 * t + 1] = a.y;
+      }
+    }
+  }
+  float* z = dlogits + (size_t)row * C;
+  float mx = -INFINITY;
+  int am = 0;
+  for (int j = 0; j < C; ++j) {
+    const float4* t4 = reinterpret_cast<const float4*>(tn + (size_t)j * 512);
+    float s = 0.f;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const float4 a = __ldg(t4 + (p * 32 + lane) * 2);
+      const float4 b = __ldg(t4 + (p * 32 + lane) * 2 + 1);
+      s += f[p * 8 + 0] * a.x + f[p * 8 + 1] * a.y + f[p * 8 + 2] * a.z + f[p * 8 + 3] * a.w +
+           f[p * 8 + 4] * b.x + f[p * 8 + 5] * b.y + f[p * 8 + 6] * b.z + f[p * 8 + 7] * b.w;
+    }
+    s = warp_sum(s) * scale;
+    if (lane == 0) z[j] = s;
+    if (s > mx) { mx = s; am = j; }
+  }
+  __syncwarp();
+  float sum = 0.f;
+  for (int j = lane; j < C; j += 32) sum += expf(z[j] - mx);
+  sum = warp_sum(sum);
+  const float lse = mx + logf(sum);
+  const int y = labels[row];
+  const float cf = coef ? coef[row] : coef_all;
+  for (int j = lane; j < C; j += 32) {
+    const float zj = z[j];
+    if (j == y) loss_rows[row] = cf * (lse - zj);
+    z[j] = cf * (expf(zj - lse) - (j == y ? 1.f : 0.f));
+  }
+  if (pred && lane == 0) pred[row] = am;
+}
+
+// tn = T / |T| (fp32 [C,512]) and 1/|T| per row: one warp per prompt.
+__global__ void __launch_bounds__(256)
+text_unit_kernel(const float* __restrict__ T, float* __restrict__ tn, float* __restrict__ inv_norm, int C) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= C) return;
+  const float4* src = reinterpret_cast<const float4*>(T + (size_t)row * 512);
+  float4 v[4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i] = src[i * 32 + lane];
+    s += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+  }
+  const float inv = 1.0f / sqrtf(warp_sum(s));
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    reinterpret_cast<float4*>(tn + (size_t)row * 512)[i * 32 + lane] =
+        make_float4(v[i].x * inv, v[i].y * inv, v[i].z * inv, v[i].w * inv);
+  if (lane == 0) inv_norm[row] = inv;
+}
+
+// One block (512 threads) per prompt j: dTn[j,d] = scale·Σ_i dz[i,j]·I[i,d] summed over the rows in index
+// order, then back through the normalisation: dT_j = (dTn_j − tn_j·⟨tn_j, dTn_j⟩)/|T_j|.  Block 0 also adds
+// up the per-row losses in index order.
+__global__ void __launch_bounds__(512)
+ce_text_grad_kernel(const float* __restrict__ dlogits, const __half* __restrict__ imfn, const float* __restrict__ tn,
+                    const float* __restrict__ inv_norm, const float* __restrict__ loss_rows, float scale, int B,
+                    int C, float* __restrict__ dT, float* __restrict__ loss) {
+  __shared__ float red[16];
+  const int j = blockIdx.x, d = threadIdx.x;
+  float acc = 0.f;
+  for (int i = 0; i < B; ++i) acc = fmaf(dlogits[(size_t)i * C + j], __half2float(imfn[(size_t)i * 512 + d]), acc);
+  acc *= scale;
+  const float t = tn[(size_t)j * 512 + d];
+  float dot = warp_sum(t * acc);
+  if ((d & 31) == 0) red[d >> 5] = dot;
+  __syncthreads();
+  dot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 16; ++w) dot += red[w];
+  dT[(size_t)j * 512 + d] = (acc - t * dot) * inv_norm[j];
+  if (j == 0 && loss) {
+    __syncthreads();
+    float s = 0.f;
+    for (int i = d; i < B; i += 512) s += loss_rows[i];
+    s = warp_sum(s);
+    if ((d & 31) == 0) red[d >> 5] = s;
+    __syncthreads();
+    if (d == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < 16; ++w) tot += red[w];
+      *loss = tot;
+    }
+  }
+}
+
+// torch.optim.SGD (dampening 0, no Nesterov) with the learning rate of utils/schedulers.py:36-65 evaluated
+// on the device from the epoch counter the caller keeps there:  g ← g + wd·p;  b ← μ·b + g (b ← g on the
+// first step);  p ← p − lr·(μ ? b : g).
+__global__ void __launch_bounds__(256)
+sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mom, size_t n, float lr,
+                float momentum, float weight_decay, int first) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float gi = fmaf(weight_decay, p[i], g[i]);
+  if (momentum != 0.f) {
+    const float b = first ? gi : fmaf(momentum, mom[i], gi);
+    mom[i] = b;
+    gi = b;
+  }
+  p[i] -= lr * gi;
+}
+
+}  // namespace
+
+extern "C" int gb_ce_text_grad(gb_ctx* c, const void* imfn16, const float* text, const int32_t* labels,
+                               const float* coef, float logit_scale_exp, int B, int C, float* dtext,
+                               float* loss, int32_t* pred, void* stream) {
+  if (!c) return GB_ERR_ARG;
+  if (!imfn16 || !text || !labels || !dtext || B <= 0 || C <= 0)
+    return gb_fail(c, GB_ERR_ARG, "ce_text_grad: bad arguments (B=%d C=%d)", B, C);
+  cudaStream_t st = (cudaStream_t)stream;
+  // scratch: tn [C,512] | inv_norm [C] | dlogits [B,C] | loss_rows [B]
+  const size_t need = ((size_t)C * 512 + C + (size_t)B * C + B) * 4 + 64;
+  int rc = gb_ws_reserve(c, gb_ctx::kWsTrain, need);
+  if (rc) return rc;
+  float* tn = reinterpret_cast<float*>(c->ws[gb_ctx::kWsTrain]);
+  float* inv_norm = tn + (size_t)C * 512;
+  float* dz = inv_norm + ((C + 3) & ~3);
+  float* loss_rows = dz + (((size_t)B * C + 3) & ~(size_t)3);
+  text_unit_kernel<<<(C * 32 + 255) / 256, 256, 0, st>>>(text, tn, inv_norm, C);
+  GB_LAUNCH_CHECK(c);
+  ce_rows_kernel<<<(int)(((size_t)B * 32 + 255) / 256), 256, 0, st>>>(
+      (const __half*)imfn16, tn, labels, coef, 1.0f / (float)B, logit_scale_exp, B, C, dz, loss_rows, pred);
+  GB_LAUNCH_CHECK(c);
+  ce_text_grad_kernel<<<C, 512, 0, st>>>(dz, (const __half*)imfn16, tn, inv_norm, loss_rows, logit_scale_exp, B, C,
+                                         dtext, loss);
+  GB_LAUNCH_CHECK(c);
+  return GB_OK;
+}
+
+extern "C" double gb_warmup_cosine_lr(double base_lr, int warmup_steps, int t_total, int step) {
+  // utils/schedulers.py:54-65 (cycles = 0.5): factor = step / max(1, warmup) during warm-up, then
+  // max(0, 0.5·(1 + cos(π·progress))) with progress = (step − warmup) / max(1, t_total − warmup); in double,
+  // like the Python it restates
+  if (step < warmup_steps) return base_lr * ((double)step / (double)(warmup_steps > 1 ? warmup_steps : 1));
+  const int rest = t_total - warmup_steps;
+  const double progress = (double)(step - warmup_steps) / (double)(rest > 1 ? rest : 1);
+  const double f = 0.5 * (1.0 + cos(M_PI * 0.5 * 2.0 * progress));
+  return base_lr * (f > 0.0 ? f : 0.0);
+}
+
+extern "C" int gb_sgd_step(gb_ctx* c, float* param, const float* grad, float* momentum_buf, long long n, float lr,
+                           float momentum, float weight_decay, int first_step, void* stream) {
+  if (!c) return GB_ERR_ARG;
+  if (!param || !grad || n <= 0 || (momentum != 0.f && !momentum_buf))
+    return gb_fail(c, GB_ERR_ARG, "sgd_step: bad arguments");
+  sgd_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(param, grad, momentum_buf, (size_t)n,
+                                                                                 lr, momentum, weight_decay, first_step);
+  GB_LAUNCH_CHECK(c);
+  return GB_OK;
+}

@@ -240,6 +240,36 @@ class Engine:
         self.ctx.check(rc, "gb_text_backward_prefix")
         return dprefix
 
+    # ---- training-step glue -----------------------------------------------------
+    def ce_text_grad(self, imfn16, text, labels, coef=None, scale=None, want_pred=False):
+        """Cosine-logit cross-entropy of the reference's training loops (textual_prompt.py:93-109) and its
+        gradient w.r.t. the un-normalised text features, on the device in three launches.
+        imfn16 fp16 [B,512] unit rows, text fp32 [C,512], labels int [B], coef fp32 [B] per-sample weights
+        or None (mean).  Returns (loss fp32 [1], dtext fp32 [C,512], pred int32 [B] | None)."""
+        B, C = imfn16.shape[0], text.shape[0]
+        scale = self.logit_scale_exp if scale is None else float(scale)
+        text = text.detach().to(self.device, torch.float32).contiguous()
+        labels = labels.to(self.device, torch.int32).contiguous()
+        if coef is not None:
+            coef = coef.to(self.device, torch.float32).contiguous()
+        dtext = torch.empty(C, EMBED, device=self.device, dtype=torch.float32)
+        loss = torch.empty(1, device=self.device, dtype=torch.float32)
+        pred = torch.empty(B, device=self.device, dtype=torch.int32) if want_pred else None
+        rc = self.lib.gb_ce_text_grad(self.ctx.h, ptr(imfn16), ptr(text), ptr(labels), ptr(coef), scale, B, C,
+                                      ptr(dtext), ptr(loss), ptr(pred), stream_ptr())
+        self.ctx.check(rc, "gb_ce_text_grad")
+        return loss, dtext, pred
+
+    def sgd_step(self, param, grad, momentum_buf, lr, momentum=0.0, weight_decay=0.0, first_step=False):
+        """In-place torch.optim.SGD step (dampening 0, no Nesterov) on fp32 device tensors."""
+        rc = self.lib.gb_sgd_step(self.ctx.h, ptr(param), ptr(grad), ptr(momentum_buf), param.numel(), float(lr),
+                                  float(momentum), float(weight_decay), int(first_step), stream_ptr())
+        self.ctx.check(rc, "gb_sgd_step")
+
+    def warmup_cosine_lr(self, base_lr, warmup_steps, t_total, step):
+        """utils/schedulers.py:36-65 (WarmupCosineSchedule) at `step`."""
+        return float(self.lib.gb_warmup_cosine_lr(float(base_lr), int(warmup_steps), int(t_total), int(step)))
+
     # ---- pool scan ----------------------------------------------------------------------------
     def sim_softmax_argmax(self, F16, T16, scale=None, mode=0, want_probs=False):
         """F16 [N,512], T16 [C,512] fp16 unit rows → (pred int32 [N], p_pred fp32 [N], probs|None)."""

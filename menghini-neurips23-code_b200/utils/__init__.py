@@ -1,4 +1,6 @@
 from .clip_pseudolabels import (compute_pseudo_labels, encode_pool, path_ranks, pseudolabel_top_k,
                                 scan_features)
+from .evaluation import predict_features, predictions_frame, test_predictions
 
-__all__ = ["compute_pseudo_labels", "encode_pool", "path_ranks", "pseudolabel_top_k", "scan_features"]
+__all__ = ["compute_pseudo_labels", "encode_pool", "path_ranks", "pseudolabel_top_k", "scan_features",
+           "predict_features", "predictions_frame", "test_predictions"]

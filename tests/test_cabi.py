@@ -83,3 +83,23 @@ def test_dropin_install_registers_the_reference_import_seam():
         "print('ok')\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+def test_warmup_cosine_lr_is_the_reference_rule():
+    """gb_warmup_cosine_lr restates utils/schedulers.py:54-65 (WarmupCosineSchedule.lr_lambda, cycles 0.5):
+    same numbers as the Python formula for every epoch of the shipped configs (WARMUP_EPOCHS 5, EPOCHS 150)."""
+    import importlib
+    import math
+
+    lib = importlib.import_module("menghini-neurips23-code_b200").load()
+
+    def lr_lambda(step, warmup_steps, t_total, cycles=0.5):
+        if step < warmup_steps:
+            return float(step) / float(max(1.0, warmup_steps))
+        progress = float(step - warmup_steps) / float(max(1, t_total - warmup_steps))
+        return max(0.0, 0.5 * (1.0 + math.cos(math.pi * float(cycles) * 2.0 * progress)))
+
+    for warm, total in ((5, 150), (0, 10), (1, 2), (5, 5)):
+        for step in range(total + 3):
+            got = lib.gb_warmup_cosine_lr(0.1, warm, total, step)
+            assert abs(got - 0.1 * lr_lambda(step, warm, total)) <= 1e-15, (warm, total, step, got)

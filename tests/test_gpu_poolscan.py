@@ -234,3 +234,37 @@ def test_grip_schedule_with_learned_prompts(pkg):
         assert idx == w_idx and lab == w_lab, k
     idx, lab = U.scan_features(_Eng(), F, T, leaderboard_ref.ALL_UNLABELED_K, paths, class_ids, mode=1)
     assert idx == list(range(N)) and lab == [class_ids[j] for j in pred.cpu().tolist()]
+
+
+def test_evaluation_path_matches_the_reference_loop():
+    """fused similarity + arg-max over a pool vs the reference's per-batch
+    `argmax(logit_scale.exp() * image_features @ text_features.t(), dim=1)` (textual_prompt.py:256-270) evaluated
+    in fp32 on the same fp16 unit features; rows whose top-2 logit margin is below fp32 accumulation noise are
+    the only ones allowed to differ (none do at these sizes), and the DataFrame has the reference's columns."""
+    import importlib
+
+    utils = importlib.import_module("menghini-neurips23-code_b200.utils")
+    engine_mod = importlib.import_module("menghini-neurips23-code_b200.engine")
+    pkg = importlib.import_module("menghini-neurips23-code_b200")
+    f, t = synth.pool(20000, 45, peaked=0.05)
+    F, T = f.half().cuda(), t.half().cuda()
+
+    class Eng:  # predict_features only needs the fused pass
+        device = torch.device("cuda:0")
+        ctx = pkg.Context.get(0)
+        lib = ctx.lib
+        logit_scale_exp = 100.0
+        sim_softmax_argmax = engine_mod.Engine.sim_softmax_argmax
+
+    pred = utils.predict_features(Eng(), F, T).cpu()
+    logits = 100.0 * F.float() @ T.float().t()
+    want = torch.argmax(logits, dim=1).cpu()
+    top2 = torch.topk(logits, 2, dim=1).values.cpu()
+    unsure = (top2[:, 0] - top2[:, 1]) < 1e-3
+    assert torch.equal(pred.long()[~unsure], want[~unsure])
+    assert (pred.long() != want).sum().item() <= unsure.sum().item()
+    names = [f"class_{j}" for j in range(45)]
+    paths = [f"/data/pool/img_{i % 19990}.png" for i in range(20000)]   # a few repeated file names
+    df = utils.predictions_frame(paths, pred, names)
+    assert list(df.columns) == ["id", "class"] and df["id"].iloc[0] == "img_0.png"
+    assert len(df) == len({(p.split("/")[-1], names[j]) for p, j in zip(paths, pred.tolist())})
