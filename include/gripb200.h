@@ -208,6 +208,11 @@ int gb_pseudolabel_scan(gb_ctx* ctx, void* state, const void* F, const void* T, 
                         int C, int k, int mode, int idx0, const int32_t* rank, int32_t* pred,
                         float* p_pred, float* probs, void* stream);
 
+/* Counter that changes whenever the ctx re-allocates one of its scratch arenas (a call larger than any
+ * before it).  Calls are otherwise allocation- and sync-free, so a sequence of them may be captured in a
+ * CUDA graph; a captured graph must be re-captured when this value changes. */
+uint64_t gb_workspace_generation(gb_ctx* ctx);
+
 /* ---- prompt-tuning step glue on the device --------------------------------------
  * Cosine-logit cross-entropy of the reference's training loops and its gradient w.r.t. the text features
  * (methods/semi_supervised_learning/textual_prompt.py:93-109: normalise both sides, logits =
@@ -220,9 +225,11 @@ int gb_pseudolabel_scan(gb_ctx* ctx, void* state, const void* F, const void* T, 
 int gb_ce_text_grad(gb_ctx* ctx, const void* imfn16, const float* text, const int32_t* labels,
                     const float* coef, float logit_scale_exp, int B, int C, float* dtext, float* loss,
                     int32_t* pred, void* stream);
-/* torch.optim.SGD step (dampening 0, no Nesterov): g += wd·p; buf = first ? g : mu·buf + g; p -= lr·(mu ? buf : g). */
+/* torch.optim.SGD step (dampening 0, no Nesterov): g += wd·p; buf = first ? g : mu·buf + g; p -= lr·(mu ? buf : g).
+ * lr_dev != NULL: the learning rate is read from that device scalar instead of `lr` (a captured CUDA graph
+ * of the step then keeps following the schedule). */
 int gb_sgd_step(gb_ctx* ctx, float* param, const float* grad, float* momentum_buf, long long n, float lr,
-                float momentum, float weight_decay, int first_step, void* stream);
+                const float* lr_dev, float momentum, float weight_decay, int first_step, void* stream);
 /* Learning rate of utils/schedulers.py:36-65 (WarmupCosineSchedule, cycles 0.5) at `step`. */
 double gb_warmup_cosine_lr(double base_lr, int warmup_steps, int t_total, int step);
 

@@ -81,8 +81,9 @@ _SIGNATURES = {
     "gb_leaderboard_export": (c_int, [P, P, c_int, c_int, P, P, P, P]),
     "gb_pseudolabel_scan": (c_int, [P, P, P, P, c_float, c_int, c_int, c_int, c_int, c_int, P, P,
                                     P, P, P]),
+    "gb_workspace_generation": (c_uint64, [P]),
     "gb_ce_text_grad": (c_int, [P, P, P, P, P, c_float, c_int, c_int, P, P, P, P]),
-    "gb_sgd_step": (c_int, [P, P, P, P, ctypes.c_longlong, c_float, c_float, c_float, c_int, P]),
+    "gb_sgd_step": (c_int, [P, P, P, P, ctypes.c_longlong, c_float, P, c_float, c_float, c_int, P]),
     "gb_warmup_cosine_lr": (ctypes.c_double, [ctypes.c_double, c_int, c_int, c_int]),
 }
 

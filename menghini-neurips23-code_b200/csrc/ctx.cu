@@ -56,8 +56,11 @@ int gb_ws_reserve(gb_ctx* c, int slot, size_t bytes) {
   c->ws_bytes[slot] = 0;
   GB_CUDA(c, cudaMalloc(&c->ws[slot], bytes));
   c->ws_bytes[slot] = bytes;
+  c->ws_gen++;
   return GB_OK;
 }
+
+extern "C" uint64_t gb_workspace_generation(gb_ctx* c) { return c ? c->ws_gen : 0; }
 
 extern "C" int gb_set_sm_limit(gb_ctx* c, int sms) {
   if (!c || sms < 0) return GB_ERR_ARG;

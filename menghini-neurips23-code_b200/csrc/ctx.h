@@ -30,6 +30,7 @@ struct gb_ctx {
   enum { kWsVit = 0, kWsText = 1, kWsScan = 2, kWsTrain = 3, kWsCount = 4 };
   void* ws[kWsCount] = {nullptr, nullptr, nullptr, nullptr};
   size_t ws_bytes[kWsCount] = {0, 0, 0, 0};
+  uint64_t ws_gen = 0;  // bumped whenever a workspace is re-allocated (captured CUDA graphs go stale)
   int sm_limit = 0;  // > 0: persistent GEMM grids use at most this many SMs (rounded down to pairs)
   gb_tower* vit = nullptr;
   gb_tower* text = nullptr;

@@ -135,9 +135,10 @@ ce_text_grad_kernel(const float* __restrict__ dlogits, const __half* __restrict_
 // first step);  p ← p − lr·(μ ? b : g).
 __global__ void __launch_bounds__(256)
 sgd_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mom, size_t n, float lr,
-                float momentum, float weight_decay, int first) {
+                const float* __restrict__ lr_dev, float momentum, float weight_decay, int first) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (lr_dev) lr = *lr_dev;  // a captured CUDA graph keeps following the schedule
   float gi = fmaf(weight_decay, p[i], g[i]);
   if (momentum != 0.f) {
     const float b = first ? gi : fmaf(momentum, mom[i], gi);
@@ -187,12 +188,13 @@ extern "C" double gb_warmup_cosine_lr(double base_lr, int warmup_steps, int t_to
 }
 
 extern "C" int gb_sgd_step(gb_ctx* c, float* param, const float* grad, float* momentum_buf, long long n, float lr,
-                           float momentum, float weight_decay, int first_step, void* stream) {
+                           const float* lr_dev, float momentum, float weight_decay, int first_step, void* stream) {
   if (!c) return GB_ERR_ARG;
   if (!param || !grad || n <= 0 || (momentum != 0.f && !momentum_buf))
     return gb_fail(c, GB_ERR_ARG, "sgd_step: bad arguments");
   sgd_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(param, grad, momentum_buf, (size_t)n,
-                                                                                 lr, momentum, weight_decay, first_step);
+                                                                                 lr, lr_dev, momentum, weight_decay,
+                                                                                 first_step);
   GB_LAUNCH_CHECK(c);
   return GB_OK;
 }

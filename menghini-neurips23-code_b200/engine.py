@@ -260,10 +260,12 @@ class Engine:
         self.ctx.check(rc, "gb_ce_text_grad")
         return loss, dtext, pred
 
-    def sgd_step(self, param, grad, momentum_buf, lr, momentum=0.0, weight_decay=0.0, first_step=False):
-        """In-place torch.optim.SGD step (dampening 0, no Nesterov) on fp32 device tensors."""
+    def sgd_step(self, param, grad, momentum_buf, lr, momentum=0.0, weight_decay=0.0, first_step=False,
+                 lr_dev=None):
+        """In-place torch.optim.SGD step (dampening 0, no Nesterov) on fp32 device tensors; `lr_dev` (fp32 [1]
+        on the device) overrides `lr` when given."""
         rc = self.lib.gb_sgd_step(self.ctx.h, ptr(param), ptr(grad), ptr(momentum_buf), param.numel(), float(lr),
-                                  float(momentum), float(weight_decay), int(first_step), stream_ptr())
+                                  ptr(lr_dev), float(momentum), float(weight_decay), int(first_step), stream_ptr())
         self.ctx.check(rc, "gb_sgd_step")
 
     def warmup_cosine_lr(self, base_lr, warmup_steps, t_total, step):

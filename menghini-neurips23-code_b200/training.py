@@ -20,18 +20,29 @@ from . import dist as _dist
 
 class CoOpStep:
     """`momentum` is the optimizer's (the reference's base trainer file is missing from the scrape, SURVEY F3;
-    torch.optim.SGD with the YAML's LR / DECAY is what its call sites imply) — pass what your trainer uses."""
+    torch.optim.SGD with the YAML's LR / DECAY is what its call sites imply) — pass what your trainer uses.
+
+    With `graph=True` (single process) the whole chain — text tower with tape, loss + gradient, prompt-only
+    backward, SGD — is captured once per (class list, batch size) as a CUDA graph and replayed: the ~160 small
+    launches of a step cost one submission.  The learning rate lives in a device scalar, so the captured graph
+    follows the schedule; the graph is re-captured when the library re-allocates a scratch arena."""
 
     def __init__(self, text_prefix_model, lr: float, weight_decay: float = 0.0, momentum: float = 0.0,
-                 warmup_epochs: int = 0, epochs: int = 1, world: int = 1):
+                 warmup_epochs: int = 0, epochs: int = 1, world: int = 1, graph: bool = True):
         self.model = text_prefix_model
         self.enc = text_prefix_model.text_encoder
         self.engine = self.enc.clip_model.engine
         self.base_lr, self.wd, self.mu = float(lr), float(weight_decay), float(momentum)
         self.warmup, self.epochs, self.epoch = int(warmup_epochs), int(epochs), 0
         self.world = world
-        self.buf = torch.zeros_like(self.model.prefix.data, dtype=torch.float32)
+        self.use_graph = bool(graph) and world == 1
+        dev = self.engine.device
+        self.buf = torch.zeros_like(self.model.prefix.data, dtype=torch.float32)  # zero ⇒ first step: buf = g
+        self.lr_dev = torch.zeros(1, device=dev, dtype=torch.float32)
         self.steps = 0
+        self._key = None
+        self._graph = None
+        self._gen = None
 
     @property
     def lr(self) -> float:
@@ -40,22 +51,78 @@ class CoOpStep:
     def update_scheduler(self):
         self.epoch += 1
 
+    # static buffers of one (classes, batch) configuration
+    def _prepare(self, classes, B, weighted):
+        eng, dev = self.engine, self.engine.device
+        P = self.model.prefix.shape[1]
+        ids = self.enc._prompt_ids(P, classes).detach().cpu()
+        eot = ids.argmax(dim=-1)
+        self._Lt = max(int(eot.max().item()) + 1, P + 2)
+        self._ids = ids.to(dev, torch.int32).contiguous()
+        self._eot = eot.to(dev, torch.int32).contiguous()
+        C = ids.shape[0]
+        self._C, self._B, self._P = C, B, P
+        f32 = dict(device=dev, dtype=torch.float32)
+        self._text = torch.empty(C, 512, **f32)
+        self._tape = torch.empty(eng.tape_bytes(C, self._Lt, 512), device=dev, dtype=torch.uint8)
+        self._imfn = torch.empty(B, 512, device=dev, dtype=torch.float16)
+        self._labels = torch.empty(B, device=dev, dtype=torch.int32)
+        self._coef = torch.empty(B, **f32) if weighted else None
+        self._dtext = torch.empty(C, 512, **f32)
+        self._loss = torch.empty(1, **f32)
+        self._pred = torch.empty(B, device=dev, dtype=torch.int32)
+        self._dprefix = torch.empty(P, 512, **f32)
+        self._graph = None
+
+    def _chain(self):
+        from ._lib import ptr, stream_ptr
+
+        eng = self.engine
+        lib, h, chk, st = eng.lib, eng.ctx.h, eng.ctx.check, stream_ptr()
+        prefix = self.model.prefix.data
+        chk(lib.gb_text_forward(h, ptr(self._ids), self._ids.stride(0), ptr(self._eot), ptr(prefix), self._C,
+                                self._P, self._Lt, ptr(self._text), None, ptr(self._tape), st), "gb_text_forward")
+        chk(lib.gb_ce_text_grad(h, ptr(self._imfn), ptr(self._text), ptr(self._labels), ptr(self._coef),
+                                eng.logit_scale_exp, self._B, self._C, ptr(self._dtext), ptr(self._loss),
+                                ptr(self._pred), st), "gb_ce_text_grad")
+        chk(lib.gb_text_backward_prefix(h, ptr(self._dtext), ptr(self._eot), self._C, self._P, self._Lt,
+                                        ptr(self._tape), ptr(self._dprefix), st), "gb_text_backward_prefix")
+        if self.world > 1:
+            _dist.allreduce_mean_(self._dprefix)
+        chk(lib.gb_sgd_step(h, ptr(prefix), ptr(self._dprefix), ptr(self.buf), prefix.numel(), 0.0,
+                            ptr(self.lr_dev), self.mu, self.wd, 0, st), "gb_sgd_step")
+
     def step(self, imfn16: torch.Tensor, labels: torch.Tensor, coef: Optional[torch.Tensor] = None,
              classes=None, want_pred: bool = False):
         """One optimisation step on a batch of cached unit image features.  Returns (loss [1] on the device,
-        pred | None); nothing is read back to the host."""
+        pred | None) — views of buffers the next step overwrites; nothing is read back to the host."""
         eng = self.engine
         classes = self.model.classes if classes is None else classes
         prefix = self.model.prefix
-        P = prefix.shape[1]
-        ids = self.enc._prompt_ids(P, classes)
+        if prefix.dtype != torch.float32 or not prefix.data.is_contiguous():
+            raise ValueError("CoOpStep needs a contiguous fp32 prefix parameter")
+        key = (tuple(classes), int(imfn16.shape[0]), coef is not None, prefix.data_ptr())
+        if key != self._key:
+            self._prepare(classes, int(imfn16.shape[0]), coef is not None)
+            self._key = key
         with torch.no_grad():
-            text, _, saved = eng.text_forward(ids, prefix[0], tape=True)
-            loss, dtext, pred = eng.ce_text_grad(imfn16, text, labels, coef, want_pred=want_pred)
-            dprefix = eng.text_backward_prefix(dtext, P, saved)
-            if self.world > 1:
-                _dist.allreduce_mean_(dprefix)
-            eng.sgd_step(prefix.data.view(-1), dprefix.view(-1), self.buf.view(-1), self.lr, self.mu, self.wd,
-                         first_step=self.steps == 0)
+            self._imfn.copy_(imfn16)
+            self._labels.copy_(labels)
+            if coef is not None:
+                self._coef.copy_(coef)
+            self.lr_dev.fill_(self.lr)
+            eng._bind()
+            gen = int(eng.lib.gb_workspace_generation(eng.ctx.h))
+            if self._graph is not None and gen == self._gen:
+                self._graph.replay()
+            else:
+                self._chain()   # eager: sizes the library's scratch arenas, and IS this step
+                self._graph = None
+                if self.use_graph:
+                    self._gen = int(eng.lib.gb_workspace_generation(eng.ctx.h))
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):   # capture only: nothing executes here
+                        self._chain()
+                    self._graph = g
         self.steps += 1
-        return loss, pred
+        return self._loss, (self._pred if want_pred else None)
