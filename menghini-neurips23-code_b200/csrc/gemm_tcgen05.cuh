@@ -374,7 +374,8 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
                                                        uint8_t* slabs, uint32_t tmem_acc, int m0,
                                                        int n_base, int warp, int lane, float2& ln_st,
                                                        int next_m0, uint32_t consts_s, uint32_t consts_next_s,
-                                                       int next_n_base, uint4 (&pre_lo)[8], WaitAcc&& wait_acc,
+                                                       int next_n_base, uint4 (&pre_lo)[8], float4 (&lp)[6],
+                                                       bool& lp_pending, WaitAcc&& wait_acc,
                                                        ReleaseAcc&& release_acc) {
   constexpr int BN = 256;
   constexpr bool kLn = kMode == kEpiLn || kMode == kEpiLnGelu;
@@ -391,9 +392,8 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
   const bool row_ok = row < p.M;
   const bool has_pre = kPre && pre_base != nullptr && row_ok;
   // The operand that comes from global memory (residual, or the saved pre-activation for act 2) is
-  // fetched half a tile ahead: columns 0-63 of this row arrived while the previous tile's second half
-  // was processed (pre_lo, carried across tiles); columns 64-127 are requested now, before the
-  // accumulator is even ready; the next tile's columns 0-63 once this tile's first half is done.
+  // fetched ahead: columns 0-63 of this row were requested at the end of the previous tile (pre_lo,
+  // carried across tiles); columns 64-127 are requested now, before the accumulator is even ready.
   uint4 pre_hi[kPre ? 8 : 1];
   if (has_pre) {
     const uint4* r4 = reinterpret_cast<const uint4*>(pre_base + (size_t)row * pre_ld + n0 + 64);
@@ -402,11 +402,17 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
   }
   // row statistics of the folded LayerNorm: (μ·rstd, rstd) of this tile's row were fetched while the
   // previous tile was processed; the next tile's are requested now
+  // (every load that is still in flight when a chunk's fence.proxy.async executes stalls the warp there —
+  // the fence comes with a CTA-wide memory barrier — so look-ahead loads are issued after the tile's last
+  // fence and land while the warp waits for the next accumulator: the statistics partials requested at
+  // the end of the previous tile are merged here)
+  if constexpr (kLn) {
+    if (lp_pending) ln_st = ln_merge_parts(lp, p.ln_nparts, p.ln_seg_n);
+  }
   const float ln_mr = -ln_st.x, ln_rstd = ln_st.y;
   float2 ln_next = make_float2(0.f, 1.f);
   const int ln_nrow = next_m0 + q * 32 + lane;
   const bool ln_parts_next = kLn && p.ln_parts != nullptr && next_m0 >= 0 && ln_nrow < p.M;
-  float4 lp[kLn ? 6 : 1];
   if (kLn && p.ln_parts == nullptr && next_m0 >= 0 && ln_nrow < p.M)
     ln_next = *reinterpret_cast<const float2*>(p.ln_stats + (size_t)ln_nrow * 2);
   // next tile's per-column constants: lane l fetches columns 4l … 4l+3 of the warp's 128
@@ -430,22 +436,10 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
 #pragma unroll
   for (int c = 0; c < 4; ++c) {  // 32-column chunks, one half-slab each
     const int col0 = n0 + c * 32;
-    if constexpr (kLn) {  // half of v is dead by now: room for the next tile's statistics partials
-      if (c == 2 && ln_parts_next) ln_load_parts(p, ln_nrow, lp);
-    }
     uint4 pre[kPre ? 4 : 1];
     if constexpr (kPre) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) pre[j] = c < 2 ? pre_lo[4 * c + j] : pre_hi[4 * (c - 2) + j];
-      if (c == 2 && next_m0 >= 0 && pre_base != nullptr) {  // pre_lo is free: the next tile's first half
-        const int nrow = next_m0 + q * 32 + lane;
-        if (nrow < p.M) {
-          const uint4* r4 = reinterpret_cast<const uint4*>(pre_base + (size_t)nrow * pre_ld +
-                                                           next_n_base + half * (BN / 2));
-#pragma unroll
-          for (int j = 0; j < 8; ++j) pre_lo[j] = r4[j];
-        }
-      }
     }
     uint8_t* slab = slabs + (c & 1) * 2048;
     const uint32_t slab_s = smem_u32(slab);
@@ -545,8 +539,21 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
   if (kMode == kEpiResid && p.stats_out != nullptr && row_ok)
     *reinterpret_cast<float4*>(p.stats_out + ((size_t)(n0 >> 7) * p.M + row) * 4) =
         make_float4(st_x0, st_sum, st_sq, 0.f);
+  // look-ahead loads for the next tile, after this tile's last fence
   if constexpr (kLn) {
-    if (ln_parts_next) ln_next = ln_merge_parts(lp, p.ln_nparts, p.ln_seg_n);
+    lp_pending = ln_parts_next;
+    if (ln_parts_next) ln_load_parts(p, ln_nrow, lp);
+  }
+  if constexpr (kPre) {
+    if (next_m0 >= 0 && pre_base != nullptr) {  // the next tile's columns 0-63 of this thread's row
+      const int nrow = next_m0 + q * 32 + lane;
+      if (nrow < p.M) {
+        const uint4* r4 = reinterpret_cast<const uint4*>(pre_base + (size_t)nrow * pre_ld + next_n_base +
+                                                         half * (BN / 2));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pre_lo[j] = r4[j];
+      }
+    }
   }
   ln_st = ln_next;
 }
@@ -759,6 +766,8 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
       sts128f(consts_s + 512 + lane * 16, cs);
       __syncwarp();
     }
+    float4 lp[6];
+    bool lp_pending = false;
     uint4 pre_lo[8];
     if ((kMode == kEpiResid || kMode == kEpiAct2) && cluster_id < num_tiles) {  // first tile's columns 0-63
       const __half* pre_base = kMode == kEpiAct2 ? p.aux : p.resid;
@@ -783,7 +792,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
       const int next_n0 = more ? tw.ni * BN : -1;
       gemm_epilogue_tile_tma<kMode>(
           p, &tmC, smem_slabs + (warp - 4) * 4096, tmem_base + as * BN, m0, n0, warp, lane, ln_st, next_m0,
-          consts_s + (it & 1) * 1024, consts_s + ((it + 1) & 1) * 1024, next_n0, pre_lo,
+          consts_s + (it & 1) * 1024, consts_s + ((it + 1) & 1) * 1024, next_n0, pre_lo, lp, lp_pending,
           [&]() {
             GB_STALL_T(t_tf);
             mbar_wait(&tfull_bar[as], aphase);
