@@ -342,6 +342,9 @@ __device__ __forceinline__ void sts128f(uint32_t saddr, const float4& v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
 }
+__device__ __forceinline__ void sts32f(uint32_t saddr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
+}
 __device__ __forceinline__ float quick_gelu(float x) {
   // x * sigmoid(1.702 x)   (openai/CLIP QuickGELU) = x / (1 + 2^(−1.702·log2(e)·x)); ex2.approx +
   // rcp.approx: ≈1e-7 relative, far below the fp16 rounding of the stored activation; branch-free

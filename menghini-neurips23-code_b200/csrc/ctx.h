@@ -88,13 +88,20 @@ inline int gb_fail(gb_ctx* c, int code, const char* fmt, ...) {
 int gb_make_tmap_2d_f16(gb_ctx* c, CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols,
                         uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols = 64);
 
+// Epilogue warps of the CTA-pair GEMM (8 or 16; see gemm_tcgen05.cuh) and, with it, the columns per partial of
+// gb_gemm_ln::stats_out — the columns one epilogue warp owns.
+#ifndef GB_EPI_WARPS
+#define GB_EPI_WARPS 8
+#endif
+#define GB_STAT_SEG (256 / (GB_EPI_WARPS / 4))
+
 // LayerNorm-folding extras of a GEMM launch (see GemmParams): statistics consumed / produced.
 struct gb_gemm_ln {
   const float* ln_stats = nullptr;  // [M][2] (μ·rstd, rstd) of A's rows → fold LayerNorm into this GEMM
   const float* ln_parts = nullptr;  // … or [nparts][M] float4 partials as a GEMM's stats_out left them
   int nparts = 0;                   //   (merged in the epilogue; K / nparts columns per segment)
   const float* col_sum = nullptr;   // [N]
-  float* stats_out = nullptr;      // [N/128][M][2] partial statistics of the output rows
+  float* stats_out = nullptr;      // [N/GB_STAT_SEG][M] float4 shifted partial statistics of the output rows
 };
 
 // internal launchers shared between op-level and tower-level entry points

@@ -42,7 +42,7 @@ static int launch_gemm_2cta(gb_ctx* c, const CUtensorMap& tmA, const CUtensorMap
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(kGemm2Threads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
   cfg.attrs = attr; cfg.numAttrs = 1;
@@ -104,7 +104,7 @@ int gb_launch_gemm(gb_ctx* c, const void* A, int lda, const void* W, int ldw, co
       return gb_fail(c, GB_ERR_ARG, "gemm: LayerNorm folding needs fp16 output and N %% 256 == 0");
     const bool fold_in = ln->ln_stats != nullptr || ln->ln_parts != nullptr;
     if (fold_in != (ln->col_sum != nullptr) || (ln->ln_stats && ln->ln_parts) ||
-        (ln->ln_parts && (ln->nparts < 1 || ln->nparts > 6 || K % ln->nparts != 0)))
+        (ln->ln_parts && (ln->nparts < 1 || ln->nparts > 768 / GB_STAT_SEG || K % ln->nparts != 0)))
       return gb_fail(c, GB_ERR_ARG, "gemm: inconsistent LayerNorm folding arguments");
     p.ln_stats = ln->ln_stats; p.col_sum = ln->col_sum;
     if (ln->ln_parts) {

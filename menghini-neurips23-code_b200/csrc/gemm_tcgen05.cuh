@@ -58,7 +58,7 @@ struct GemmParams {
   // … or the row statistics still in the form the producing GEMM left them (its stats_out): the
   // epilogue merges the ln_nparts segments of a row itself, one tile ahead (no finalize launch)
   const float4* ln_parts;  // [ln_nparts][M] (x0, Σ(x−x0), Σ(x−x0)², −), or nullptr
-  int ln_nparts;           // ≤ 6
+  int ln_nparts;           // ≤ kLnMaxParts
   float ln_seg_n;          // columns per segment
   // shifted partial sums of every OUTPUT row over this warp's 128 columns, [N/128][M] float4 =
   // (x0, Σ(x−x0), Σ(x−x0)², −) with x0 the segment's first stored value, or nullptr: the statistics the
@@ -329,13 +329,29 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 //    row segments and clips rows >= M.  Direct per-thread stores (32 row-strided 16-byte pieces per
 //    instruction) were the bottleneck of every K=768 GEMM.  Two half-slabs per warp alternate, so one
 //    is rewritten only after the store issued two chunks earlier has finished reading it.
+// Epilogue geometry of the CTA-pair kernel: GB_EPI_WARPS epilogue warps (8 or 16) — TMEM lane quadrant
+// warp % 4, column group (warp − 4) / 4 of 256 / (GB_EPI_WARPS / 4) columns.  Measured on B200 (same box,
+// sustained loops): 16 warps of 112 registers are SLOWER than 8 warps of 232 on every flavour (plain fc
+// 1029 vs 1084 TFLOP/s; LN+GELU fc in the ViT loop 395 vs 270 µs — the 12 statistics segments per row and the
+// 64-column slices no longer fit the register budget), so 8 is the default.
+#ifndef GB_EPI_WARPS
+#define GB_EPI_WARPS 8
+#endif
+constexpr int kEpiWarps2 = GB_EPI_WARPS;
+static_assert(kEpiWarps2 == 8 || kEpiWarps2 == 16, "8 or 16 epilogue warps");
+constexpr int kEpiCols = 256 / (kEpiWarps2 / 4);
+constexpr int kGemm2Threads = 128 + 32 * kEpiWarps2;
+constexpr int kEpiRegs = kEpiWarps2 == 8 ? 232 : 112;   // setmaxnreg budgets: (128·kCtlRegs + 32·warps·kEpiRegs)
+constexpr int kCtlRegs = kEpiWarps2 == 8 ? 40 : 24;     //   must fit 65536 / threads rounded down to 8, per thread
+constexpr int kLnMaxParts = 768 / kEpiCols;             // statistics segments of a row (D ≤ 768)
+
 // (μ·rstd, rstd) of one row from its per-segment shifted partials (x0, Σ(x−x0), Σ(x−x0)²): per segment
 // mean and centred second moment, then Chan's pairwise update in a fixed segment order (deterministic,
 // free of the E[x²]−μ² cancellation).
-__device__ __forceinline__ float2 ln_merge_parts(const float4 (&lp)[6], int nparts, float seg_n) {
+__device__ __forceinline__ float2 ln_merge_parts(const float4 (&lp)[kLnMaxParts], int nparts, float seg_n) {
   float n = 0.f, mean = 0.f, m2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < 6; ++i) {
+  for (int i = 0; i < kLnMaxParts; ++i) {
     if (i < nparts) {
       const float4 t = lp[i];
       const float mp = t.x + t.y / seg_n;
@@ -350,9 +366,9 @@ __device__ __forceinline__ float2 ln_merge_parts(const float4 (&lp)[6], int npar
   const float rstd = rsqrtf(fmaxf(m2 / n, 0.f) + 1e-5f);
   return make_float2(mean * rstd, rstd);
 }
-__device__ __forceinline__ void ln_load_parts(const GemmParams& p, int row, float4 (&lp)[6]) {
+__device__ __forceinline__ void ln_load_parts(const GemmParams& p, int row, float4 (&lp)[kLnMaxParts]) {
 #pragma unroll
-  for (int i = 0; i < 6; ++i)
+  for (int i = 0; i < kLnMaxParts; ++i)
     if (i < p.ln_nparts) lp[i] = __ldg(p.ln_parts + (size_t)i * p.M + row);
 }
 
@@ -374,31 +390,33 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
                                                        uint8_t* slabs, uint32_t tmem_acc, int m0,
                                                        int n_base, int warp, int lane, float2& ln_st,
                                                        int next_m0, uint32_t consts_s, uint32_t consts_next_s,
-                                                       int next_n_base, uint4 (&pre_lo)[8], float4 (&lp)[6],
-                                                       bool& lp_pending, WaitAcc&& wait_acc,
-                                                       ReleaseAcc&& release_acc) {
-  constexpr int BN = 256;
+                                                       int next_n_base, uint4 (&pre_lo)[kEpiCols / 16],
+                                                       float4 (&lp)[kLnMaxParts], bool& lp_pending,
+                                                       WaitAcc&& wait_acc, ReleaseAcc&& release_acc) {
+  constexpr int kCols = kEpiCols;         // accumulator columns per warp: 128 (8 warps) or 64 (16 warps)
+  constexpr int kChunks = kCols / 32;     // 32-column chunks, one half-slab each
+  constexpr int kPreHalf = kCols / 16;    // 16-byte pieces of fp16 in half of a warp's row slice
   constexpr bool kLn = kMode == kEpiLn || kMode == kEpiLnGelu;
   constexpr bool kGelu = kMode == kEpiGelu || kMode == kEpiLnGelu;
   constexpr bool kAct2 = kMode == kEpiAct2;
   constexpr bool kPre = kMode == kEpiResid || kMode == kEpiAct2;
   const int q = warp & 3;
-  const int half = (warp - 4) >> 2;
+  const int cg = (warp - 4) >> 2;   // column group of this warp
   const __half* pre_base = kAct2 ? p.aux : p.resid;
   const int pre_ld = kAct2 ? p.ldo : p.ldr;
-  const int n0 = n_base + half * (BN / 2);
+  const int n0 = n_base + cg * kCols;
   const int row0 = m0 + q * 32;
   const int row = row0 + lane;
   const bool row_ok = row < p.M;
   const bool has_pre = kPre && pre_base != nullptr && row_ok;
   // The operand that comes from global memory (residual, or the saved pre-activation for act 2) is
-  // fetched ahead: columns 0-63 of this row were requested at the end of the previous tile (pre_lo,
-  // carried across tiles); columns 64-127 are requested now, before the accumulator is even ready.
-  uint4 pre_hi[kPre ? 8 : 1];
+  // fetched ahead: the first half of this row's columns was requested at the end of the previous tile
+  // (pre_lo, carried across tiles); the second half is requested now, before the accumulator is even ready.
+  uint4 pre_hi[kPre ? kPreHalf : 1];
   if (has_pre) {
-    const uint4* r4 = reinterpret_cast<const uint4*>(pre_base + (size_t)row * pre_ld + n0 + 64);
+    const uint4* r4 = reinterpret_cast<const uint4*>(pre_base + (size_t)row * pre_ld + n0 + kCols / 2);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) pre_hi[j] = r4[j];
+    for (int j = 0; j < kPreHalf; ++j) pre_hi[j] = r4[j];
   }
   // row statistics of the folded LayerNorm: (μ·rstd, rstd) of this tile's row were fetched while the
   // previous tile was processed; the next tile's are requested now
@@ -415,31 +433,38 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
   const bool ln_parts_next = kLn && p.ln_parts != nullptr && next_m0 >= 0 && ln_nrow < p.M;
   if (kLn && p.ln_parts == nullptr && next_m0 >= 0 && ln_nrow < p.M)
     ln_next = *reinterpret_cast<const float2*>(p.ln_stats + (size_t)ln_nrow * 2);
-  // next tile's per-column constants: lane l fetches columns 4l … 4l+3 of the warp's 128
-  float4 nb = make_float4(0.f, 0.f, 0.f, 0.f), ns = nb;
+  // next tile's per-column constants: lane l fetches kCols/32 consecutive columns of the warp's slice
+  constexpr int kCPL = kCols / 32;
+  float nb[kCPL], ns[kCPL];
+#pragma unroll
+  for (int i = 0; i < kCPL; ++i) nb[i] = ns[i] = 0.f;
   if (!kAct2 && next_n_base >= 0) {
-    const int nc = next_n_base + half * (BN / 2) + 4 * lane;
-    if (p.bias != nullptr) nb = __ldg(reinterpret_cast<const float4*>(p.bias + nc));
-    if (kLn) ns = __ldg(reinterpret_cast<const float4*>(p.col_sum + nc));
+    const int nc = next_n_base + cg * kCols + kCPL * lane;
+#pragma unroll
+    for (int i = 0; i < kCPL; ++i) {
+      if (p.bias != nullptr) nb[i] = __ldg(p.bias + nc + i);
+      if (kLn) ns[i] = __ldg(p.col_sum + nc + i);
+    }
   }
   float st_sum = 0.f, st_sq = 0.f, st_x0 = 0.f;
   wait_acc();
   tc_fence_after();
-  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + half * (BN / 2);
-  uint32_t v[128];
-  tmem_ld_32x64(taddr, v);
-  tmem_ld_32x64(taddr + 64, v + 64);
+  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + cg * kCols;
+  uint32_t v[kCols];
+#pragma unroll
+  for (int i = 0; i < kCols / 64; ++i) tmem_ld_32x64(taddr + 64 * i, v + 64 * i);
   tmem_ld_wait();
   tc_fence_before();
   __syncwarp();
   release_acc();  // the accumulator is in registers: the MMA thread may overwrite it
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {  // 32-column chunks, one half-slab each
+  for (int c = 0; c < kChunks; ++c) {  // 32-column chunks, one half-slab each
     const int col0 = n0 + c * 32;
     uint4 pre[kPre ? 4 : 1];
     if constexpr (kPre) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) pre[j] = c < 2 ? pre_lo[4 * c + j] : pre_hi[4 * (c - 2) + j];
+      for (int j = 0; j < 4; ++j)
+        pre[j] = c < kChunks / 2 ? pre_lo[4 * c + j] : pre_hi[4 * (c - kChunks / 2) + j];
     }
     uint8_t* slab = slabs + (c & 1) * 2048;
     const uint32_t slab_s = smem_u32(slab);
@@ -454,7 +479,7 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 bb = lds128f(consts_s + (c * 32 + 4 * j) * 4);
-        const float4 ss = lds128f(consts_s + 512 + (c * 32 + 4 * j) * 4);
+        const float4 ss = lds128f(consts_s + kCols * 4 + (c * 32 + 4 * j) * 4);
         f[4 * j + 0] = fmaf(f[4 * j + 0], ln_rstd, fmaf(ln_mr, ss.x, bb.x));
         f[4 * j + 1] = fmaf(f[4 * j + 1], ln_rstd, fmaf(ln_mr, ss.y, bb.y));
         f[4 * j + 2] = fmaf(f[4 * j + 2], ln_rstd, fmaf(ln_mr, ss.z, bb.z));
@@ -532,12 +557,15 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
     }
   }
   if (!kAct2 && next_n_base >= 0) {  // park the next tile's constants (all reads of this tile's are done)
-    sts128f(consts_next_s + lane * 16, nb);
-    if (kLn) sts128f(consts_next_s + 512 + lane * 16, ns);
+#pragma unroll
+    for (int i = 0; i < kCPL; ++i) {
+      sts32f(consts_next_s + (kCPL * lane + i) * 4, nb[i]);
+      if (kLn) sts32f(consts_next_s + kCols * 4 + (kCPL * lane + i) * 4, ns[i]);
+    }
     __syncwarp();
   }
   if (kMode == kEpiResid && p.stats_out != nullptr && row_ok)
-    *reinterpret_cast<float4*>(p.stats_out + ((size_t)(n0 >> 7) * p.M + row) * 4) =
+    *reinterpret_cast<float4*>(p.stats_out + ((size_t)(n0 / kCols) * p.M + row) * 4) =
         make_float4(st_x0, st_sum, st_sq, 0.f);
   // look-ahead loads for the next tile, after this tile's last fence
   if constexpr (kLn) {
@@ -545,13 +573,13 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
     if (ln_parts_next) ln_load_parts(p, ln_nrow, lp);
   }
   if constexpr (kPre) {
-    if (next_m0 >= 0 && pre_base != nullptr) {  // the next tile's columns 0-63 of this thread's row
+    if (next_m0 >= 0 && pre_base != nullptr) {  // the first half of the next tile's slice of this thread's row
       const int nrow = next_m0 + q * 32 + lane;
       if (nrow < p.M) {
         const uint4* r4 = reinterpret_cast<const uint4*>(pre_base + (size_t)nrow * pre_ld + next_n_base +
-                                                         half * (BN / 2));
+                                                         cg * kCols);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) pre_lo[j] = r4[j];
+        for (int j = 0; j < kPreHalf; ++j) pre_lo[j] = r4[j];
       }
     }
   }
@@ -591,9 +619,12 @@ struct TileWalk {
 
 struct Gemm2Cfg {
   static constexpr int BN = 256;
-  static constexpr int kStages = 5;
-  static constexpr int kSlabBytes = 8 * 2 * 2048;      // two 32x64 B output half-slabs per epilogue warp
-  static constexpr int kConstBytes = 8 * 2 * 1024;     // per warp, double-buffered: 128 biases + 128 column sums
+#ifndef GB_STAGES2
+#define GB_STAGES2 (GB_EPI_WARPS == 8 ? 5 : 4)  // measured: 4, 5 and 6 stages perform alike; 16 warps need the smem
+#endif
+  static constexpr int kStages = GB_STAGES2;
+  static constexpr int kSlabBytes = kEpiWarps2 * 2 * 2048;          // two 32x64 B output half-slabs per epilogue warp
+  static constexpr int kConstBytes = kEpiWarps2 * 2 * kEpiCols * 8;  // per warp, double-buffered: biases + column sums
   static constexpr int kABytes = kBM * kBK * 2;        // 16 KB: this CTA's 128 rows of A
   static constexpr int kBBytes = (BN / 2) * kBK * 2;   // 16 KB: this CTA's half of the W tile
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -602,7 +633,7 @@ struct Gemm2Cfg {
 };
 
 template <int kPairs, int kMode>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemm2Threads, 1)
 gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
                              const __grid_constant__ CUtensorMap tmB,
                              const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
@@ -653,7 +684,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);    // the leader's multicast commit
-      mbar_init(&tempty_bar[s], 16);  // 8 epilogue warps of each CTA
+      mbar_init(&tempty_bar[s], 2 * kEpiWarps2);  // the epilogue warps of both CTAs
     }
     fence_barrier_init();
   }
@@ -666,7 +697,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) reg_dealloc<40>();  // warpgroup 0 (TMA, MMA, TMEM-alloc, idle) hands its registers over
+  if (warp < 4) reg_dealloc<kCtlRegs>();  // warpgroup 0 (TMA, MMA, TMEM-alloc, idle) hands its registers over
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
@@ -739,7 +770,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
     }
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps, both CTAs; fp16 output through TMA stores) =====================
-    reg_alloc<232>();
+    reg_alloc<kEpiRegs>();
     int it = 0;
     GB_STALL_DECL(w_tfull);
     GB_STALL_T(t_epi0);
@@ -748,7 +779,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
       const int r = (cluster_id / n_tiles) * kClusterRows + row_off + (warp & 3) * 32 + lane;
       if (cluster_id < num_tiles && r < p.M) {
         if (p.ln_parts != nullptr) {
-          float4 lp[6];
+          float4 lp[kLnMaxParts];
           ln_load_parts(p, r, lp);
           ln_st = ln_merge_parts(lp, p.ln_nparts, p.ln_seg_n);
         } else {
@@ -756,28 +787,31 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
         }
       }
     }
-    const uint32_t consts_s = smem_u32(smem_consts + (warp - 4) * 2048);
+    constexpr int kStrip = kEpiCols * 8;  // one buffer of the warp's constants: biases | column sums
+    const uint32_t consts_s = smem_u32(smem_consts + (warp - 4) * 2 * kStrip);
     if (kMode != kEpiAct2 && cluster_id < num_tiles) {  // the first tile's per-column constants
-      const int nc = (cluster_id % n_tiles) * BN + ((warp - 4) >> 2) * (BN / 2) + 4 * lane;
-      float4 b = make_float4(0.f, 0.f, 0.f, 0.f), cs = b;
-      if (p.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.bias + nc));
-      if (kMode == kEpiLn || kMode == kEpiLnGelu) cs = __ldg(reinterpret_cast<const float4*>(p.col_sum + nc));
-      sts128f(consts_s + lane * 16, b);
-      sts128f(consts_s + 512 + lane * 16, cs);
+      constexpr int kCPL = kEpiCols / 32;
+      const int nc = (cluster_id % n_tiles) * BN + ((warp - 4) >> 2) * kEpiCols + kCPL * lane;
+#pragma unroll
+      for (int i = 0; i < kCPL; ++i) {
+        sts32f(consts_s + (kCPL * lane + i) * 4, p.bias != nullptr ? __ldg(p.bias + nc + i) : 0.f);
+        if (kMode == kEpiLn || kMode == kEpiLnGelu)
+          sts32f(consts_s + kEpiCols * 4 + (kCPL * lane + i) * 4, __ldg(p.col_sum + nc + i));
+      }
       __syncwarp();
     }
-    float4 lp[6];
+    float4 lp[kLnMaxParts];
     bool lp_pending = false;
-    uint4 pre_lo[8];
+    uint4 pre_lo[kEpiCols / 16];
     if ((kMode == kEpiResid || kMode == kEpiAct2) && cluster_id < num_tiles) {  // first tile's columns 0-63
       const __half* pre_base = kMode == kEpiAct2 ? p.aux : p.resid;
       const int pre_ld = kMode == kEpiAct2 ? p.ldo : p.ldr;
       const int r = (cluster_id / n_tiles) * kClusterRows + row_off + (warp & 3) * 32 + lane;
       if (pre_base != nullptr && r < p.M) {
         const uint4* r4 = reinterpret_cast<const uint4*>(
-            pre_base + (size_t)r * pre_ld + (cluster_id % n_tiles) * BN + ((warp - 4) >> 2) * (BN / 2));
+            pre_base + (size_t)r * pre_ld + (cluster_id % n_tiles) * BN + ((warp - 4) >> 2) * kEpiCols);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) pre_lo[j] = r4[j];
+        for (int j = 0; j < kEpiCols / 16; ++j) pre_lo[j] = r4[j];
       }
     }
     TileWalk tw(cluster_id, num_clusters, n_tiles);
@@ -792,7 +826,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
       const int next_n0 = more ? tw.ni * BN : -1;
       gemm_epilogue_tile_tma<kMode>(
           p, &tmC, smem_slabs + (warp - 4) * 4096, tmem_base + as * BN, m0, n0, warp, lane, ln_st, next_m0,
-          consts_s + (it & 1) * 1024, consts_s + ((it + 1) & 1) * 1024, next_n0, pre_lo, lp, lp_pending,
+          consts_s + (it & 1) * kStrip, consts_s + ((it + 1) & 1) * kStrip, next_n0, pre_lo, lp, lp_pending,
           [&]() {
             GB_STALL_T(t_tf);
             mbar_wait(&tfull_bar[as], aphase);

@@ -89,7 +89,7 @@ struct Tape {
 // in their epilogue, and the two residual GEMMs emit the (Σ, Σ²) partials of the rows they write,
 // which a tiny kernel turns into (μ·rstd, rstd) per row.
 // st_fin: [M][2] (μ·rstd, rstd) of the current residual stream (valid for x on entry);
-// st_part: [D/128][M] float4 scratch for the shifted partial sums.
+// st_part: [D/GB_STAT_SEG][M] float4 scratch for the shifted partial sums.
 // first_rows != nullptr (inference only, no tape): the caller needs just row 0 of every sample from the last
 // block (the image tower's CLS token, models/clip_encoders.py:189-192).  Everything after that block's
 // attention — out-proj + residual, ln_2, c_fc, QuickGELU, c_proj + residual — is row-wise, so it runs on
@@ -115,7 +115,7 @@ int run_blocks(gb_ctx* c, const gb_tower* t, int S, int L, int causal, void* x, 
       // layer 0 reads the statistics the assemble kernel finalized; later layers merge the partials the
       // previous c_proj GEMM emitted in their own epilogue
       gb_gemm_ln ln1; ln1.col_sum = w.s_qkv;
-      if (l == 0) ln1.ln_stats = st_fin; else { ln1.ln_parts = st_part; ln1.nparts = D / 128; }
+      if (l == 0) ln1.ln_stats = st_fin; else { ln1.ln_parts = st_part; ln1.nparts = D / GB_STAT_SEG; }
       if ((rc = gb_launch_gemm(c, x0, D, w.w_qkv, D, w.b_qkv, nullptr, 0, qkv, 3 * D, M, 3 * D, D, 0, 0, st, nullptr, &ln1))) return rc;
     } else {
       if ((rc = gb_launch_layernorm(c, x0, D, nullptr, 1, w.ln1_g, w.ln1_b, h, D, M, D, 0, st))) return rc;
@@ -129,7 +129,7 @@ int run_blocks(gb_ctx* c, const gb_tower* t, int S, int L, int causal, void* x, 
       const int ldr = L * D;  // row 0 of sample s sits at row s·L of the [M, D] buffers
       if ((rc = gb_launch_gemm(c, a, ldr, w.w_o, D, w.b_o, x0, ldr, xc1, D, S, D, D, 0, 0, st, nullptr, fold ? &emit : nullptr))) return rc;
       if (fold) {
-        gb_gemm_ln ln2; ln2.ln_parts = st_part; ln2.nparts = D / 128; ln2.col_sum = w.s_fc;
+        gb_gemm_ln ln2; ln2.ln_parts = st_part; ln2.nparts = D / GB_STAT_SEG; ln2.col_sum = w.s_fc;
         if ((rc = gb_launch_gemm(c, xc1, D, w.w_fc, D, w.b_fc, nullptr, 0, gc, 4 * D, S, 4 * D, D, 1, 0, st, nullptr, &ln2))) return rc;
       } else {
         if ((rc = gb_launch_layernorm(c, xc1, D, nullptr, 1, w.ln2_g, w.ln2_b, h, D, S, D, 0, st))) return rc;
@@ -140,7 +140,7 @@ int run_blocks(gb_ctx* c, const gb_tower* t, int S, int L, int causal, void* x, 
     }
     if ((rc = gb_launch_gemm(c, a, D, w.w_o, D, w.b_o, x0, D, x1, D, M, D, D, 0, 0, st, nullptr, fold ? &emit : nullptr))) return rc;
     if (fold) {
-      gb_gemm_ln ln2; ln2.ln_parts = st_part; ln2.nparts = D / 128; ln2.col_sum = w.s_fc;
+      gb_gemm_ln ln2; ln2.ln_parts = st_part; ln2.nparts = D / GB_STAT_SEG; ln2.col_sum = w.s_fc;
       if ((rc = gb_launch_gemm(c, x1, D, w.w_fc, D, w.b_fc, nullptr, 0, g, 4 * D, M, 4 * D, D, 1, 0, st,
                                tape ? tape->f(l) : nullptr, &ln2))) return rc;
     } else {
@@ -247,7 +247,7 @@ extern "C" int gb_vit_forward(gb_ctx* c, const void* img, int img_f32, const flo
     Bump b(nullptr);
     b.take(h2(M, D)); b.take(h2(M, D)); b.take(h2(M, 3 * D)); b.take(h2(M, D));
     b.take(h2(M > (size_t)B * 49 ? M : (size_t)B * 49, 4 * D)); b.take(h2(B, D)); b.take((size_t)B * 512 * 4);
-    b.take(M * 8); b.take(M * (D / 128) * 16); b.take(h2(B, 6 * D));
+    b.take(M * 8); b.take(M * (D / GB_STAT_SEG) * 16); b.take(h2(B, 6 * D));
     need = b.off;
   }
   int rc = gb_ws_reserve(c, gb_ctx::kWsVit, need);
@@ -261,7 +261,7 @@ extern "C" int gb_vit_forward(gb_ctx* c, const void* img, int img_f32, const flo
   void* cls_ln = b.take(h2(B, D));
   float* feat_ws = reinterpret_cast<float*>(b.take((size_t)B * 512 * 4));
   float* st_a = reinterpret_cast<float*>(b.take(M * 8));                 // (μ·rstd, rstd) per row
-  float* st_b = reinterpret_cast<float*>(b.take(M * (D / 128) * 16));    // shifted partials per 128 columns
+  float* st_b = reinterpret_cast<float*>(b.take(M * (D / GB_STAT_SEG) * 16));    // shifted partials per GB_STAT_SEG columns
   void* cls_rows = b.take(h2(B, 6 * D));                                 // last block on the CLS rows only
   Tape tape{reinterpret_cast<uint8_t*>(tape_mem), M, (size_t)D};
   void* x = tape_mem ? tape.x0(0) : x_ws;
@@ -344,7 +344,7 @@ extern "C" int gb_text_forward(gb_ctx* c, const int32_t* ids, int ld_ids, const 
     Bump b(nullptr);
     b.take(h2(M, D)); b.take(h2(M, D)); b.take(h2(M, 3 * D)); b.take(h2(M, D)); b.take(h2(M, 4 * D));
     b.take(h2(C, D)); b.take((size_t)C * 512 * 4); b.take((size_t)C * 4);
-    b.take(M * 8); b.take(M * (D / 128) * 16);
+    b.take(M * 8); b.take(M * (D / GB_STAT_SEG) * 16);
     need = b.off;
   }
   int rc = gb_ws_reserve(c, gb_ctx::kWsText, need);
@@ -359,7 +359,7 @@ extern "C" int gb_text_forward(gb_ctx* c, const int32_t* ids, int ld_ids, const 
   float* feat_ws = reinterpret_cast<float*>(b.take((size_t)C * 512 * 4));
   int32_t* rows = reinterpret_cast<int32_t*>(b.take((size_t)C * 4));
   float* st_a = reinterpret_cast<float*>(b.take(M * 8));                 // (μ·rstd, rstd) per row
-  float* st_b = reinterpret_cast<float*>(b.take(M * (D / 128) * 16));    // shifted partials per 128 columns
+  float* st_b = reinterpret_cast<float*>(b.take(M * (D / GB_STAT_SEG) * 16));    // shifted partials per GB_STAT_SEG columns
   Tape tape{reinterpret_cast<uint8_t*>(tape_mem), M, (size_t)D};
   void* x = tape_mem ? tape.x0(0) : x_ws;
   // token embedding, prefix overwrite of rows 1..P, + positional embedding: models/clip_encoders.py:63-74
