@@ -143,6 +143,7 @@ template <int NT>
 __global__ void __launch_bounds__(128)
 attn_fwd_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int L, int D,
                 int causal) {
+  pdl_launch_dependents();  // the out-proj GEMM behind us may set itself up while we drain
   constexpr int Lp = NT * 8;  // multiple of 16
   extern __shared__ __align__(16) uint8_t attn_smem[];
   __half* Qs = reinterpret_cast<__half*>(attn_smem);
@@ -207,6 +208,7 @@ template <int NT>
 __global__ void __launch_bounds__(128)
 attn_bwd_kernel(const __half* __restrict__ qkv, const __half* __restrict__ dout,
                 __half* __restrict__ dqkv, int L, int D, int causal) {
+  pdl_launch_dependents();
   constexpr int Lp = NT * 8;
   constexpr int ldp = Lp + 8;   // row stride of the [Lp, Lp] P / dS tiles
   extern __shared__ __align__(16) uint8_t attn_smem[];

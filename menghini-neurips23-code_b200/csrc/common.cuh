@@ -63,6 +63,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ----------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may
+// become resident while its predecessor in the stream is still draining; pdl_wait() blocks until the
+// predecessor has completed and its memory is visible (a no-op for an ordinary launch), and
+// pdl_launch_dependents() lets the successor be scheduled early.  Nothing before pdl_wait() may touch
+// global memory another kernel of the stream writes or reads (frozen weights are fine).
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------
 // TMA
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

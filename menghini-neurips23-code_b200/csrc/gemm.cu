@@ -5,6 +5,16 @@
 
 using namespace gb;
 
+// Programmatic dependent launch of the GEMMs (GB_PDL=0 turns it off, for A/B measurements).
+static bool gb_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("GB_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+
 
 template <int BN>
 static int launch_gemm_bn(gb_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmB,
@@ -20,9 +30,16 @@ static int launch_gemm_bn(gb_ctx* c, const CUtensorMap& tmA, const CUtensorMap& 
   const int tiles = m_tiles * (p.N / BN);
   const int sms = gb_gemm_sms(c);
   const int grid = tiles < sms ? tiles : sms;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = st;
+  cfg.attrs = attr; cfg.numAttrs = gb_pdl_enabled() ? 1 : 0;
   {
     gb_prof_scope prof(c, st, 0, 2.0 * p.M * p.N * p.K, p.M, p.N, p.K);
-    gemm_f16_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+    GB_CUDA(c, cudaLaunchKernelEx(&cfg, gemm_f16_tcgen05_kernel<BN>, tmA, tmB, p));
   }
   GB_LAUNCH_CHECK(c);
   return GB_OK;
@@ -39,13 +56,15 @@ static int launch_gemm_2cta(gb_ctx* c, const CUtensorMap& tmA, const CUtensorMap
   constexpr int kCluster = 2 * kPairs;
   auto kernel = gemm_f16_tcgen05_2cta_kernel<kPairs, kMode>;
   cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see pdl_wait() in the kernel
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.blockDim = dim3(kGemm2Threads);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  cfg.attrs = attr; cfg.numAttrs = gb_pdl_enabled() ? 2 : 1;
   static bool attr_set[16] = {false};
   if (!attr_set[c->device & 15]) {
     GB_CUDA(c, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));

@@ -242,6 +242,9 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above overlapped the predecessor's tail (programmatic dependent launch)
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -696,6 +699,11 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
   cluster_sync_all();  // barriers of BOTH CTAs are initialised before anything can signal them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: barrier set-up, TMEM allocation and descriptor prefetch above ran while the
+  // previous kernel of the stream was still draining its last tiles; its results (A, residual, statistics)
+  // are touched only from here on, and the next kernel may be scheduled as soon as SMs free up.
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp < 4) reg_dealloc<kCtlRegs>();  // warpgroup 0 (TMA, MMA, TMEM-alloc, idle) hands its registers over
   if (warp == 0) {

@@ -86,6 +86,7 @@ layernorm_kernel(const __half* __restrict__ x, int ldx, const int32_t* __restric
 template <typename InT>
 __global__ void __launch_bounds__(256)
 im2col_patch32_kernel(const InT* __restrict__ img, __half* __restrict__ out, int B) {
+  pdl_launch_dependents();
   // one thread per 8 consecutive kx: total = B*3*224*28 groups
   const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)B * 3 * 224 * 28;
@@ -128,6 +129,7 @@ im2col_patch32_kernel(const InT* __restrict__ img, __half* __restrict__ out, int
 // divisions made the kernel ALU-bound at a third of the HBM rate.
 __global__ void __launch_bounds__(256)
 im2col_patch32_u8_kernel(const uint8_t* __restrict__ img, __half* __restrict__ out, int B) {
+  pdl_launch_dependents();
   __shared__ __half lut[3 * 256];
   for (int i = threadIdx.x; i < 3 * 256; i += 256) {
     const int c = i >> 8;
@@ -170,6 +172,7 @@ vit_assemble_lnpre_kernel(const __half* __restrict__ patch, const float* __restr
                           const float* __restrict__ pos, const float* __restrict__ prefix, int P,
                           const float* __restrict__ gamma, const float* __restrict__ beta,
                           __half* __restrict__ x, int B, float eps, float* __restrict__ stats) {
+  pdl_launch_dependents();
   constexpr int D = 768, V = 3;
   const int L = 50 + P;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -254,6 +257,7 @@ __global__ void __launch_bounds__(256)
 text_assemble_kernel(const int32_t* __restrict__ ids, int ld_ids, const __half* __restrict__ tok_emb,
                      const float* __restrict__ pos, const float* __restrict__ prefix, int P,
                      __half* __restrict__ x, int C, int ctx_len, float* __restrict__ stats) {
+  pdl_launch_dependents();
   constexpr int D = 512, V = 2;
   float st_sum = 0.f, st_sq = 0.f;
   float kept[V * 8];  // the stored (rounded) row, for the two-pass statistics
@@ -350,6 +354,7 @@ layernorm_bwd_kernel(const __half* __restrict__ dy, int lddy, const __half* __re
                      const int32_t* __restrict__ row_idx, int in_row_mul,
                      const float* __restrict__ gamma, __half* __restrict__ dx, int lddx, int rows,
                      int accumulate, float eps) {
+  pdl_launch_dependents();
   constexpr int V = D / 256;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
