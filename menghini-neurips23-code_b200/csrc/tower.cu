@@ -90,19 +90,19 @@ struct Tape {
 // which a tiny kernel turns into (μ·rstd, rstd) per row.
 // st_fin: [M][2] (μ·rstd, rstd) of the current residual stream (valid for x on entry);
 // st_part: [D/GB_STAT_SEG][M] float4 scratch for the shifted partial sums.
-// first_rows != nullptr (inference only, no tape): the caller needs just row 0 of every sample from the last
-// block (the image tower's CLS token, models/clip_encoders.py:189-192).  Everything after that block's
-// attention — out-proj + residual, ln_2, c_fc, QuickGELU, c_proj + residual — is row-wise, so it runs on
-// those S rows only (read in place through a row stride of L·D) and leaves them compact in first_rows
-// [S, 6·D halves: x1 | x2 | 4·D of MLP scratch].  Per-row arithmetic is unchanged, so the features are
-// bit-identical to the dense evaluation; the reference computes and discards the other rows
-// (5.6 % of the tower's FLOPs at L = 50).
+// first_rows != nullptr: the caller needs just row 0 of every sample from the last block (the image tower's
+// CLS token, models/clip_encoders.py:189-192).  Everything after that block's attention — out-proj +
+// residual, ln_2, c_fc, QuickGELU, c_proj + residual — is row-wise, so it runs on those S rows only, read in
+// place through a row stride of L·D.  Without a tape the rows are left compact in first_rows [S, 6·D halves:
+// x1 | x2 | 4·D of MLP scratch]; with a tape they are written to their own places in the tape (x1, f and
+// x_final of the last block are then valid on the CLS rows only — run_blocks_bwd(cls_only) reads nothing
+// else).  Per-row arithmetic is unchanged, so features and gradients are bit-identical to the dense
+// evaluation; the reference computes and discards the other rows (5.6 % of the tower's FLOPs at L = 50).
 int run_blocks(gb_ctx* c, const gb_tower* t, int S, int L, int causal, void* x, const Tape* tape,
                void* h, void* qkv_ws, void* a, void* g, float* st_fin, float* st_part, cudaStream_t st,
                void* first_rows = nullptr) {
   const int D = t->width, M = S * L;
   int rc;
-  if (first_rows && tape) return gb_fail(c, GB_ERR_ARG, "run_blocks: first_rows is an inference-only path");
   for (int l = 0; l < t->layers; ++l) {
     const gb_block_weights& w = t->blocks[l];
     void* x0 = tape ? tape->x0(l) : x;
@@ -123,19 +123,23 @@ int run_blocks(gb_ctx* c, const gb_tower* t, int S, int L, int causal, void* x, 
     }
     if ((rc = gb_launch_attn_fwd(c, qkv, a, S, L, D, causal, st))) return rc;
     if (first_rows && l + 1 == t->layers) {
-      uint8_t* xc1 = reinterpret_cast<uint8_t*>(first_rows);
-      uint8_t* xc2 = xc1 + h2(S, D);
-      uint8_t* gc = xc2 + h2(S, D);
       const int ldr = L * D;  // row 0 of sample s sits at row s·L of the [M, D] buffers
-      if ((rc = gb_launch_gemm(c, a, ldr, w.w_o, D, w.b_o, x0, ldr, xc1, D, S, D, D, 0, 0, st, nullptr, fold ? &emit : nullptr))) return rc;
+      // compact scratch without a tape; the rows' own places in the tape (and in g) with one
+      void* xc1 = tape ? x1 : first_rows;
+      void* xc2 = tape ? x2 : reinterpret_cast<uint8_t*>(first_rows) + h2(S, D);
+      void* gc = tape ? g : reinterpret_cast<uint8_t*>(first_rows) + 2 * h2(S, D);
+      const int ld1 = tape ? ldr : D, ldg = tape ? 4 * ldr : 4 * D;
+      if ((rc = gb_launch_gemm(c, a, ldr, w.w_o, D, w.b_o, x0, ldr, xc1, ld1, S, D, D, 0, 0, st, nullptr, fold ? &emit : nullptr))) return rc;
       if (fold) {
         gb_gemm_ln ln2; ln2.ln_parts = st_part; ln2.nparts = D / GB_STAT_SEG; ln2.col_sum = w.s_fc;
-        if ((rc = gb_launch_gemm(c, xc1, D, w.w_fc, D, w.b_fc, nullptr, 0, gc, 4 * D, S, 4 * D, D, 1, 0, st, nullptr, &ln2))) return rc;
+        if ((rc = gb_launch_gemm(c, xc1, ld1, w.w_fc, D, w.b_fc, nullptr, 0, gc, ldg, S, 4 * D, D, 1, 0, st,
+                                 tape ? tape->f(l) : nullptr, &ln2))) return rc;
       } else {
-        if ((rc = gb_launch_layernorm(c, xc1, D, nullptr, 1, w.ln2_g, w.ln2_b, h, D, S, D, 0, st))) return rc;
-        if ((rc = gb_launch_gemm(c, h, D, w.w_fc, D, w.b_fc, nullptr, 0, gc, 4 * D, S, 4 * D, D, 1, 0, st))) return rc;
+        if ((rc = gb_launch_layernorm(c, xc1, ld1, nullptr, 1, w.ln2_g, w.ln2_b, h, D, S, D, 0, st))) return rc;
+        if ((rc = gb_launch_gemm(c, h, D, w.w_fc, D, w.b_fc, nullptr, 0, gc, ldg, S, 4 * D, D, 1, 0, st,
+                                 tape ? tape->f(l) : nullptr))) return rc;
       }
-      if ((rc = gb_launch_gemm(c, gc, 4 * D, w.w_proj, 4 * D, w.b_proj, xc1, D, xc2, D, S, D, 4 * D, 0, 0, st))) return rc;
+      if ((rc = gb_launch_gemm(c, gc, ldg, w.w_proj, 4 * D, w.b_proj, xc1, ld1, xc2, ld1, S, D, 4 * D, 0, 0, st))) return rc;
       break;
     }
     if ((rc = gb_launch_gemm(c, a, D, w.w_o, D, w.b_o, x0, D, x1, D, M, D, D, 0, 0, st, nullptr, fold ? &emit : nullptr))) return rc;
@@ -156,14 +160,30 @@ int run_blocks(gb_ctx* c, const gb_tower* t, int S, int L, int causal, void* x, 
 
 // Reverse pass through the blocks: dx (fp16 [M,D], loss-scaled) is d loss / d x_final on entry and
 // d loss / d x0(layer 0) on exit.
+// cls_only: d loss / d x_final is non-zero on row 0 of every sample only (and zero elsewhere in dx), and the
+// forward left x1 / f of the last block valid on those rows only (run_blocks with first_rows + tape): the last
+// block's MLP and out-proj backward run on the S CLS rows through a row stride of L·D; from its attention
+// backward on everything is dense (every key and value contributes to the CLS query).
 int run_blocks_bwd(gb_ctx* c, const gb_tower* t, int S, int L, int causal, void* dx,
-                   const Tape& tape, void* dh, void* dqkv, void* dg, cudaStream_t st) {
+                   const Tape& tape, void* dh, void* dqkv, void* dg, cudaStream_t st, bool cls_only = false) {
   const int D = t->width, M = S * L;
   int rc;
   for (int l = t->layers - 1; l >= 0; --l) {
     const gb_block_weights& w = t->blocks[l];
     if (!w.w_qkv_t || !w.w_o_t || !w.w_fc_t || !w.w_proj_t)
       return gb_fail(c, GB_ERR_STATE, "backward: transposed weights were not provided");
+    if (cls_only && l + 1 == t->layers) {
+      const int ldr = L * D;
+      if ((rc = gb_launch_gemm(c, dx, ldr, w.w_proj_t, D, nullptr, nullptr, 0, dg, 4 * ldr, S, 4 * D, D, 2, 0, st, tape.f(l)))) return rc;
+      GB_CUDA(c, cudaMemsetAsync(dh, 0, h2(M, D), st));  // the attention backward reads dO of every row
+      if ((rc = gb_launch_gemm(c, dg, 4 * ldr, w.w_fc_t, 4 * D, nullptr, nullptr, 0, dh, ldr, S, D, 4 * D, 0, 0, st))) return rc;
+      if ((rc = gb_launch_layernorm_bwd(c, dh, ldr, tape.x1(l), ldr, nullptr, 1, w.ln2_g, dx, ldr, S, D, 1, st))) return rc;
+      if ((rc = gb_launch_gemm(c, dx, ldr, w.w_o_t, D, nullptr, nullptr, 0, dh, ldr, S, D, D, 0, 0, st))) return rc;
+      if ((rc = gb_launch_attn_bwd(c, tape.qkv(l), dh, dqkv, S, L, D, causal, st))) return rc;
+      if ((rc = gb_launch_gemm(c, dqkv, 3 * D, w.w_qkv_t, 3 * D, nullptr, nullptr, 0, dh, D, M, D, 3 * D, 0, 0, st))) return rc;
+      if ((rc = gb_launch_layernorm_bwd(c, dh, D, tape.x0(l), D, nullptr, 1, w.ln1_g, dx, D, M, D, 1, st))) return rc;
+      continue;
+    }
     // MLP branch: x2 = x1 + c_proj(QuickGELU(c_fc(ln_2(x1))))
     if ((rc = gb_launch_gemm(c, dx, D, w.w_proj_t, D, nullptr, nullptr, 0, dg, 4 * D, M, 4 * D, D, 2, 0, st, tape.f(l)))) return rc;
     if ((rc = gb_launch_gemm(c, dg, 4 * D, w.w_fc_t, 4 * D, nullptr, nullptr, 0, dh, D, M, D, 4 * D, 0, 0, st))) return rc;
@@ -271,9 +291,8 @@ extern "C" int gb_vit_forward(gb_ctx* c, const void* img, int img_f32, const flo
   if ((rc = gb_launch_gemm(c, g, 3072, w.conv_w, 3072, nullptr, nullptr, 0, a, D, B * 49, D, 3072, 0, 0, st))) return rc;
   // CLS + pos-emb, prefix rows, ln_pre: :135-157
   if ((rc = gb_launch_vit_assemble(c, a, w.cls, w.pos, prefix, P, w.ln_pre_g, w.ln_pre_b, x, B, st, st_a))) return rc;
-  // without a tape only the CLS rows of the last block are evaluated past its attention (see run_blocks)
-  if ((rc = run_blocks(c, t, B, L, 0, x, tape_mem ? &tape : nullptr, h, qkv, a, g, st_a, st_b, st,
-                       tape_mem ? nullptr : cls_rows))) return rc;
+  // only the CLS rows of the last block are evaluated past its attention (see run_blocks)
+  if ((rc = run_blocks(c, t, B, L, 0, x, tape_mem ? &tape : nullptr, h, qkv, a, g, st_a, st_b, st, cls_rows))) return rc;
   // ln_post(x[:,0,:]) @ proj: :189-192
   if (tape_mem) {
     if ((rc = gb_launch_layernorm(c, tape.x_final(t->layers), D, nullptr, L, w.ln_post_g, w.ln_post_b, cls_ln, D, B, D, 0, st))) return rc;
@@ -321,7 +340,7 @@ extern "C" int gb_vit_backward_prefix(gb_ctx* c, const float* dfeat, const float
   if ((rc = gb_launch_gemm(c, d16, 512, w.proj, 512, nullptr, nullptr, 0, dcls, D, B, D, 512, 0, 0, st))) return rc;
   GB_CUDA(c, cudaMemsetAsync(dx, 0, h2(M, D), st));
   if ((rc = gb_launch_layernorm_bwd(c, dcls, D, tape.x_final(t->layers), D, nullptr, L, w.ln_post_g, dx, D, B, D, 0, st))) return rc;
-  if ((rc = run_blocks_bwd(c, t, B, L, 0, dx, tape, dh, dqkv, dg, st))) return rc;
+  if ((rc = run_blocks_bwd(c, t, B, L, 0, dx, tape, dh, dqkv, dg, st, /*cls_only=*/true))) return rc;
   return gb_launch_prefix_grad(c, dx, L, B, P, D, prefix, w.ln_pre_g, 1, 1.0f / kGradScale, dprefix, st);
 }
 
