@@ -381,6 +381,17 @@ __device__ __forceinline__ void quick_gelu4(float& a, float& b, float& c, float&
   d *= rcd * ec;
 }
 
+// Two QuickGELUs sharing one reciprocal (1.5 MUFU and 7 instructions per element).
+__device__ __forceinline__ void quick_gelu2(float& a, float& b) {
+  constexpr float k = -2.4554669595930157f;
+  constexpr float kMax = 1.8446744073709552e19f;  // 2^64: the product of two cannot overflow
+  const float ea = fminf(fast_exp2(k * a), kMax) + 1.0f;
+  const float eb = fminf(fast_exp2(k * b), kMax) + 1.0f;
+  const float r = fast_rcp(ea * eb);
+  a *= r * eb;
+  b *= r * ea;
+}
+
 __device__ __forceinline__ float quick_gelu_grad(float x) {
   // d/dx [x·σ(1.702x)] = σ + 1.702·x·σ·(1−σ)
   const float s = fast_rcp(1.0f + fast_exp2(-2.4554669595930157f * x));

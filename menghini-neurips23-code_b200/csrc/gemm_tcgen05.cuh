@@ -332,6 +332,10 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 //    row segments and clips rows >= M.  Direct per-thread stores (32 row-strided 16-byte pieces per
 //    instruction) were the bottleneck of every K=768 GEMM.  Two half-slabs per warp alternate, so one
 //    is rewritten only after the store issued two chunks earlier has finished reading it.
+#ifndef GB_GELU_SHARE
+#define GB_GELU_SHARE 4  // QuickGELUs per shared reciprocal (1, 2 or 4)
+#endif
+
 // Epilogue geometry of the CTA-pair kernel: GB_EPI_WARPS epilogue warps (8 or 16) — TMEM lane quadrant
 // warp % 4, column group (warp − 4) / 4 of 256 / (GB_EPI_WARPS / 4) columns.  Measured on B200 (same box,
 // sustained loops): 16 warps of 112 registers are SLOWER than 8 warps of 232 on every flavour (plain fc
@@ -508,8 +512,16 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
           a4[j] = o;
         }
       }
+#if GB_GELU_SHARE == 4
 #pragma unroll
       for (int j = 0; j < 8; ++j) quick_gelu4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+#elif GB_GELU_SHARE == 2
+#pragma unroll
+      for (int j = 0; j < 16; ++j) quick_gelu2(f[2 * j], f[2 * j + 1]);
+#else
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
+#endif
     } else if (kAct2 && has_pre) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {

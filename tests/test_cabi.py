@@ -103,3 +103,18 @@ def test_warmup_cosine_lr_is_the_reference_rule():
         for step in range(total + 3):
             got = lib.gb_warmup_cosine_lr(0.1, warm, total, step)
             assert abs(got - 0.1 * lr_lambda(step, warm, total)) <= 1e-15, (warm, total, step, got)
+
+
+def test_wave_aligned_batch_fills_whole_gemm_waves():
+    """Engine.wave_aligned_batch: the returned batch makes every tower GEMM's tile count (256-row blocks x
+    N/256 column tiles, N in {768, 2304, 3072}) a multiple of the CTA pairs in use, and is the largest such."""
+    import importlib
+
+    Engine = importlib.import_module("menghini-neurips23-code_b200.engine").Engine
+    for sms, L in ((144, 50), (148, 50), (144, 66), (148, 66)):
+        b = Engine.wave_aligned_batch(1024, L=L, sms=sms)
+        pairs = sms // 2
+        blocks = -(-(b * L) // 256)
+        assert all((blocks * n) % pairs == 0 for n in (3, 9, 12)), (sms, L, b)
+        assert all((-(-(c * L) // 256) * 3) % pairs != 0 for c in range(b + 1, 1025)), (sms, L, b)
+    assert Engine.wave_aligned_batch(1024, L=50, sms=144) == 983
