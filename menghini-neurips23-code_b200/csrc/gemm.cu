@@ -138,7 +138,7 @@ int gb_launch_gemm(gb_ctx* c, const void* A, int lda, const void* W, int ldw, co
   if (!wide) return launch_gemm_bn<128>(c, tmA, tmB, p, st);
   // output tensor map for the TMA-store epilogue: 32-column x 32-row boxes (64 B swizzle)
   CUtensorMap tmC;
-  rc = gb_make_tmap_2d_f16(c, &tmC, out, (uint64_t)M, (uint64_t)N, (uint64_t)ldo, 32, 32);
+  rc = gb_make_tmap_2d_f16(c, &tmC, out, (uint64_t)M, (uint64_t)N, (uint64_t)ldo, 32, GB_SLAB_COLS);
   if (rc) return rc;
   const bool fold = p.ln_stats != nullptr || p.ln_parts != nullptr;
   if (p.stats_out != nullptr && (fold || act != 0 || !resid))

@@ -332,6 +332,9 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 //    row segments and clips rows >= M.  Direct per-thread stores (32 row-strided 16-byte pieces per
 //    instruction) were the bottleneck of every K=768 GEMM.  Two half-slabs per warp alternate, so one
 //    is rewritten only after the store issued two chunks earlier has finished reading it.
+#ifndef GB_SLAB_COLS
+#define GB_SLAB_COLS 32  // columns per TMA store of the epilogue: 32 (2 KB half-slabs, 64B swizzle) or 64 (4 KB, 128B)
+#endif
 #ifndef GB_GELU_SHARE
 #define GB_GELU_SHARE 4  // QuickGELUs per shared reciprocal (1, 2 or 4)
 #endif
@@ -473,11 +476,21 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
       for (int j = 0; j < 4; ++j)
         pre[j] = c < kChunks / 2 ? pre_lo[4 * c + j] : pre_hi[4 * (c - kChunks / 2) + j];
     }
+#if GB_SLAB_COLS == 64
+    uint8_t* slab = slabs + ((c >> 1) & 1) * 4096;
+    const uint32_t slab_s = smem_u32(slab);
+    if ((c & 1) == 0) {
+      // the store that last used this slab (two stores ago) must be done reading it
+      if (lane == 0) tma_store_wait_read<1>();
+      __syncwarp();
+    }
+#else
     uint8_t* slab = slabs + (c & 1) * 2048;
     const uint32_t slab_s = smem_u32(slab);
     // the store that last used this half-slab (two chunks ago) must be done reading it
     if (lane == 0) tma_store_wait_read<1>();
     __syncwarp();
+#endif
     float f[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[32 * c + j]);
@@ -562,14 +575,29 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
           st_sq = fmaf(d0, d0, fmaf(d1, d1, st_sq));
         }
       }
+#if GB_SLAB_COLS == 64
+      sts128(slab_s + lane * 128 + ((((c & 1) * 4 + j) ^ (lane & 7)) << 4), o);
+#else
       sts128(slab_s + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), o);
+#endif
     }
+#if GB_SLAB_COLS == 64
+    if (c & 1) {
+      fence_proxy_async();  // generic-proxy writes → visible to the TMA engine
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmC, slab, col0 - 32, row0);
+        tma_store_commit();
+      }
+    }
+#else
     fence_proxy_async();  // generic-proxy writes → visible to the TMA engine
     __syncwarp();
     if (lane == 0) {
       tma_store_2d(tmC, slab, col0, row0);
       tma_store_commit();
     }
+#endif
   }
   if (!kAct2 && next_n_base >= 0) {  // park the next tile's constants (all reads of this tile's are done)
 #pragma unroll
@@ -635,10 +663,10 @@ struct TileWalk {
 struct Gemm2Cfg {
   static constexpr int BN = 256;
 #ifndef GB_STAGES2
-#define GB_STAGES2 (GB_EPI_WARPS == 8 ? 5 : 4)  // measured: 4, 5 and 6 stages perform alike; 16 warps need the smem
+#define GB_STAGES2 ((GB_EPI_WARPS == 8 && GB_SLAB_COLS == 32) ? 5 : 4)  // measured: 4, 5 and 6 stages perform alike; 16 warps need the smem
 #endif
   static constexpr int kStages = GB_STAGES2;
-  static constexpr int kSlabBytes = kEpiWarps2 * 2 * 2048;          // two 32x64 B output half-slabs per epilogue warp
+  static constexpr int kSlabBytes = kEpiWarps2 * 2 * 64 * GB_SLAB_COLS;  // two 32-row output (half-)slabs per epilogue warp
   static constexpr int kConstBytes = kEpiWarps2 * 2 * kEpiCols * 8;  // per warp, double-buffered: biases + column sums
   static constexpr int kABytes = kBM * kBK * 2;        // 16 KB: this CTA's 128 rows of A
   static constexpr int kBBytes = (BN / 2) * kBK * 2;   // 16 KB: this CTA's half of the W tile
@@ -845,7 +873,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
       const int next_m0 = more ? tw.mi * kClusterRows + row_off : -1;
       const int next_n0 = more ? tw.ni * BN : -1;
       gemm_epilogue_tile_tma<kMode>(
-          p, &tmC, smem_slabs + (warp - 4) * 4096, tmem_base + as * BN, m0, n0, warp, lane, ln_st, next_m0,
+          p, &tmC, smem_slabs + (warp - 4) * (128 * GB_SLAB_COLS), tmem_base + as * BN, m0, n0, warp, lane, ln_st, next_m0,
           consts_s + (it & 1) * kStrip, consts_s + ((it + 1) & 1) * kStrip, next_n0, pre_lo, lp, lp_pending,
           [&]() {
             GB_STALL_T(t_tf);
