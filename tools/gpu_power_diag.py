@@ -65,7 +65,7 @@ t.join()
 ms = e0.elapsed_time(e1) / n
 flop = 2 * 49 * 3072 * 768 + 12 * (24 * 50 * 768 ** 2 + 4 * 50 ** 2 * 768) + 2 * 768 * 512
 print(f"vit fwd B={B}: {ms:.3f} ms/iter over {n} iters = {B / ms * 1e3:.0f} img/s = "
-      f"{B * flop / ms / 1e9:.0f} TFLOP/s (GB_GEMM_PAIRS={os.environ.get('GB_GEMM_PAIRS', 'auto')})")
+      f"{B * flop / ms / 1e9:.0f} TFLOP/s")
 body = samples[len(samples) // 4:]
 clk = sorted(s[1] for s in body)
 pw = sorted(s[2] for s in body)
