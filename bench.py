@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0,
-                    help="images per GPU per step (0: the largest batch ≤ 1024 whose GEMM tile counts fill whole "
+                    help="images per GPU per step (0: the largest batch ≤ 2048 whose GEMM tile counts fill whole "
                          "waves of the CTA pairs the image tower runs on, see Engine.wave_aligned_batch)")
     ap.add_argument("--classes", type=int, default=10)
     ap.add_argument("--prefix", type=int, default=16)
@@ -523,11 +523,11 @@ def run_b200(a, rank, local_rank, world):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f16 (fp32 accumulate)",
                 "data": "synthetic",
                 "config": {"workload": workload_name(a, B), "weights": "random-init ViT-B/32 (seed 1234)",
-                           "l2_policy": "inputs larger than L2 (154 MB uint8 image batch per step + 0.3 GB of weights, "
-                                        "~2 GB of activations)",
+                           "l2_policy": f"inputs larger than L2 ({B * 150528 / 1e6:.0f} MB uint8 image batch per step + 0.3 GB "
+                                        f"of weights, GBs of activations)",
                            "input": "uint8 pixels, ToTensor + Normalize fused into the patch gather on the device "
                                     "(bit-identical to host-normalised fp32 input)",
-                           "batch_per_gpu": f"{B} (largest ≤ 1024 that fills whole GEMM waves on the "
+                           "batch_per_gpu": f"{B} (largest ≤ {1024 if vpt else 2048} that fills whole GEMM waves on the "
                                             f"{(a.sm_limit if overlap and a.sm_limit > 0 else 148) // 2} CTA pairs in use)",
                            "parallelism": f"dp{world}: image batch and pool sharded, prefix-grad all-reduce, "
                                           f"ordered leaderboard hand-off" if world > 1 else "single GPU",
@@ -556,7 +556,7 @@ def main():
         vpt = a.workload == "vpt"
         capped = not a.no_overlap and not vpt and a.sm_limit > 0
         a.batch = importlib.import_module(PKG + ".engine").Engine.wave_aligned_batch(
-            1024, L=50 + (a.prefix if vpt else 0), sms=a.sm_limit if capped else 148)
+            1024 if vpt else 2048, L=50 + (a.prefix if vpt else 0), sms=a.sm_limit if capped else 148)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
