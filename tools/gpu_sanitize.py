@@ -1,0 +1,39 @@
+"""Small end-to-end pass for compute-sanitizer (memcheck): every kernel family once at tiny sizes.
+usage: compute-sanitizer --tool memcheck python tools/gpu_sanitize.py"""
+import importlib
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+PKG = "menghini-neurips23-code_b200"
+clip = importlib.import_module(PKG + ".clip")
+models = importlib.import_module(PKG + ".models")
+engine_mod = importlib.import_module(PKG + ".engine")
+training = importlib.import_module(PKG + ".training")
+synthetic = importlib.import_module(PKG + ".synthetic")
+
+model, _ = clip.load("ViT-B/32", "cuda:0", state_dict=synthetic.synthetic_state_dict(1234))
+eng = model.engine
+classes = ["annual crop", "forest", "river lake"]
+img = torch.randint(0, 256, (3, 3, 224, 224), dtype=torch.uint8, device="cuda")
+feat, featn, _ = eng.vit_forward(img, None, want_feat=True, want_featn=True)                 # frozen tower, CLS-only tail
+cie = models.CustomImageEncoder(model.visual)
+ipm = models.ImagePrefixModel(((768 ** -0.5) * torch.randn(4, 768)).cuda(), cie, device="cuda:0")
+ipm(img.float()).square().sum().backward()                                                   # taped forward + backward
+cte = models.CustomTextEncoder(model, "cuda:0", torch.float16)
+tpm = models.TextPrefixModel((0.02 * torch.randn(1, 16, 512)).cuda(), cte, classes, device="cuda:0")
+step = training.CoOpStep(tpm, lr=1e-3, weight_decay=0.1, momentum=0.9, warmup_epochs=1, epochs=3, graph=False)
+labels = torch.tensor([0, 1, 2], device="cuda")
+for _ in range(2):
+    loss, _ = step.step(featn, labels)                                                       # text fwd/bwd, CE, SGD
+f16 = torch.nn.functional.normalize(torch.randn(700, 512, device="cuda"), dim=1).half()
+t16 = torch.nn.functional.normalize(torch.randn(45, 512, device="cuda"), dim=1).half()
+lb = engine_mod.Leaderboard(45, 4, "cuda:0")
+lb.scan(f16, t16, 100.0, rank=torch.randperm(700).to(torch.int32).cuda())                    # sim + leaderboard
+t200 = torch.nn.functional.normalize(torch.randn(200, 512, device="cuda"), dim=1).half()
+eng.sim_softmax_argmax(f16, t200, 100.0, want_probs=True)                                    # class-chunked path
+torch.cuda.synchronize()
+print("sanitize pass done: loss", float(loss), "boards", sum(len(b) for b in lb.result()[0:1]))
