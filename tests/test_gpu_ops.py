@@ -54,6 +54,17 @@ def test_gemm_epilogues(ctx):
     _gemm_case(ctx, 333, 512, 768, out_f32=True)
 
 
+def test_gemm_epilogues_many_tiles_per_cta(ctx):
+    """Every epilogue flavour at a size where a persistent CTA pair walks 5-19 tiles: exercises the look-ahead
+    paths (next tile's column constants, residual half carried across tiles, incremental tile walk)."""
+    _gemm_case(ctx, 30000, 768, 768)
+    _gemm_case(ctx, 30000, 2304, 768, bias=True)
+    _gemm_case(ctx, 30000, 3072, 768, bias=True, act=1)
+    _gemm_case(ctx, 30000, 768, 768, bias=True, resid=True)
+    _gemm_case(ctx, 30000, 768, 3072, bias=True, resid=True, inplace=True)
+    _gemm_case(ctx, 29999, 768, 3072, resid=True)
+
+
 def test_gemm_rows_do_not_depend_on_batch(ctx):
     """Bit-identical rows whatever M is (tile shape is a function of N only)."""
     g = torch.Generator(device="cuda").manual_seed(1)
