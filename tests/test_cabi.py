@@ -118,3 +118,23 @@ def test_wave_aligned_batch_fills_whole_gemm_waves():
         assert all((blocks * n) % pairs == 0 for n in (3, 9, 12)), (sms, L, b)
         assert all((-(-(c * L) // 256) * 3) % pairs != 0 for c in range(b + 1, 1025)), (sms, L, b)
     assert Engine.wave_aligned_batch(1024, L=50, sms=144) == 983
+
+
+def test_predictions_frame_matches_the_reference_bookkeeping():
+    """utils.predictions_frame = the tail of the reference's test_predictions
+    (methods/semi_supervised_learning/textual_prompt.py:256-294): ids are file names, classes are names, rows with
+    the same (id, class) are dropped, first occurrence order is kept."""
+    import importlib
+
+    import pandas as pd
+
+    utils = importlib.import_module("menghini-neurips23-code_b200.utils")
+    classes = ["forest", "river", "highway"]
+    paths = ["/d/a/img1.jpg", "/d/b/img2.jpg", "/d/c/img1.jpg", "/d/a/img3.jpg", "/d/z/img2.jpg"]
+    pred = [2, 0, 2, 1, 1]
+    got = utils.predictions_frame(paths, pred, classes)
+    # what the reference builds (:289-294)
+    want = pd.DataFrame({"id": [p.split("/")[-1] for p in paths], "class": [classes[i] for i in pred]})
+    want.drop_duplicates(subset=["id", "class"], inplace=True)
+    pd.testing.assert_frame_equal(got, want)
+    assert list(got["id"]) == ["img1.jpg", "img2.jpg", "img3.jpg", "img2.jpg"]
