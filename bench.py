@@ -242,7 +242,8 @@ def run_b200(a, rank, local_rank, world):
     tpm = models.TextPrefixModel((0.02 * torch.randn(1, P, 512, generator=gp)).to(dev), cte, classes, device=dev)
     opt = torch.optim.SGD([tpm.prefix], lr=1e-4)   # WARMUP_LR of textual_prompt_config.yml
     scale = eng.logit_scale_exp
-    total_steps = a.warmup + a.steps + 3 + a.warmup + a.steps
+    # device-resident arm, 3 roofline steps, e2e arm, e2e_f32 arm: every step scans its own slice of image indices
+    total_steps = 3 * (a.warmup + a.steps) + 3
     n_total = total_steps * world * B
     rank_all = torch.randperm(n_total, generator=torch.Generator().manual_seed(7)).to(torch.int32).to(dev)
     board = engine_mod.Leaderboard(C, k, dev)
