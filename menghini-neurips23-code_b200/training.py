@@ -18,6 +18,26 @@ import torch
 from . import dist as _dist
 
 
+def fpl_coefficients(second_group: torch.Tensor, w_first: float = 1.0, w_second: float = 1.0) -> torch.Tensor:
+    """Per-sample weights that turn the FPL strategies' two-term loss into one weighted sum.
+
+    The reference computes `w_first * CE(batch[first]) + w_second * CE(batch[second])`, each CE the MEAN over its
+    group and an empty group contributing 0 — SSL: first = labeled (not in `check_unlabeled`), w_first =
+    `balance_param`, second = pseudolabeled, w_second = 1 (methods/semi_supervised_learning/textual_fpl.py:123-165);
+    TRZSL: first = seen-class samples, w_first = 1, second = unseen-class samples, w_second = `balance_param`
+    (methods/transductive_zsl/textual_fpl.py:117-147).  `second_group` is the boolean membership mask of the batch;
+    the result feeds `CoOpStep.step(..., coef=...)` / `gb_ce_text_grad`."""
+    second = second_group.bool()
+    n2 = int(second.sum().item())
+    n1 = int(second.numel()) - n2
+    coef = torch.zeros(second.shape, dtype=torch.float32, device=second.device)
+    if n1:
+        coef[~second] = float(w_first) / n1
+    if n2:
+        coef[second] = float(w_second) / n2
+    return coef
+
+
 class CoOpStep:
     """`momentum` is the optimizer's (the reference's base trainer file is missing from the scrape, SURVEY F3;
     torch.optim.SGD with the YAML's LR / DECAY is what its call sites imply) — pass what your trainer uses.

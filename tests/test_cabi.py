@@ -138,3 +138,25 @@ def test_predictions_frame_matches_the_reference_bookkeeping():
     want.drop_duplicates(subset=["id", "class"], inplace=True)
     pd.testing.assert_frame_equal(got, want)
     assert list(got["id"]) == ["img1.jpg", "img2.jpg", "img3.jpg", "img2.jpg"]
+
+
+def test_fpl_coefficients_reproduce_the_two_term_loss():
+    """training.fpl_coefficients: Σ coef_i · CE_i equals the reference's `w1 * mean CE(first) + w2 * mean CE(second)`
+    (methods/semi_supervised_learning/textual_fpl.py:123-165, methods/transductive_zsl/textual_fpl.py:117-147),
+    including batches where one group is empty."""
+    import importlib
+
+    import torch
+
+    training = importlib.import_module("menghini-neurips23-code_b200.training")
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(16, 7, generator=g) * 3
+    labels = torch.randint(0, 7, (16,), generator=g)
+    ce = torch.nn.functional.cross_entropy
+    for mask in (torch.rand(16, generator=g) < 0.4, torch.zeros(16, dtype=torch.bool), torch.ones(16, dtype=torch.bool)):
+        for w1, w2 in ((2.5, 1.0), (1.0, 0.3)):
+            want = (w1 * ce(logits[~mask], labels[~mask]) if (~mask).any() else 0) + \\
+                   (w2 * ce(logits[mask], labels[mask]) if mask.any() else 0)
+            coef = training.fpl_coefficients(mask, w1, w2)
+            got = (coef * ce(logits, labels, reduction="none")).sum()
+            assert abs(float(got) - float(want)) <= 1e-6 * max(1.0, abs(float(want)))
