@@ -155,8 +155,9 @@ def test_fpl_coefficients_reproduce_the_two_term_loss():
     ce = torch.nn.functional.cross_entropy
     for mask in (torch.rand(16, generator=g) < 0.4, torch.zeros(16, dtype=torch.bool), torch.ones(16, dtype=torch.bool)):
         for w1, w2 in ((2.5, 1.0), (1.0, 0.3)):
-            want = (w1 * ce(logits[~mask], labels[~mask]) if (~mask).any() else 0) + \\
-                   (w2 * ce(logits[mask], labels[mask]) if mask.any() else 0)
+            first = w1 * ce(logits[~mask], labels[~mask]) if (~mask).any() else 0
+            second = w2 * ce(logits[mask], labels[mask]) if mask.any() else 0
+            want = first + second
             coef = training.fpl_coefficients(mask, w1, w2)
             got = (coef * ce(logits, labels, reduction="none")).sum()
             assert abs(float(got) - float(want)) <= 1e-6 * max(1.0, abs(float(want)))
