@@ -359,21 +359,25 @@ constexpr int kLnMaxParts = 768 / kEpiCols;             // statistics segments o
 // mean and centred second moment, then Chan's pairwise update in a fixed segment order (deterministic,
 // free of the E[x²]−μ² cancellation).
 __device__ __forceinline__ float2 ln_merge_parts(const float4 (&lp)[kLnMaxParts], int nparts, float seg_n) {
-  float n = 0.f, mean = 0.f, m2 = 0.f;
+  // All segments have the same length, so Chan's weights are constants of the segment index: after i
+  // segments  mean += δ/(i+1)  and  M2 += M2_seg + δ²·seg_n·i/(i+1).  No run-time divisions (the IEEE
+  // division sequence of the straightforward form was a sixth of the LN-folding epilogues' instructions);
+  // 1/seg_n is exact (seg_n is a power of two).
+  const float inv_seg = 1.0f / seg_n;
+  float mean = 0.f, m2 = 0.f;
 #pragma unroll
   for (int i = 0; i < kLnMaxParts; ++i) {
     if (i < nparts) {
       const float4 t = lp[i];
-      const float mp = t.x + t.y / seg_n;
-      const float m2p = t.z - t.y * t.y / seg_n;
-      const float nn = n + seg_n;
+      const float sm = t.y * inv_seg;              // segment mean − x0
+      const float mp = t.x + sm;                   // segment mean
+      const float m2p = fmaf(-sm, t.y, t.z);       // Σ (x − segment mean)²
       const float delta = mp - mean;
-      mean += delta * (seg_n / nn);
-      m2 += m2p + delta * delta * (n * seg_n / nn);
-      n = nn;
+      mean = fmaf(delta, 1.0f / (float)(i + 1), mean);
+      m2 += m2p + delta * delta * (seg_n * ((float)i / (float)(i + 1)));
     }
   }
-  const float rstd = rsqrtf(fmaxf(m2 / n, 0.f) + 1e-5f);
+  const float rstd = rsqrtf(fmaxf(m2 * (1.0f / ((float)nparts * seg_n)), 0.f) + 1e-5f);
   return make_float2(mean * rstd, rstd);
 }
 __device__ __forceinline__ void ln_load_parts(const GemmParams& p, int row, float4 (&lp)[kLnMaxParts]) {
