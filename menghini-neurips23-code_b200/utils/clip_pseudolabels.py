@@ -22,7 +22,7 @@ from ..engine import Leaderboard
 log = logging.getLogger(__name__)
 
 ALL_UNLABELED_K = 10000000  # :27
-ENCODE_BATCH = 256
+ENCODE_BATCH = None  # None: Engine.wave_aligned_batch — the largest chunk ≤ 2048 that fills whole GEMM waves
 
 
 def path_ranks(paths):
@@ -45,6 +45,8 @@ def encode_pool(clip_model, filepaths, transform, device, batch=ENCODE_BATCH, lo
     from PIL import Image
 
     eng = clip_model.engine
+    if not batch:
+        batch = type(eng).wave_aligned_batch(2048, L=50, sms=148)
     feats = torch.empty(len(filepaths), 512, device=eng.device, dtype=torch.float16)
     for s in range(0, len(filepaths), batch):
         chunk = filepaths[s:s + batch]

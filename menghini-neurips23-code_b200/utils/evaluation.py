@@ -34,7 +34,7 @@ def predictions_frame(filepaths, pred_idx, class_names):
     return df
 
 
-def test_predictions(clip_model, text_features, dataset, transform, class_names, loader=None, batch=256):
+def test_predictions(clip_model, text_features, dataset, transform, class_names, loader=None, batch=None):
     """Batched replacement of the per-strategy `test_predictions` bodies: `text_features` are the caller's prompts
     [C,512] (any float dtype, normalised or not — they are normalised here as at :250-251)."""
     eng = clip_model.engine
