@@ -55,6 +55,10 @@ def _preprocess(raw: bool = False):
             return x.contiguous()
         return (x.float() / 255.0 - mean) / std
 
+    if not raw:
+        # the same transform without its ToTensor / Normalize tail: batched pool encoders use it and let the
+        # device normalise (bit-identical features, a quarter of the host→device bytes)
+        transform.raw_u8 = _preprocess(raw=True)
     return transform
 
 

@@ -41,22 +41,39 @@ def path_ranks(paths):
 
 
 def encode_pool(clip_model, filepaths, transform, device, batch=ENCODE_BATCH, loader=None):
-    """Unit-norm fp16 image features [N,512] of the whole pool, encoded in batches."""
+    """Unit-norm fp16 image features [N,512] of the whole pool, encoded in batches.
+
+    The reference decodes and encodes one image at a time (:55-61).  Here a background thread decodes chunk
+    i+1 (PIL releases the GIL) into pinned memory while the device encodes chunk i; when `transform` is this
+    package's CLIP transform its `raw_u8` twin is used — resize + centre crop on the host, ToTensor +
+    Normalize on the device, bit-identical features."""
+    from concurrent.futures import ThreadPoolExecutor
+
     from PIL import Image
 
     eng = clip_model.engine
     if not batch:
         batch = type(eng).wave_aligned_batch(2048, L=50, sms=148)
     feats = torch.empty(len(filepaths), 512, device=eng.device, dtype=torch.float16)
-    for s in range(0, len(filepaths), batch):
-        chunk = filepaths[s:s + batch]
+    tf = getattr(transform, "raw_u8", None) or transform
+
+    def load(chunk):
         if loader is not None:
             imgs = loader(chunk)
         else:
-            imgs = torch.stack([transform(Image.open(p).convert("RGB")) for p in chunk])
-        imgs = imgs.to(eng.device, non_blocking=True)
-        _, fn, _ = eng.vit_forward(imgs, None, want_feat=False, want_featn=True)
-        feats[s:s + len(chunk)] = fn
+            imgs = torch.stack([tf(Image.open(p).convert("RGB")) for p in chunk])
+        return imgs.pin_memory() if imgs.device.type == "cpu" else imgs
+
+    starts = list(range(0, len(filepaths), batch))
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        fut = pool.submit(load, filepaths[starts[0]:starts[0] + batch]) if starts else None
+        for i, s in enumerate(starts):
+            imgs = fut.result()
+            if i + 1 < len(starts):
+                fut = pool.submit(load, filepaths[starts[i + 1]:starts[i + 1] + batch])
+            imgs = imgs.to(eng.device, non_blocking=True)
+            _, fn, _ = eng.vit_forward(imgs, None, want_feat=False, want_featn=True)
+            feats[s:s + imgs.shape[0]] = fn
     return feats
 
 
