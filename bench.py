@@ -14,9 +14,16 @@ pseudolabel assignment (k=16) on the same batch:
                                                            (assign_pseudo_labels, textual_fpl.py:195-283)
 Images are raw uint8 pixels (the resized + centre-cropped crop); ToTensor + Normalize run on the device,
 fused into the patch gather, bit-identical to the reference's host transform (tests/test_gpu_towers.py).
+Steps 2-3 run through `training.CoOpStep` (gb_text_forward with tape → gb_ce_text_grad → gb_text_backward_prefix →
+gb_sgd_step, replayed as one CUDA graph at N = 1): no torch / cuBLAS kernel is left in the timed step.
 `value` times the step with the batch already resident in HBM; `e2e` feeds every step from pinned host
 memory (H2D copy inside the timed region, double buffered) and reads the loss and predictions back;
 `e2e_f32` is the same with host-normalised fp32 tensors, what the reference's DataLoader hands over.
+Extra keys, measured outside the timed region: at N = 1 `vpt_step` (configs[2] shape: P=16, C=102, forward with tape +
+prompt-only backward through the image tower), `upt_step` (configs[4] shape: 4+4 coupled prompts, C=100, both
+towers) and `ref_batch16` (the CoOp step at the reference's own BATCH_SIZE 16, fused and through the plain
+drop-in classes); at N > 1 `multi_gpu_parity` (C/G prompts per rank → ONE all-gather of the prototypes → two-phase
+sharded pool scan with the ordered leaderboard hand-off, boards compared with a single-GPU scan of the same pool).
 """
 from __future__ import annotations
 
@@ -36,7 +43,24 @@ if ROOT not in sys.path:
 PKG = "menghini-neurips23-code_b200"
 
 METRIC = "images/sec ViT-B/32 prompt-tune+pseudolabel"
-FLOP_VIT_P0 = 2 * 49 * 3072 * 768 + 12 * (24 * 50 * 768 ** 2 + 4 * 50 ** 2 * 768) + 2 * 768 * 512  # 8.818 G
+
+
+def flop_vit(P=0):
+    """Dense forward FLOPs per image of the ViT-B/32 tower with P prompt rows (SURVEY §8d / BASELINE.md §3)."""
+    L = 50 + P
+    return 2 * 49 * 3072 * 768 + 12 * (24 * L * 768 ** 2 + 4 * L ** 2 * 768) + 2 * 768 * 512
+
+
+def flop_vit_executed(P=0):
+    """… minus what the CLS-only last block skips (out-proj + MLP of the other L−1 rows): what really runs."""
+    return flop_vit(P) - (50 + P - 1) * 18 * 768 ** 2
+
+
+def flop_text(L):
+    return 12 * (24 * L * 512 ** 2 + 4 * L ** 2 * 512) + 2 * 512 ** 2
+
+
+FLOP_VIT_P0 = flop_vit(0)  # 8.818 G
 
 
 def parse():
@@ -53,6 +77,7 @@ def parse():
     ap.add_argument("--k", type=int, default=16)
     ap.add_argument("--cpu-batch", type=int, default=16, help="reference BATCH_SIZE for the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip vpt_step / upt_step / ref_batch16 / parity")
     ap.add_argument("--workload", default="coop", choices=["coop", "vpt"],
                     help="coop: BASELINE configs[1] (the bench line); vpt: configs[2] shape — visual prompt "
                          "(P=16) train step with backward through the image tower, C=102, extra data point")
@@ -70,6 +95,27 @@ def workload_name(a, batch):
                 f"{batch} synthetic 224x224x3 uint8 images per GPU per step")
     return (f"CoOp prompt-tune step (P={a.prefix}, C={a.classes}, ViT-B/32, SGD) + FPL pseudolabel "
             f"leaderboard (k={a.k}) on {batch} synthetic 224x224x3 uint8 images per GPU per step")
+
+
+def config_dict(a, B, world):
+    """`config` of the JSON line: the same keys and values on both arms (the driver compares them)."""
+    vpt = a.workload == "vpt"
+    overlap = not a.no_overlap and not vpt
+    return {"workload": workload_name(a, B), "weights": "random-init ViT-B/32 (seed 1234)",
+            "l2_policy": f"inputs larger than L2 ({B * 150528 / 1e6:.0f} MB uint8 image batch per step + 0.3 GB "
+                         f"of weights, GBs of activations)",
+            "input": "uint8 pixels, ToTensor + Normalize fused into the patch gather on the device "
+                     "(bit-identical to host-normalised fp32 input)",
+            "batch_per_gpu": f"{B} (largest <= {1024 if vpt else 2048} that fills whole GEMM waves on the "
+                             f"{(a.sm_limit if overlap and a.sm_limit > 0 else 148) // 2} CTA pairs in use)",
+            "parallelism": (f"dp{world}: image batch and pool sharded, prefix-grad all-reduce, "
+                            f"ordered leaderboard hand-off") if world > 1 else "single GPU",
+            "streams": (f"image tower on the main stream (GEMM grids capped at {a.sm_limit} SMs), text "
+                        f"chain + pseudolabel scan of the same step on a side stream") if overlap
+                       else "single stream",
+            "text_positions": "positions after EOT skipped (exact under the causal mask)",
+            "reference_arm": f"the same step on the host cores (fp32 torch oracle port of the reference path), each "
+                             f"step a bounded sample of {a.cpu_batch} images (the reference's BATCH_SIZE)"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -115,21 +161,20 @@ def cpu_arm(a, steps, warmup, budget_s=None):
                       f"(fp32 torch CPU oracle of the reference path, {dt:.1f} s)"}, dt / done * 1e3, done
 
 
-def run_reference(a, rank):
+def run_reference(a, rank, world):
     if rank != 0:
         return
-    base, ms, done = cpu_arm(a, a.steps, min(a.warmup, 1), budget_s=150.0)
+    base, ms, done = cpu_arm(a, a.steps, a.warmup, budget_s=150.0)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "images/s",
-            "n_gpus": a.gpus, "steps": done, "warmup": min(a.warmup, 1), "ms_per_step": ms,
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": workload_name(a, a.batch),
-                                            "note": f"reference CPU path (oracle port of the same step), each step "
-                                                    f"a bounded sample of {a.cpu_batch} images (the reference's "
-                                                    f"BATCH_SIZE) on all host cores"},
+            "data": "synthetic", "config": config_dict(a, a.batch, world),
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if done != a.steps:
+        line["steps_completed"] = done   # the 150 s budget cut the run short
     print(json.dumps(line), flush=True)
 
 
@@ -187,11 +232,234 @@ def peaks():
             p = json.load(open(path))
             return {"hbm_gbs": float(p["hbm_gbs"]),
                     "tflops": float(p.get("bf16_tflops_sustained", p.get("bf16_tflops"))),
-                    "src": "measured (MEASURED_PEAKS.json: hbm_gbs, bf16_tflops_sustained)"}
+                    "tflops_burst": float(p.get("bf16_tflops", p.get("bf16_tflops_sustained"))),
+                    "src": "measured (MEASURED_PEAKS.json: hbm_gbs, bf16_tflops_sustained; burst = bf16_tflops)"}
         except Exception:
             pass
-    return {"hbm_gbs": 6650.0, "tflops": 1400.0,
-            "src": "fallback (B200_PROFILING.md: 6.65 TB/s copy, 1.4 PFLOP/s sustained cuBLAS bf16)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "tflops_burst": 1650.0,
+            "src": "fallback (B200_PROFILING.md: 6.65 TB/s copy, 1.4 PFLOP/s sustained / 1.65 burst cuBLAS bf16)"}
+
+
+def event_ms(fn, steps, warmup=1):
+    """Median-free simple timing: `warmup` untimed calls, then `steps` calls between two CUDA events."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def make_classes(C, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    words = ["annual", "crop", "forest", "highway", "industrial", "pasture", "river", "lake", "residential",
+             "vegetation", "sea", "road", "land", "buildings"]
+    return [" ".join(words[int(torch.randint(0, len(words), (1,), generator=g))]
+                     for _ in range(int(torch.randint(1, 5, (1,), generator=g)))) + f" {j}"
+            for j in range(C)]
+
+
+# --------------------------------------------------------------------------------------------------
+# extras at N = 1: the other BASELINE configs, each with its own executed-FLOP roofline fraction
+# --------------------------------------------------------------------------------------------------
+def extras_single_gpu(a, model, dev, pk):
+    clip = importlib.import_module(PKG + ".clip")
+    models = importlib.import_module(PKG + ".models")
+    training = importlib.import_module(PKG + ".training")
+    Engine = importlib.import_module(PKG + ".engine").Engine
+    eng = model.engine
+    eng.ctx.set_sm_limit(0)
+    out = {}
+    gp = torch.Generator().manual_seed(2)
+    gi = torch.Generator().manual_seed(321)
+
+    def frac(tflops):
+        return {"tflops": tflops, "frac_of_sustained_peak": tflops / pk["tflops"],
+                "frac_of_burst_peak": tflops / pk["tflops_burst"]}
+
+    # ---- configs[2]: VPT, P = 16, C = 102 (Flowers102): forward with tape + prompt-only backward ----
+    P, C = 16, 102
+    B = Engine.wave_aligned_batch(1024, L=50 + P, sms=148)
+    classes = make_classes(C, seed=3)
+    cie = models.CustomImageEncoder(model.visual)
+    ipm = models.ImagePrefixModel(((768 ** -0.5) * torch.randn(P, 768, generator=gp)).to(dev), cie, device=dev)
+    with torch.no_grad():
+        tfix = model.encode_text(clip.tokenize([f"a photo of a {c}, a type of flower." for c in classes])).float()
+    vstep = training.VPTStep(ipm, tfix, lr=1e-4)
+    img = torch.randint(0, 256, (B, 3, 224, 224), generator=gi, dtype=torch.uint8).to(dev)
+    lab = torch.randint(0, C, (B,), generator=gi).to(dev)
+    l0 = eng.ctx.launches
+    ms = event_ms(lambda: vstep.step(img, lab), steps=5, warmup=2)
+    per_step = (eng.ctx.launches - l0) // 7
+    # forward (dense count, P = 16) + dgrad-only backward ≈ the block GEMMs and attention once more
+    f_fwd, f_exec = flop_vit(P), flop_vit_executed(P)
+    f_bwd = f_exec - 2 * 49 * 3072 * 768 - 2 * 768 * 512 + 12 * 4 * (50 + P) ** 2 * 768  # attention bwd = 2× its fwd
+    out["vpt_step"] = {"config": f"configs[2] shape: VPT P={P}, C={C}, batch {B}, uint8 pixels, SGD; image tower forward "
+                                 f"with tape + gb_ce_image_grad + prompt-only backward + gb_sgd_step (training.VPTStep)",
+                       "images_per_s": B / (ms * 1e-3), "ms_per_step": ms, "gpu_launches_per_step": per_step,
+                       "flop_per_image_executed": f_exec + f_bwd,
+                       "roofline_executed": frac(B * (f_exec + f_bwd) / (ms * 1e-3) / 1e12),
+                       "roofline_dense_fwd_x2": frac(B * 2 * f_fwd / (ms * 1e-3) / 1e12)}
+    del vstep, ipm, img, lab
+    torch.cuda.empty_cache()
+
+    # ---- configs[4]: UPT, 4 + 4 coupled prompts, C = 100 (FGVCAircraft): both towers with tape + backward ----
+    Pt = Pv = 4
+    C = 100
+    B = Engine.wave_aligned_batch(1024, L=50 + Pv, sms=148)
+    classes = make_classes(C, seed=5)
+    cte = models.CustomTextEncoder(model, dev, torch.float32)
+    torch.manual_seed(4)
+    upt = models.UPTModel((0.02 * torch.randn(1, Pt, 512, generator=gp)).to(dev),
+                          ((768 ** -0.5) * torch.randn(1, Pv, 768, generator=gp)).to(dev), None, cie, cte, classes, 128,
+                          device=dev, dtype=torch.float32)
+    opt = torch.optim.SGD(upt.parameters(), lr=1e-4)
+    ustep = training.UPTStep(upt, opt)
+    img = torch.randint(0, 256, (B, 3, 224, 224), generator=gi, dtype=torch.uint8).to(dev)
+    lab = torch.randint(0, C, (B,), generator=gi).to(dev)
+    l0 = eng.ctx.launches
+    ms = event_ms(lambda: ustep.step(img, lab), steps=5, warmup=2)
+    per_step = (eng.ctx.launches - l0) // 7
+    ids = cte._prompt_ids(Pt, classes)
+    Lt = int(ids.argmax(dim=-1).max().item()) + 1
+    fi = flop_vit_executed(Pv)
+    fi_b = fi - 2 * 49 * 3072 * 768 - 2 * 768 * 512 + 12 * 4 * (50 + Pv) ** 2 * 768
+    ft = flop_text(Lt)
+    ft_b = ft - 2 * 512 ** 2 + 12 * 4 * Lt ** 2 * 512
+    tot = B * (fi + fi_b) + C * (ft + ft_b)
+    out["upt_step"] = {"config": f"configs[4] shape: UPT {Pt}+{Pv} coupled prompts (128-wide 1-layer coupling transformer in "
+                                 f"torch), C={C}, batch {B}, uint8 pixels, SGD; both towers with tape + "
+                                 f"gb_ce_image_grad (both gradients) + two prompt-only backward passes "
+                                 f"(training.UPTStep); text positions after EOT skipped (Lt={Lt})",
+                       "images_per_s": B / (ms * 1e-3), "ms_per_step": ms, "gpu_launches_per_step": per_step,
+                       "flop_per_step_executed": tot, "roofline_executed": frac(tot / (ms * 1e-3) / 1e12)}
+    del ustep, upt, img, lab
+    torch.cuda.empty_cache()
+
+    # ---- the reference's own BATCH_SIZE: CoOp, B = 16, C = 10, P = 16 ----
+    P, C, B = 16, 10, 16
+    classes = make_classes(C, seed=1)
+    tpm = models.TextPrefixModel((0.02 * torch.randn(1, P, 512, generator=gp)).to(dev), cte, classes, device=dev)
+    fused = training.CoOpStep(tpm, lr=1e-4, graph=True)
+    img = torch.randint(0, 256, (B, 3, 224, 224), generator=gi, dtype=torch.uint8).to(dev)
+    img32 = clip.normalize_u8(img.cpu()).to(dev)
+    lab = torch.randint(0, C, (B,), generator=gi).to(dev)
+
+    def fused_step():
+        _, fn, _ = eng.vit_forward(img, None, want_feat=False, want_featn=True)
+        fused.step(fn, lab)
+
+    ms_fused = event_ms(fused_step, steps=50, warmup=5)
+    with torch.no_grad():
+        _, fn_cached, _ = eng.vit_forward(img, None, want_feat=False, want_featn=True)
+    ms_cached = event_ms(lambda: fused.step(fn_cached, lab), steps=50, warmup=5)
+    tpm2 = models.TextPrefixModel((0.02 * torch.randn(1, P, 512, generator=gp)).to(dev), cte, classes, device=dev)
+    opt2 = torch.optim.SGD([tpm2.prefix], lr=1e-4)
+    scale = eng.logit_scale_exp
+
+    def dropin_step():   # the reference's loop body, textual_prompt.py:93-135, on the drop-in classes
+        tf = tpm2(classes)
+        tf = tf / tf.norm(dim=-1, keepdim=True)
+        with torch.no_grad():
+            imf = model.encode_image(img32)
+            imf = imf / imf.norm(dim=-1, keepdim=True)
+        loss = torch.nn.functional.cross_entropy(scale * imf @ tf.t(), lab)
+        loss.backward()
+        opt2.step()
+        opt2.zero_grad()
+
+    ms_dropin = event_ms(dropin_step, steps=30, warmup=5)
+    ids = cte._prompt_ids(P, classes)
+    Lt = int(ids.argmax(dim=-1).max().item()) + 1
+    out["ref_batch16"] = {"config": f"CoOp step at the reference BATCH_SIZE: B={B}, C={C}, P={P} (launch-latency bound: "
+                                    f"M = {B * 50} image rows, {C * Lt} text rows)",
+                          "fused_ms": ms_fused, "fused_images_per_s": B / (ms_fused * 1e-3),
+                          "fused_cached_features_ms": ms_cached,
+                          "dropin_classes_ms": ms_dropin, "dropin_images_per_s": B / (ms_dropin * 1e-3),
+                          "note": "fused = gb_vit_forward + training.CoOpStep (one CUDA graph); cached = CoOpStep alone on "
+                                  "cached image features (SURVEY §8f N1); dropin = the reference's loop body on "
+                                  "models.TextPrefixModel / clip_model.encode_image with torch loss and optimiser"}
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# N > 1: the north_star's sharded pool path, with parity against one GPU (outside the timed region)
+# --------------------------------------------------------------------------------------------------
+def multi_gpu_parity(model, dev, rank, world):
+    import torch.distributed as dist
+
+    clip = importlib.import_module(PKG + ".clip")
+    engine_mod = importlib.import_module(PKG + ".engine")
+    gdist = importlib.import_module(PKG + ".dist")
+    eng = model.engine
+    eng.ctx.set_sm_limit(0)
+    N = 131072
+    cases = [(18, 16), (18, N // 18 // 10), (100, 16), (100, N // 100)]   # (C, k): RESICS45 unseen / FGVCAircraft; FPL k and GRIP k
+    results = []
+    g = torch.Generator(device=dev).manual_seed(5)      # the same pool on every rank
+    F = torch.nn.functional.normalize(torch.randn(N, 512, device=dev, generator=g), dim=1).half()
+    rank_all = torch.randperm(N, generator=torch.Generator().manual_seed(9)).to(torch.int32).to(dev)
+    bounds = gdist.shard_bounds(N, world)
+    F_local = F[bounds[rank]:bounds[rank + 1]].contiguous()
+    for C, k in cases:
+        classes = make_classes(C, seed=10 + C)
+        ids = clip.tokenize([f"a photo of a {c}." for c in classes])
+        mine = gdist.class_shards(C, world)[rank]
+        with torch.no_grad():
+            if len(mine):
+                _, local, _ = eng.text_forward(ids[mine.start:mine.stop], None, want_feat=False, want_featn=True)
+            else:
+                local = torch.empty(0, 512, device=dev, dtype=torch.float16)
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            protos = gdist.gather_prototypes(local, C)     # ONE all-gather of the [C,512] prototypes
+            torch.cuda.synchronize()
+            t_gather = time.perf_counter() - t0
+            # sharded scan: similarity on every rank at once, exact replay handed rank → rank
+            tm = {}
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            board = gdist.sharded_pool_scan(F_local, protos, 100.0, k, N, rank_all,
+                                            lambda st: engine_mod.Leaderboard(C, k, dev, state=st), mode=1, timings=tm)
+            torch.cuda.synchronize()
+            t_sharded = time.perf_counter() - t0
+            got = board.result()
+            # reference: the whole pool on ONE GPU (every rank computes it: results must agree everywhere)
+            one = engine_mod.Leaderboard(C, k, dev)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            one.scan(F, protos, 100.0, mode=1, idx0=0, rank=rank_all)
+            torch.cuda.synchronize()
+            t_single = time.perf_counter() - t0
+            want = one.result()
+            # … and the prototypes against the un-sharded text tower
+            _, full, _ = eng.text_forward(ids, None, want_feat=False, want_featn=True)
+        same = torch.tensor([int(got == want), int(torch.equal(full, protos))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        times = torch.tensor([t_sharded, tm.get("similarity_ms", 0.0), tm.get("replay_ms", 0.0)], device=dev)
+        tmax = times.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = times.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        results.append({"n": N, "c": C, "k": k, "identical": bool(same[0].item()),
+                        "prototypes_identical": bool(same[1].item()), "pseudolabels": len(got[0]),
+                        "allgather_bytes": int(-(-C // world) * world * 512 * 2), "allgather_ms": t_gather * 1e3,
+                        "sharded_scan_ms": float(tmax[0].item()) * 1e3,
+                        "similarity_ms_per_rank_max": float(tmax[1].item()),
+                        "replay_ms_per_rank_mean": float(tsum[2].item()) / world,
+                        "single_gpu_scan_ms": t_single * 1e3})
+    del F, F_local
+    return {"pool": f"N={N} unit fp16 features (seed 5), prompts through the text tower, mode 1 (arg-max of the logits, "
+                    f"assign_pseudo_labels)", "world": world, "cases": results,
+            "identical": all(r["identical"] and r["prototypes_identical"] for r in results),
+            "note": "wall-clock ms between barriers incl. launch + hand-off latency (max over ranks); similarity = "
+                    "phase 1 on every rank at once, replay = phase 2 in rank order (CUDA events)"}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -205,25 +473,16 @@ def run_b200(a, rank, local_rank, world):
     models = importlib.import_module(PKG + ".models")
     engine_mod = importlib.import_module(PKG + ".engine")
     gdist = importlib.import_module(PKG + ".dist")
+    training = importlib.import_module(PKG + ".training")
     synthetic = importlib.import_module(PKG + ".synthetic")
     if not torch.cuda.is_available():
         raise pkg.GripB200Error("bench.py needs a B200: there is no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL prints its version banner on stdout when the first communicator is built: keep stdout for
-        # the one JSON line (the banner goes to stderr)
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=dev)
-            dist.barrier()
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+        torch.cuda.synchronize()
 
     vpt = a.workload == "vpt"
     overlap = not a.no_overlap and not vpt   # the VPT step is one dependent chain: nothing to run beside it
@@ -231,16 +490,11 @@ def run_b200(a, rank, local_rank, world):
     model, _ = clip.load("ViT-B/32", dev, state_dict=synthetic.synthetic_state_dict(1234))
     eng = model.engine
     ctx = eng.ctx
-    g = torch.Generator().manual_seed(1)
-    words = ["annual", "crop", "forest", "highway", "industrial", "pasture", "river", "lake", "residential",
-             "vegetation", "sea", "road", "land", "buildings"]
-    classes = [" ".join(words[int(torch.randint(0, len(words), (1,), generator=g))]
-                        for _ in range(int(torch.randint(1, 5, (1,), generator=g)))) + f" {j}"
-               for j in range(C)]
+    classes = make_classes(C, seed=1)
     gp = torch.Generator().manual_seed(2)
     cte = models.CustomTextEncoder(model, dev, torch.float16)
     tpm = models.TextPrefixModel((0.02 * torch.randn(1, P, 512, generator=gp)).to(dev), cte, classes, device=dev)
-    opt = torch.optim.SGD([tpm.prefix], lr=1e-4)   # WARMUP_LR of textual_prompt_config.yml
+    coop = training.CoOpStep(tpm, lr=1e-4, world=world, graph=True)   # WARMUP_LR of textual_prompt_config.yml
     scale = eng.logit_scale_exp
     # device-resident arm, 3 roofline steps, e2e arm, e2e_f32 arm: every step scans its own slice of image indices
     total_steps = 3 * (a.warmup + a.steps) + 3
@@ -263,44 +517,40 @@ def run_b200(a, rank, local_rank, world):
         # per epoch from the frozen text tower, learnable rows in the IMAGE tower
         cie = models.CustomImageEncoder(model.visual)
         ipm = models.ImagePrefixModel(((768 ** -0.5) * torch.randn(P, 768, generator=gp)).to(dev), cie, device=dev)
-        opt = torch.optim.SGD([ipm.prefix], lr=1e-4)
         with torch.no_grad():
-            tfix = model.encode_text(clip.tokenize([f"a photo of a {c}" for c in classes]))
-            tfix = tfix / tfix.norm(dim=-1, keepdim=True)
-        protos_fix = tfix.half()
+            tfix = model.encode_text(clip.tokenize([f"a photo of a {c}" for c in classes])).float()
+            protos_fix = (tfix / tfix.norm(dim=-1, keepdim=True)).half()
+        vstep = training.VPTStep(ipm, tfix, lr=1e-4, world=world)
 
-    # Two streams: the frozen image tower runs back to back on the main stream; the text chain of the same
-    # step (text tower with the learnable prefix, loss, prompt-only backward, SGD, pseudolabel scan — ~230
-    # small, latency-bound launches) runs beside it on a side stream and joins on the image features.
-    # Nothing is reordered across a true dependency: prefix(i) → text(i) → loss(i) ← image(i).
+    # Two streams: the frozen image tower runs back to back on the main stream; the text chain of a step (text
+    # tower with the learnable prefix, loss, prompt-only backward, SGD — one CUDA graph at N = 1 — and the
+    # pseudolabel scan; ~230 small, latency-bound kernels) runs beside the NEXT batch's image tower on a side
+    # stream.  Nothing is reordered across a true dependency: prefix(i) → text(i) → loss(i) ← image(i).
     main_stream = torch.cuda.current_stream()
     side_stream = torch.cuda.Stream(device=dev)
     mode = {"overlap": overlap}
     if overlap and a.sm_limit > 0:
         ctx.set_sm_limit(a.sm_limit)
 
-    def step_vpt(img, labels):
-        s = state["step"]
-        vf = ipm(img)
-        vfn = vf / vf.norm(dim=-1, keepdim=True)
-        loss = torch.nn.functional.cross_entropy(scale * vfn @ tfix.t(), labels)
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        if world > 1:
-            gdist.allreduce_mean_(ipm.prefix.grad)
-        opt.step()
-        featn = vfn.detach().half()
+    def scan_step(featn, protos, s):
         idx0 = (s * world + rank) * B
 
         def scan(st):
             b = engine_mod.Leaderboard(C, k, dev, state=st)
-            state["pred"] = b.scan(featn, protos_fix, scale, mode=1, idx0=idx0, rank=rank_all)[0]
+            b.scan(featn, protos, scale, mode=1, idx0=idx0, rank=rank_all)
             return b.state
 
         if world > 1:
             state["board"].state = gdist.ordered_handoff(state["board"].state, scan, ring=True)
         else:
             scan(state["board"].state)
+
+    def step_vpt(img, labels):
+        s = state["step"]
+        loss, feat, pred = vstep.step(img, labels, want_pred=True)
+        featn, _ = ctx.l2norm512(feat)
+        state["pred"] = pred
+        scan_step(featn, protos_fix, s)
         state["step"] = s + 1
         return loss
 
@@ -311,38 +561,18 @@ def run_b200(a, rank, local_rank, world):
         overlap = mode["overlap"]
         side = side_stream if overlap else main_stream
         with torch.no_grad():
-            feat, featn, _ = eng.vit_forward(img, None, want_feat=True, want_featn=True)
+            _, featn, _ = eng.vit_forward(img, None, want_feat=False, want_featn=True)
         if overlap:
             ev = torch.cuda.Event()
             ev.record(main_stream)
-            feat.record_stream(side)
             featn.record_stream(side)
         with torch.cuda.stream(side):
-            tf = tpm(classes)
             if overlap:
                 side.wait_event(ev)
-            with torch.no_grad():
-                imfn = feat / feat.norm(dim=-1, keepdim=True)
-            tfn = tf / tf.norm(dim=-1, keepdim=True)
-            logits = scale * imfn @ tfn.t()
-            loss = torch.nn.functional.cross_entropy(logits, labels)
-            opt.zero_grad(set_to_none=True)
-            loss.backward()
-            if world > 1:
-                gdist.allreduce_mean_(tpm.prefix.grad)
-            opt.step()
-            protos = tfn.detach().half()
-            idx0 = (s * world + rank) * B
-
-            def scan(st):
-                b = engine_mod.Leaderboard(C, k, dev, state=st)
-                state["pred"] = b.scan(featn, protos, scale, mode=1, idx0=idx0, rank=rank_all)[0]
-                return b.state
-
-            if world > 1:
-                state["board"].state = gdist.ordered_handoff(state["board"].state, scan, ring=True)
-            else:
-                scan(state["board"].state)
+            loss, pred = coop.step(featn, labels, want_pred=True)
+            protos, _ = ctx.l2norm512(coop._text)   # unit fp16 prompts of THIS step's forward
+            state["pred"] = pred
+            scan_step(featn, protos, s)
         state["step"] = s + 1
         return loss
 
@@ -373,22 +603,37 @@ def run_b200(a, rank, local_rank, world):
     # ---- device-resident arm -------------------------------------------------------------------
     for i in range(a.warmup):
         step(dev_img[i % 2], dev_lab[i % 2])
+    join()
+    torch.cuda.synchronize()
+    graph_launches = 0
+    if not vpt and coop._graph is not None:
+        # a replayed CUDA graph launches its captured kernels without passing through the C ABI's counter
+        l0 = ctx.launches
+        coop._chain()
+        graph_launches = ctx.launches - l0
+        torch.cuda.synchronize()
     with Clocks(local_rank) as clk:
         ms, launches = timed(lambda i: step(dev_img[i % 2], dev_lab[i % 2]), a.steps)
+    launches += graph_launches * a.steps
     value = a.steps * B * world / (ms / 1e3)
 
     # ---- roofline: per-launch CUDA-event timing (on the launching stream) of every tcgen05 GEMM and sim
     # launch in 3 more steps of the same loop; the dominant kernel launch = the GEMM shape with the
     # largest total time
-    # (issued on ONE stream with the SM cap lifted, so a launch's event pair times that kernel alone)
+    # (issued on ONE stream with the SM cap lifted, so a launch's event pair times that kernel alone; the per-launch
+    # event pairs also break the programmatic-dependent-launch overlap between consecutive GEMMs, which is why the
+    # shares below can add up to slightly more than one step)
     join()
     mode["overlap"] = False
     ctx.set_sm_limit(0)
+    use_graph = coop.use_graph
+    coop.use_graph, coop._graph = False, None   # eager chain: every launch is visible to the profiler hooks
     ctx.profile_begin()
     for i in range(3):
         step(dev_img[i % 2], dev_lab[i % 2])
     launches_rec = ctx.profile_launches()
     (g_n, g_ms, g_flop), (s_n, s_ms, s_bytes) = ctx.profile_end()
+    coop.use_graph = use_graph
     mode["overlap"] = overlap
     if overlap and a.sm_limit > 0:
         ctx.set_sm_limit(a.sm_limit)
@@ -405,17 +650,28 @@ def run_b200(a, rank, local_rank, world):
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(f"gemm_{dm}x{dn}x{dk}")
+    step_s = ms / a.steps * 1e-3
+    fP = P if vpt else 0
     roofline = {"bound": "tensor", "kernel": f"gemm_f16_tcgen05_2cta_kernel M={dm} N={dn} K={dk}",
                 "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
+                "frac_of_burst_peak": achieved / pk["tflops_burst"], "peak_burst": pk["tflops_burst"],
                 "traffic": traffic, "peak_source": pk["src"],
                 "flop_per_launch": 2.0 * dm * dn * dk, "avg_launch_ms": d_ms / d_cnt, "launches_timed": d_cnt,
                 "share_of_step": d_ms / 3 / (ms / a.steps),
+                "per_shape": {f"{m_}x{n_}x{k_}": {"launches": v[0], "tflops": v[2] / (v[1] * 1e-3) / 1e12,
+                                                  "frac": v[2] / (v[1] * 1e-3) / 1e12 / pk["tflops"],
+                                                  "share_of_step": v[1] / 3 / (ms / a.steps)}
+                              for (m_, n_, k_), v in sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:6]},
                 "all_gemm_launches": {"achieved": all_gemm, "frac": all_gemm / pk["tflops"], "launches": g_n,
-                                      "share_of_step": g_ms / 3 / (ms / a.steps)},
-                "step_vit_fwd_frac_of_peak": B * FLOP_VIT_P0 / (ms / a.steps * 1e-3) / 1e12 / pk["tflops"],
-                "step_vit_fwd_flop_note": "dense reference count, 8.818 GFLOP per image (SURVEY §8d), over the whole "
-                                          "step time; the frozen tower evaluates the last block past its attention on "
-                                          "the CLS rows only (bit-identical features), 5.6 % fewer FLOPs actually run"}
+                                      "share_of_step": g_ms / 3 / (ms / a.steps),
+                                      "note": "per-launch event pairs serialise the launches (no PDL overlap): the shares "
+                                              "of a profiled step can add up to more than the un-profiled step time"},
+                "step_vit_fwd_frac_of_peak": B * flop_vit(fP) / step_s / 1e12 / pk["tflops"],
+                "step_vit_fwd_frac_of_peak_executed": B * flop_vit_executed(fP) / step_s / 1e12 / pk["tflops"],
+                "step_vit_fwd_frac_of_burst_peak_executed": B * flop_vit_executed(fP) / step_s / 1e12 / pk["tflops_burst"],
+                "step_vit_fwd_flop_note": "dense = the reference count, 8.818 GFLOP per image (SURVEY §8d), over the whole "
+                                          "step time; executed = minus the 5.9 % the CLS-only last block skips "
+                                          "(bit-identical features); both count the image tower's forward only"}
 
     # pool-scale sim kernel (HBM bound): N = 2^20 rows against C=100 prototypes, timed alone
     roofline_sim = None
@@ -449,8 +705,10 @@ def run_b200(a, rank, local_rank, world):
                         "traffic": (json.load(open(tpath)).get("sim_1048576x100") if os.path.exists(tpath) else None),
                         "launches_timed": n1, "images_per_s": Np * n1 / (ms1 * 1e-3),
                         "full_scan_k16": {"ms": scan_ms, "images_per_s": Np / (scan_ms * 1e-3),
+                                          "hbm_frac": Np * 1032.0 / (scan_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                                           "note": "gb_pseudolabel_scan: every chunk's similarity kernel + "
-                                                  "pre-filter + exact sequential leaderboard replay"}}
+                                                  "pre-filter + exact leaderboard replay (boards replayed in "
+                                                  "parallel by their owner warps)"}}
         del F, T, rk
 
     # ---- end-to-end arm: pinned host → device every step, loss + predictions read back ---------
@@ -509,7 +767,7 @@ def run_b200(a, rank, local_rank, world):
     h2d = B * 3 * 224 * 224 + B * 8
     d2h = 4 + B * 4
     # the same with the fp32 tensors the reference's DataLoader yields (4x the bytes over PCIe)
-    host_f32 = [importlib.import_module(PKG + ".clip").normalize_u8(h).pin_memory() for h in host]
+    host_f32 = [clip.normalize_u8(h).pin_memory() for h in host]
     dev_f32 = [torch.empty(B, 3, 224, 224, device=dev) for _ in range(2)]
     ms_e2e_f32 = run_e2e(host_f32, dev_f32)
     e2e_f32 = {"value": a.steps * B * world / (ms_e2e_f32 / 1e3), "unit": "images/s",
@@ -517,41 +775,38 @@ def run_b200(a, rank, local_rank, world):
                "d2h_bytes_per_step": d2h,
                "note": "host-normalised fp32 tensors (the reference DataLoader's output) instead of uint8 pixels"}
     del host_f32, dev_f32
+    host.clear(); dev_img.clear()
+    join()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+
+    extras = {}
+    if not a.no_extras:
+        if world == 1:
+            extras = extras_single_gpu(a, model, dev, pk)
+        else:
+            extras = {"multi_gpu_parity": multi_gpu_parity(model, dev, rank, world)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f16 (fp32 accumulate)",
-                "data": "synthetic",
-                "config": {"workload": workload_name(a, B), "weights": "random-init ViT-B/32 (seed 1234)",
-                           "l2_policy": f"inputs larger than L2 ({B * 150528 / 1e6:.0f} MB uint8 image batch per step + 0.3 GB "
-                                        f"of weights, GBs of activations)",
-                           "input": "uint8 pixels, ToTensor + Normalize fused into the patch gather on the device "
-                                    "(bit-identical to host-normalised fp32 input)",
-                           "batch_per_gpu": f"{B} (largest ≤ {1024 if vpt else 2048} that fills whole GEMM waves on the "
-                                            f"{(a.sm_limit if overlap and a.sm_limit > 0 else 148) // 2} CTA pairs in use)",
-                           "parallelism": f"dp{world}: image batch and pool sharded, prefix-grad all-reduce, "
-                                          f"ordered leaderboard hand-off" if world > 1 else "single GPU",
-                           "streams": (f"image tower on the main stream (GEMM grids capped at {a.sm_limit} SMs), text "
-                                       f"chain + pseudolabel scan of the same step on a side stream") if overlap
-                                      else "single stream",
-                           "text_positions": "positions after EOT skipped (exact under the causal mask)"},
+                "data": "synthetic", "config": config_dict(a, B, world),
                 "clocks": clk.summary(), "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / a.steps,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "e2e_f32": e2e_f32,
                 "roofline": roofline, "roofline_sim": roofline_sim}
+        line.update(extras)
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_arm(a, 1000, 1, budget_s=15.0)[0]
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
-    # NCCL's banner ("NCCL version …", printed on stdout at NCCL_DEBUG=VERSION) would precede the one JSON line
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
     a = parse()
     if a.batch <= 0:  # both arms name the same workload
         vpt = a.workload == "vpt"
@@ -562,7 +817,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if a.impl == "reference":
-        run_reference(a, rank)
+        run_reference(a, rank, world)
         return
     if world != a.gpus:
         if a.gpus == 1 and world == 1:

@@ -225,6 +225,13 @@ uint64_t gb_workspace_generation(gb_ctx* ctx);
 int gb_ce_text_grad(gb_ctx* ctx, const void* imfn16, const float* text, const int32_t* labels,
                     const float* coef, float logit_scale_exp, int B, int C, float* dtext, float* loss,
                     int32_t* pred, void* stream);
+/* The same loss with the image side trainable (VPT / UPT: methods/semi_supervised_learning/visual_prompt.py:122-135,
+ * multimodal_prompt.py:103-121): image fp32 [B,512] and text fp32 [C,512] both UN-normalised; returns
+ * dimage fp32 [B,512] = d loss / d image and / or dtext fp32 [C,512] = d loss / d text (either may be NULL, not
+ * both), each through its side's normalisation.  Deterministic. */
+int gb_ce_image_grad(gb_ctx* ctx, const float* image, const float* text, const int32_t* labels,
+                     const float* coef, float logit_scale_exp, int B, int C, float* dimage, float* dtext,
+                     float* loss, int32_t* pred, void* stream);
 /* torch.optim.SGD step (dampening 0, no Nesterov): g += wd·p; buf = first ? g : mu·buf + g; p -= lr·(mu ? buf : g).
  * lr_dev != NULL: the learning rate is read from that device scalar instead of `lr` (a captured CUDA graph
  * of the step then keeps following the schedule). */

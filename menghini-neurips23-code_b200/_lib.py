@@ -83,6 +83,7 @@ _SIGNATURES = {
                                     P, P, P]),
     "gb_workspace_generation": (c_uint64, [P]),
     "gb_ce_text_grad": (c_int, [P, P, P, P, P, c_float, c_int, c_int, P, P, P, P]),
+    "gb_ce_image_grad": (c_int, [P, P, P, P, P, c_float, c_int, c_int, P, P, P, P, P]),
     "gb_sgd_step": (c_int, [P, P, P, P, ctypes.c_longlong, c_float, P, c_float, c_float, c_int, P]),
     "gb_warmup_cosine_lr": (ctypes.c_double, [ctypes.c_double, c_int, c_int, c_int]),
 }
@@ -119,10 +120,12 @@ def ptr(t):
     return None if t is None else c_void_p(t.data_ptr())
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """The current torch stream of `device` (an Engine / Leaderboard passes its own device: the caller's
+    current device may be another GPU)."""
     import torch
 
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 class Context:
@@ -190,7 +193,7 @@ class Context:
         rc = self.lib.gb_gemm_f16(
             self.h, ptr(A), A.stride(0), ptr(W), W.stride(0), ptr(bias), ptr(resid),
             0 if resid is None else resid.stride(0), ptr(out), out.stride(0), M, N, K, int(act),
-            int(bool(out_f32)), stream_ptr())
+            int(bool(out_f32)), stream_ptr(self.device))
         self.check(rc, "gb_gemm_f16")
         return out
 
@@ -202,7 +205,7 @@ class Context:
         y = torch.empty(rows, D, device=x.device, dtype=torch.float32 if out_f32 else torch.float16)
         rc = self.lib.gb_layernorm_f16(self.h, ptr(x), x.stride(0), ptr(row_idx), in_row_mul,
                                        ptr(gamma), ptr(beta), ptr(y), D, rows, D, int(out_f32),
-                                       stream_ptr())
+                                       stream_ptr(self.device))
         self.check(rc, "gb_layernorm_f16")
         return y
 
@@ -212,7 +215,7 @@ class Context:
         rows = x.shape[0]
         y16 = torch.empty(rows, 512, device=x.device, dtype=torch.float16) if want16 else None
         y32 = torch.empty(rows, 512, device=x.device, dtype=torch.float32) if want32 else None
-        self.check(self.lib.gb_l2norm512(self.h, ptr(x), ptr(y16), ptr(y32), rows, stream_ptr()),
+        self.check(self.lib.gb_l2norm512(self.h, ptr(x), ptr(y16), ptr(y32), rows, stream_ptr(self.device)),
                    "gb_l2norm512")
         return y16, y32
 
@@ -221,7 +224,7 @@ class Context:
 
         out = torch.empty(B * L, D, device=qkv.device, dtype=torch.float16)
         self.check(self.lib.gb_attention_fwd(self.h, ptr(qkv), ptr(out), B, L, D, int(causal),
-                                             stream_ptr()), "gb_attention_fwd")
+                                             stream_ptr(self.device)), "gb_attention_fwd")
         return out
 
     def attention_bwd(self, qkv, dout, B, L, D, causal):
@@ -229,5 +232,5 @@ class Context:
 
         dqkv = torch.empty_like(qkv)
         self.check(self.lib.gb_attention_bwd(self.h, ptr(qkv), ptr(dout), ptr(dqkv), B, L, D,
-                                             int(causal), stream_ptr()), "gb_attention_bwd")
+                                             int(causal), stream_ptr(self.device)), "gb_attention_bwd")
         return dqkv

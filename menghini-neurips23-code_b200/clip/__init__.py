@@ -27,6 +27,7 @@ from ..synthetic import synthetic_state_dict
 
 SOT, EOT = 49406, 49407
 _warned = False
+_real_weights = False  # set by load() when the weights came from a file of trained parameters
 
 
 def available_models():
@@ -44,11 +45,16 @@ def _preprocess(raw: bool = False):
     std = torch.tensor((0.26862954, 0.26130258, 0.27577711)).view(3, 1, 1)
 
     def transform(img):
+        # torchvision Resize(224): the short side becomes exactly 224, the long side int(224·long/short)
+        # (truncation); CenterCrop(224): origin int(round((dim − 224) / 2.0)) (Python's round)
         w, h = img.size
-        s = 224 / min(w, h)
-        img = img.resize((max(224, round(w * s)), max(224, round(h * s))), Image.BICUBIC)
-        w, h = img.size
-        l, t = (w - 224) // 2, (h - 224) // 2
+        if w <= h:
+            nw, nh = 224, int(224 * h / w)
+        else:
+            nw, nh = int(224 * w / h), 224
+        if (nw, nh) != (w, h):
+            img = img.resize((nw, nh), Image.BICUBIC)
+        l, t = int(round((nw - 224) / 2.0)), int(round((nh - 224) / 2.0))
         img = img.crop((l, t, l + 224, t + 224)).convert("RGB")
         x = torch.from_numpy(np.asarray(img, dtype=np.uint8).copy()).permute(2, 0, 1)
         if raw:
@@ -81,7 +87,9 @@ def load(name="ViT-B/32", device="cuda", jit=False, state_dict=None, download_ro
         path = os.environ.get("GRIPB200_CLIP_WEIGHTS")
         seed = os.environ.get("GRIPB200_SYNTHETIC_SEED")
         if path:
+            global _real_weights
             state_dict = torch.load(path, map_location="cpu")
+            _real_weights = True
         elif seed is not None:
             state_dict = synthetic_state_dict(int(seed))
         else:
@@ -108,6 +116,12 @@ def tokenize(texts, context_length: int = 77, truncate: bool = False):
     vocab = os.environ.get("GRIPB200_BPE_VOCAB")
     if vocab:
         return _tokenize_bpe(texts, context_length, truncate, vocab)
+    if _real_weights and os.environ.get("GRIPB200_ALLOW_HASH_TOKENIZER") != "1":
+        # hash ids bear no relation to a trained token embedding: everything would run and mean nothing
+        raise GripB200Error(
+            "clip.tokenize: real CLIP weights were loaded (GRIPB200_CLIP_WEIGHTS) but no BPE vocabulary is "
+            "configured; set GRIPB200_BPE_VOCAB to bpe_simple_vocab_16e6.txt.gz (or GRIPB200_ALLOW_HASH_TOKENIZER=1 "
+            "to opt into the word-hash tokenizer)")
     if not _warned:
         warnings.warn("clip.tokenize: BPE vocabulary unavailable offline, using the word-hash tokenizer")
         _warned = True

@@ -116,23 +116,28 @@ class CLIP(nn.Module):
             self._engine = _engine.Engine(self.state_dict(), dev)
         return self._engine
 
+    # The engine produces fp32 features (fp16 storage / fp32 accumulation inside the towers).  The reference's
+    # CUDA model returns them in the model dtype, fp16 (clip.load's convention); a caller that needs that
+    # rounding — e.g. to mix them with fp16 tensors of its own — sets `clip_model.feature_dtype = torch.float16`
+    # (or GRIPB200_FEATURE_DTYPE=fp16 before clip.load); the default keeps the extra precision.
+    feature_dtype = torch.float32
+
     def _feat_dtype(self, t):
-        # the reference returns features in the model dtype (fp16 on CUDA); the engine produces fp32
-        return t
+        return t if t.dtype == self.feature_dtype else t.to(self.feature_dtype)
 
     def _encode_image(self, image, prefix=None):
         image = image.to(self.visual.conv1.weight.device)
         if prefix is None:
-            return self.engine.vit_forward(image, None)[0]
-        return _engine.vit_with_prefix(self.engine, image, prefix)
+            return self._feat_dtype(self.engine.vit_forward(image, None)[0])
+        return self._feat_dtype(_engine.vit_with_prefix(self.engine, image, prefix))
 
     def encode_image(self, image):
         return self._encode_image(image, None)
 
     def encode_text(self, text, prefix=None):
         if prefix is None:
-            return self.engine.text_forward(text, None)[0]
-        return _engine.text_with_prefix(self.engine, text, prefix)
+            return self._feat_dtype(self.engine.text_forward(text, None)[0])
+        return self._feat_dtype(_engine.text_with_prefix(self.engine, text, prefix))
 
     def forward(self, image, text):
         eng = self.engine
@@ -175,4 +180,7 @@ def build_model(state_dict, device="cuda:0"):
     model = model.to(device).eval()
     for p in model.parameters():
         p.requires_grad_(False)
+    import os
+    if os.environ.get("GRIPB200_FEATURE_DTYPE", "").lower() in ("fp16", "float16", "half"):
+        model.feature_dtype = torch.float16
     return model

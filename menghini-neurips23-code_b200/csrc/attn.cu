@@ -473,6 +473,7 @@ int gb_launch_attn_bwd(gb_ctx* c, const void* qkv, const void* dout, void* dqkv,
 extern "C" int gb_attention_fwd(gb_ctx* c, const void* qkv, void* out, int B, int L, int D,
                                 int causal, void* stream) {
   if (!c) return GB_ERR_ARG;
+  gb_dev_guard dev_guard(c);
   if (!qkv || !out) return gb_fail(c, GB_ERR_ARG, "attention: null pointer");
   return gb_launch_attn_fwd(c, qkv, out, B, L, D, causal, (cudaStream_t)stream);
 }
@@ -480,6 +481,7 @@ extern "C" int gb_attention_fwd(gb_ctx* c, const void* qkv, void* out, int B, in
 extern "C" int gb_attention_bwd(gb_ctx* c, const void* qkv, const void* dout, void* dqkv, int B,
                                 int L, int D, int causal, void* stream) {
   if (!c) return GB_ERR_ARG;
+  gb_dev_guard dev_guard(c);
   if (!qkv || !dout || !dqkv) return gb_fail(c, GB_ERR_ARG, "attention: null pointer");
   return gb_launch_attn_bwd(c, qkv, dout, dqkv, B, L, D, causal, (cudaStream_t)stream);
 }

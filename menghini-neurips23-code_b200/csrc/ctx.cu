@@ -14,10 +14,10 @@ extern "C" int gb_create(gb_ctx** out, int device) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return GB_ERR_CUDA;
   if (prop.major != 10) return GB_ERR_NO_DEVICE;  // tcgen05 kernels are sm_100a-only
-  if (cudaSetDevice(device) != cudaSuccess) return GB_ERR_CUDA;
-  cudaFree(0);
   gb_ctx* c = new gb_ctx();
   c->device = device;
+  gb_dev_guard dev_guard(c);  // the caller's current device is restored on return
+  cudaFree(0);
   c->num_sms = prop.multiProcessorCount;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
@@ -36,6 +36,7 @@ void gb_tower_free(gb_tower* t);
 
 extern "C" int gb_destroy(gb_ctx* c) {
   if (!c) return GB_ERR_ARG;
+  gb_dev_guard dev_guard(c);
   cudaSetDevice(c->device);
   for (int i = 0; i < gb_ctx::kWsCount; ++i)
     if (c->ws[i]) cudaFree(c->ws[i]);
@@ -90,6 +91,7 @@ int gb_make_tmap_2d_f16(gb_ctx* c, CUtensorMap* out, const void* ptr, uint64_t r
 
 extern "C" int gb_profile_begin(gb_ctx* c) {
   if (!c) return GB_ERR_ARG;
+  gb_dev_guard dev_guard(c);
   for (auto& r : c->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   c->prof.clear();
   c->prof_on = true;
@@ -98,6 +100,7 @@ extern "C" int gb_profile_begin(gb_ctx* c) {
 
 extern "C" int gb_profile_launches(gb_ctx* c, gb_profile_launch* out, int cap) {
   if (!c || (cap > 0 && !out)) return GB_ERR_ARG;
+  gb_dev_guard dev_guard(c);
   if (cudaDeviceSynchronize() != cudaSuccess) return GB_ERR_CUDA;
   int n = 0;
   for (auto& r : c->prof) {
@@ -114,6 +117,7 @@ extern "C" int gb_profile_launches(gb_ctx* c, gb_profile_launch* out, int cap) {
 
 extern "C" int gb_profile_end(gb_ctx* c, gb_profile_stats* out, int kinds) {
   if (!c || !out || kinds <= 0) return GB_ERR_ARG;
+  gb_dev_guard dev_guard(c);
   c->prof_on = false;
   GB_CUDA(c, cudaDeviceSynchronize());
   for (int k = 0; k < kinds; ++k) { out[k].launches = 0; out[k].ms = 0; out[k].work = 0; }

@@ -56,6 +56,19 @@ struct gb_prof_scope {
   ~gb_prof_scope() { if (on) cudaEventRecord(c->prof.back().e1, st); }
 };
 
+// Every C-ABI entry point runs on its ctx's device whatever the caller's current device is, and leaves the
+// caller's current device as it found it (one ctx per (process, device); several may be alive).
+struct gb_dev_guard {
+  int prev = -1, dev;
+  explicit gb_dev_guard(const gb_ctx* c) : dev(c->device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~gb_dev_guard() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+};
+
 inline int gb_fail(gb_ctx* c, int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;

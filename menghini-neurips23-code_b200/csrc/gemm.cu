@@ -183,6 +183,7 @@ extern "C" int gb_gemm_f16(gb_ctx* c, const void* A, int lda, const void* W, int
                            const float* bias, const void* resid, int ldr, void* out, int ldo, int M,
                            int N, int K, int act, int out_f32, void* stream) {
   if (!c) return GB_ERR_ARG;
+  gb_dev_guard dev_guard(c);
   if (act < 0 || act > 1) return gb_fail(c, GB_ERR_ARG, "gemm: act must be 0 or 1");
   return gb_launch_gemm(c, A, lda, W, ldw, bias, resid, ldr, out, ldo, M, N, K, act, out_f32,
                         reinterpret_cast<cudaStream_t>(stream), nullptr);

@@ -622,6 +622,7 @@ extern "C" int gb_layernorm_f16(gb_ctx* c, const void* x, int ldx, const int32_t
                                 int in_row_mul, const float* gamma, const float* beta, void* y,
                                 int ldy, int rows, int D, int out_f32, void* stream) {
   if (!c) return GB_ERR_ARG;
+  gb_dev_guard dev_guard(c);
   if (!x || !gamma || !beta || !y) return gb_fail(c, GB_ERR_ARG, "layernorm: null pointer");
   return gb_launch_layernorm(c, x, ldx, row_idx, in_row_mul, gamma, beta, y, ldy, rows, D, out_f32,
                              (cudaStream_t)stream);
@@ -630,6 +631,7 @@ extern "C" int gb_layernorm_f16(gb_ctx* c, const void* x, int ldx, const int32_t
 extern "C" int gb_l2norm512(gb_ctx* c, const float* x, void* y16, float* y32, int rows,
                             void* stream) {
   if (!c) return GB_ERR_ARG;
+  gb_dev_guard dev_guard(c);
   if (!x || (!y16 && !y32)) return gb_fail(c, GB_ERR_ARG, "l2norm: null pointer");
   return gb_launch_l2norm512(c, x, y16, y32, rows, (cudaStream_t)stream);
 }

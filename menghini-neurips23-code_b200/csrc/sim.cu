@@ -15,6 +15,8 @@
 // soft-max / arg-max / filter need no cross-thread reduction at all.  Algorithmic HBM traffic:
 // 1024 B (fp16 row) + 8 B (pred, p_pred) per image; full prob rows are written only on request or for
 // rows that can still change a leaderboard.
+#include <stdlib.h>
+
 #include "ctx.h"
 #include "common.cuh"
 
@@ -422,6 +424,13 @@ __global__ void __launch_bounds__(kLbThreads, 1) lb_replay_kernel(const LbReplay
   float* s_last = reinterpret_cast<float*>(ring_n + 2);                     // [C]
   int32_t* s_cnt = reinterpret_cast<int32_t*>(s_last + C);                  // [C]
 
+  {  // a state written for another (C, k) must not be interpreted with this one's offsets
+    int32_t* hdr = reinterpret_cast<int32_t*>(p.state);
+    if (hdr[0] != C || hdr[1] != k) {
+      if (threadIdx.x == 0) hdr[2] = 1;  // sticky error flag, reported by gb_leaderboard_export
+      return;
+    }
+  }
   const LbView g = lb_view(p.state, C, k);  // the state in global memory
   // Boards small enough (C·k ≤ kLbSmemEntries) live in shared memory for the duration of the launch:
   // an admission then costs a few hundred cycles instead of several global-memory round trips.
@@ -641,10 +650,18 @@ __device__ void lb_admit(const LbView& v, int j, float pj, int idx, const int32_
   __syncwarp();
 }
 
+#include "lb_replay_par.cuh"
+
 __global__ void lb_export_kernel(void* base, int C, int k, int32_t* out_idx, int32_t* out_len,
                                  float* out_p) {
   const LbView v = lb_view(base, C, k);
+  const int32_t* hdr = reinterpret_cast<const int32_t*>(base);
+  const bool bad = hdr[0] != C || hdr[1] != k || hdr[2] != 0;  // foreign (C, k) or a replay refused it
   for (int j = blockIdx.x; j < C; j += gridDim.x) {
+    if (bad) {
+      if (threadIdx.x == 0) out_len[j] = -1;
+      continue;
+    }
     const int c = v.cnt[j];
     if (threadIdx.x == 0) out_len[j] = c;
     for (int e = threadIdx.x; e < k; e += blockDim.x) {
@@ -700,6 +717,12 @@ size_t lb_replay_smem_bytes(int C, int k) {
   size_t b = (size_t)2 * kLbBatch * C * 4 + (size_t)(4 * kLbBatch + 2) * 4 + (size_t)2 * C * 4 + 16;
   if ((size_t)C * k <= kLbSmemEntries) b += (size_t)C * k * 8 + (size_t)C * 4 + ((size_t)k + 1) * 12 + 16;
   return b;
+}
+
+// GB_LB_SERIAL=1 forces the single-warp replay (A/B measurements; the tests exercise both)
+bool lb_parallel_enabled() {
+  const char* e = getenv("GB_LB_SERIAL");
+  return !(e && e[0] == '1');
 }
 
 struct SimChunk {  // class-chunk phase of a launch (see SimParams)
@@ -805,6 +828,22 @@ int launch_replay(gb_ctx* c, void* state, int C, int k, const float* rows, int r
                   const int32_t* pred, const int32_t* rank, const uint32_t* flags, int row_begin,
                   int row_end, int idx0, cudaStream_t st) {
   if (row_end <= row_begin) return GB_OK;
+  if (C <= kLbpMaxC && k <= kLbpMaxK && (size_t)C * k <= kLbSmemEntries && lb_parallel_enabled()) {
+    static bool par_attr_set[16] = {false};
+    if (!par_attr_set[c->device & 15]) {
+      GB_CUDA(c, cudaFuncSetAttribute(lb_replay_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)lb_replay_par_smem_bytes(kLbpMaxC, kLbpMaxK)));
+      par_attr_set[c->device & 15] = true;
+    }
+    LbReplayParams q;
+    q.state = state; q.C = C; q.k = k;
+    q.rows = rows; q.rows_row0 = rows_row0;
+    q.pred = pred; q.rank = rank; q.flags = flags;
+    q.row_begin = row_begin; q.row_end = row_end; q.idx0 = idx0;
+    lb_replay_par_kernel<<<1, kLbpThreads, lb_replay_par_smem_bytes(C, k), st>>>(q);
+    GB_LAUNCH_CHECK(c);
+    return GB_OK;
+  }
   const size_t smem = lb_replay_smem_bytes(C, k);
   static bool attr_set[16] = {false};
   if (!attr_set[c->device & 15]) {
@@ -829,6 +868,7 @@ extern "C" int gb_sim_softmax_argmax(gb_ctx* c, const void* F, const void* T, fl
                                      int C, int mode, int32_t* pred, float* p_pred, float* probs,
                                      void* stream) {
   if (!c) return GB_ERR_ARG;
+  gb_dev_guard dev_guard(c);
   if (N <= 0) return GB_OK;
   if (!F || !T || !pred || !p_pred) return gb_fail(c, GB_ERR_ARG, "sim: null pointer");
   if (C > 128) {
@@ -849,6 +889,7 @@ extern "C" size_t gb_leaderboard_state_bytes(int C, int k) {
 
 extern "C" int gb_leaderboard_init(gb_ctx* c, void* state, int C, int k, void* stream) {
   if (!c) return GB_ERR_ARG;
+  gb_dev_guard dev_guard(c);
   if (!state || C <= 0 || C > kLbMaxC || k <= 0)
     return gb_fail(c, GB_ERR_ARG, "leaderboard_init: bad arguments (C=%d in 1..512, k=%d > 0)", C, k);
   lb_init_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(state, C, k);
@@ -861,6 +902,7 @@ extern "C" int gb_leaderboard_update(gb_ctx* c, void* state, int C, int k, const
                                      const int32_t* pred, const int32_t* rank, int row_begin,
                                      int row_end, int idx0, int prefilter, void* stream) {
   if (!c) return GB_ERR_ARG;
+  gb_dev_guard dev_guard(c);
   if (!state || !probs || !pred || C <= 0 || C > kLbMaxC || k <= 0 || row_begin < 0)
     return gb_fail(c, GB_ERR_ARG, "leaderboard_update: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
@@ -888,6 +930,7 @@ extern "C" int gb_leaderboard_update(gb_ctx* c, void* state, int C, int k, const
 extern "C" int gb_leaderboard_export(gb_ctx* c, const void* state, int C, int k, int32_t* out_idx,
                                      int32_t* out_len, float* out_p, void* stream) {
   if (!c) return GB_ERR_ARG;
+  gb_dev_guard dev_guard(c);
   if (!state || !out_idx || !out_len) return gb_fail(c, GB_ERR_ARG, "leaderboard_export: null pointer");
   lb_export_kernel<<<C < 64 ? C : 64, 128, 0, (cudaStream_t)stream>>>(const_cast<void*>(state), C, k,
                                                                      out_idx, out_len, out_p);
@@ -904,6 +947,7 @@ extern "C" int gb_pseudolabel_scan(gb_ctx* c, void* state, const void* F, const 
                                    const int32_t* rank, int32_t* pred, float* p_pred, float* probs,
                                    void* stream) {
   if (!c) return GB_ERR_ARG;
+  gb_dev_guard dev_guard(c);
   if (N <= 0) return GB_OK;
   if (!state || !F || !T || !pred || !p_pred || k <= 0)
     return gb_fail(c, GB_ERR_ARG, "pseudolabel_scan: bad arguments");

@@ -217,6 +217,7 @@ extern "C" size_t gb_tape_bytes(int samples, int L, int D, int layers) {
 
 extern "C" int gb_vit_set_weights(gb_ctx* c, const gb_vit_weights* w) {
   if (!c) return GB_ERR_ARG;
+  gb_dev_guard dev_guard(c);
   if (!w || w->width != 768 || w->out_dim != 512 || w->heads * 64 != w->width)
     return gb_fail(c, GB_ERR_ARG, "vit_set_weights: only ViT-B/32 geometry (width 768, 12 heads, out 512)");
   if (!w->conv_w || !w->cls || !w->pos || !w->ln_pre_g || !w->ln_pre_b || !w->ln_post_g ||
@@ -235,6 +236,7 @@ extern "C" int gb_vit_set_weights(gb_ctx* c, const gb_vit_weights* w) {
 
 extern "C" int gb_text_set_weights(gb_ctx* c, const gb_text_weights* w) {
   if (!c) return GB_ERR_ARG;
+  gb_dev_guard dev_guard(c);
   if (!w || w->width != 512 || w->out_dim != 512 || w->heads * 64 != w->width || w->ctx_len > 96)
     return gb_fail(c, GB_ERR_ARG, "text_set_weights: only the ViT-B/32 text geometry (width 512, 8 heads, out 512)");
   if (!w->tok_emb || !w->pos || !w->ln_final_g || !w->ln_final_b || !w->proj_t)
@@ -253,6 +255,7 @@ extern "C" int gb_text_set_weights(gb_ctx* c, const gb_text_weights* w) {
 extern "C" int gb_vit_forward(gb_ctx* c, const void* img, int img_f32, const float* prefix, int B,
                               int P, float* feat, void* featn, void* tape_mem, void* stream) {
   if (!c) return GB_ERR_ARG;
+  gb_dev_guard dev_guard(c);
   gb_tower* t = c->vit;
   if (!t) return gb_fail(c, GB_ERR_STATE, "vit_forward: weights not set");
   if (B <= 0) return GB_OK;
@@ -309,6 +312,7 @@ extern "C" int gb_vit_forward(gb_ctx* c, const void* img, int img_f32, const flo
 extern "C" int gb_vit_backward_prefix(gb_ctx* c, const float* dfeat, const float* prefix, int B,
                                       int P, const void* tape_mem, float* dprefix, void* stream) {
   if (!c) return GB_ERR_ARG;
+  gb_dev_guard dev_guard(c);
   gb_tower* t = c->vit;
   if (!t) return gb_fail(c, GB_ERR_STATE, "vit_backward_prefix: weights not set");
   if (!dfeat || !prefix || !tape_mem || !dprefix || B <= 0 || P <= 0 || P > 46)
@@ -348,6 +352,7 @@ extern "C" int gb_text_forward(gb_ctx* c, const int32_t* ids, int ld_ids, const 
                                const float* prefix, int C, int P, int Lt, float* feat, void* featn,
                                void* tape_mem, void* stream) {
   if (!c) return GB_ERR_ARG;
+  gb_dev_guard dev_guard(c);
   gb_tower* t = c->text;
   if (!t) return gb_fail(c, GB_ERR_STATE, "text_forward: weights not set");
   if (C <= 0) return GB_OK;
@@ -398,6 +403,7 @@ extern "C" int gb_text_backward_prefix(gb_ctx* c, const float* dfeat, const int3
                                        int P, int Lt, const void* tape_mem, float* dprefix,
                                        void* stream) {
   if (!c) return GB_ERR_ARG;
+  gb_dev_guard dev_guard(c);
   gb_tower* t = c->text;
   if (!t) return gb_fail(c, GB_ERR_STATE, "text_backward_prefix: weights not set");
   const gb_text_weights& w = t->text;

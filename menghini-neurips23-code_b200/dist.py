@@ -66,39 +66,68 @@ def ordered_handoff(state: torch.Tensor, scan_own_range: Callable[[torch.Tensor]
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     if world == 1:
         return scan_own_range(state)
+
+    def peer(r):  # send / recv / broadcast address processes by GLOBAL rank, also inside a sub-group
+        return r if group is None else dist.get_global_rank(group, r)
+
     if rank > 0:
-        dist.recv(state, src=rank - 1, group=group)
+        dist.recv(state, src=peer(rank - 1), group=group)
     state = scan_own_range(state)
     if rank < world - 1:
-        dist.send(state, dst=rank + 1, group=group)
+        dist.send(state, dst=peer(rank + 1), group=group)
     if ring:
         if rank == world - 1:
-            dist.send(state, dst=0, group=group)
+            dist.send(state, dst=peer(0), group=group)
         if rank == 0:
-            dist.recv(state, src=world - 1, group=group)
+            dist.recv(state, src=peer(world - 1), group=group)
     else:
-        dist.broadcast(state, src=world - 1, group=group)
+        dist.broadcast(state, src=peer(world - 1), group=group)
     return state
 
 
 def sharded_pool_scan(features_local: torch.Tensor, protos: torch.Tensor, scale: float, k: int,
-                      n_total: int, rank_all: torch.Tensor, make_board, mode: int = 0, group=None):
+                      n_total: int, rank_all: torch.Tensor, make_board, mode: int = 0, group=None,
+                      timings: dict = None):
     """Exact pseudolabel boards for a pool sharded over the ranks.  features_local are this rank's
     rows of the pool (range shard_bounds(n_total, world)[rank]…); rank_all the global tie-break ranks.
     make_board(state_or_None) builds a Leaderboard (engine.Leaderboard on GPU).  Returns the board
-    holding the final state (identical on every rank)."""
+    holding the final state (identical on every rank).
+
+    Two phases, so that only the order-dependent part is serialised:
+      1. every rank, concurrently: similarity + soft-max + arg-max over its own rows (the HBM pass),
+         probabilities kept (`board.similarity`);
+      2. rank 0 → 1 → … → G-1: conservative pre-filter against the bounds of the arriving state + exact replay
+         of the surviving rows (`board.update`), then the few-KB state moves on.
+    Per-row arithmetic is the one of the single-GPU fused scan (`board.scan`), so the boards are identical
+    for every G.  `timings` (optional dict) receives CUDA-event handles / seconds of the two phases."""
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     bounds = shard_bounds(n_total, world)
     board = make_board(None)
+    if world == 1:
+        board.scan(features_local, protos, scale, mode=mode, idx0=bounds[rank], rank=rank_all)
+        return board
 
-    def scan(state):
+    cuda = features_local.device.type == "cuda"
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if cuda and timings is not None else None
+    if ev:
+        ev[0].record()
+    pred, _, probs = board.similarity(features_local, protos, scale, mode=mode)
+    if ev:
+        ev[1].record()
+
+    def replay(state):
         b = make_board(state)
-        b.scan(features_local, protos, scale, mode=mode, idx0=bounds[rank], rank=rank_all)
+        if ev:
+            ev[2].record()
+        b.update(probs, pred, rank=rank_all, idx0=bounds[rank])
+        if ev:
+            ev[3].record()
         return b.state
 
-    if world == 1:
-        board = make_board(scan(board.state))
-    else:
-        board = make_board(ordered_handoff(board.state, scan, group=group))
+    board = make_board(ordered_handoff(board.state, replay, group=group))
+    if ev:
+        torch.cuda.synchronize()
+        timings["similarity_ms"] = ev[0].elapsed_time(ev[1])
+        timings["replay_ms"] = ev[2].elapsed_time(ev[3])
     return board

@@ -186,7 +186,7 @@ class Engine:
         self._bind()
         rc = self.lib.gb_vit_forward(self.ctx.h, ptr(img), fmt,
                                      ptr(prefix) if P else None, B, P, ptr(feat), ptr(featn), ptr(tp),
-                                     stream_ptr())
+                                     stream_ptr(self.device))
         self.ctx.check(rc, "gb_vit_forward")
         return feat, featn, tp
 
@@ -197,7 +197,7 @@ class Engine:
         dprefix = torch.empty(P, V_WIDTH, device=self.device, dtype=torch.float32)
         self._bind()
         rc = self.lib.gb_vit_backward_prefix(self.ctx.h, ptr(dfeat), ptr(prefix), B, P, ptr(tape),
-                                             ptr(dprefix), stream_ptr())
+                                             ptr(dprefix), stream_ptr(self.device))
         self.ctx.check(rc, "gb_vit_backward_prefix")
         return dprefix
 
@@ -225,7 +225,7 @@ class Engine:
         self._bind()
         rc = self.lib.gb_text_forward(self.ctx.h, ptr(ids_d), ids_d.stride(0), ptr(eot_d),
                                       ptr(prefix) if P else None, C, P, Lt, ptr(feat), ptr(featn),
-                                      ptr(tp), stream_ptr())
+                                      ptr(tp), stream_ptr(self.device))
         self.ctx.check(rc, "gb_text_forward")
         return feat, featn, (tp, eot_d, Lt)
 
@@ -236,7 +236,7 @@ class Engine:
         dprefix = torch.empty(P, T_WIDTH, device=self.device, dtype=torch.float32)
         self._bind()
         rc = self.lib.gb_text_backward_prefix(self.ctx.h, ptr(dfeat), ptr(eot_d), C, P, Lt, ptr(tape),
-                                              ptr(dprefix), stream_ptr())
+                                              ptr(dprefix), stream_ptr(self.device))
         self.ctx.check(rc, "gb_text_backward_prefix")
         return dprefix
 
@@ -256,16 +256,37 @@ class Engine:
         loss = torch.empty(1, device=self.device, dtype=torch.float32)
         pred = torch.empty(B, device=self.device, dtype=torch.int32) if want_pred else None
         rc = self.lib.gb_ce_text_grad(self.ctx.h, ptr(imfn16), ptr(text), ptr(labels), ptr(coef), scale, B, C,
-                                      ptr(dtext), ptr(loss), ptr(pred), stream_ptr())
+                                      ptr(dtext), ptr(loss), ptr(pred), stream_ptr(self.device))
         self.ctx.check(rc, "gb_ce_text_grad")
         return loss, dtext, pred
+
+    def ce_image_grad(self, image, text, labels, coef=None, scale=None, want_dimage=True, want_dtext=False,
+                      want_pred=False):
+        """The same loss with the image side trainable (VPT / UPT, visual_prompt.py:122-135,
+        multimodal_prompt.py:103-121): image fp32 [B,512], text fp32 [C,512], both un-normalised.
+        Returns (loss fp32 [1], dimage fp32 [B,512] | None, dtext fp32 [C,512] | None, pred int32 [B] | None)."""
+        B, C = image.shape[0], text.shape[0]
+        scale = self.logit_scale_exp if scale is None else float(scale)
+        image = image.detach().to(self.device, torch.float32).contiguous()
+        text = text.detach().to(self.device, torch.float32).contiguous()
+        labels = labels.to(self.device, torch.int32).contiguous()
+        if coef is not None:
+            coef = coef.to(self.device, torch.float32).contiguous()
+        dimage = torch.empty(B, EMBED, device=self.device, dtype=torch.float32) if want_dimage else None
+        dtext = torch.empty(C, EMBED, device=self.device, dtype=torch.float32) if want_dtext else None
+        loss = torch.empty(1, device=self.device, dtype=torch.float32)
+        pred = torch.empty(B, device=self.device, dtype=torch.int32) if want_pred else None
+        rc = self.lib.gb_ce_image_grad(self.ctx.h, ptr(image), ptr(text), ptr(labels), ptr(coef), scale, B, C,
+                                       ptr(dimage), ptr(dtext), ptr(loss), ptr(pred), stream_ptr(self.device))
+        self.ctx.check(rc, "gb_ce_image_grad")
+        return loss, dimage, dtext, pred
 
     def sgd_step(self, param, grad, momentum_buf, lr, momentum=0.0, weight_decay=0.0, first_step=False,
                  lr_dev=None):
         """In-place torch.optim.SGD step (dampening 0, no Nesterov) on fp32 device tensors; `lr_dev` (fp32 [1]
         on the device) overrides `lr` when given."""
         rc = self.lib.gb_sgd_step(self.ctx.h, ptr(param), ptr(grad), ptr(momentum_buf), param.numel(), float(lr),
-                                  ptr(lr_dev), float(momentum), float(weight_decay), int(first_step), stream_ptr())
+                                  ptr(lr_dev), float(momentum), float(weight_decay), int(first_step), stream_ptr(self.device))
         self.ctx.check(rc, "gb_sgd_step")
 
     def warmup_cosine_lr(self, base_lr, warmup_steps, t_total, step):
@@ -281,7 +302,7 @@ class Engine:
         p_pred = torch.empty(N, device=self.device, dtype=torch.float32)
         probs = torch.empty(N, C, device=self.device, dtype=torch.float32) if want_probs else None
         rc = self.lib.gb_sim_softmax_argmax(self.ctx.h, ptr(F16), ptr(T16), scale, N, C, mode,
-                                            ptr(pred), ptr(p_pred), ptr(probs), stream_ptr())
+                                            ptr(pred), ptr(p_pred), ptr(probs), stream_ptr(self.device))
         self.ctx.check(rc, "gb_sim_softmax_argmax")
         return pred, p_pred, probs
 
@@ -302,7 +323,7 @@ class Leaderboard:
         if state is None:
             self.state = torch.empty(nbytes, device=self.device, dtype=torch.uint8)
             self.ctx.check(self.lib.gb_leaderboard_init(self.ctx.h, ptr(self.state), self.C, self.k,
-                                                        stream_ptr()), "gb_leaderboard_init")
+                                                        stream_ptr(self.device)), "gb_leaderboard_init")
         else:
             if state.numel() != nbytes or state.dtype != torch.uint8:
                 raise GripB200Error("leaderboard state has the wrong size for (C, k)")
@@ -314,8 +335,20 @@ class Leaderboard:
         row_end = n if row_end is None else row_end
         rc = self.lib.gb_leaderboard_update(self.ctx.h, ptr(self.state), self.C, self.k, ptr(probs),
                                             ptr(pred), ptr(rank), row_begin, row_end, idx0,
-                                            int(bool(prefilter)), stream_ptr())
+                                            int(bool(prefilter)), stream_ptr(self.device))
         self.ctx.check(rc, "gb_leaderboard_update")
+
+    def similarity(self, F16, T16, scale, mode=0):
+        """The order-independent half of `scan`: (pred int32 [n], p_pred fp32 [n], probs fp32 [n,C]) of the rows
+        of F16 — the same bits `scan` feeds to the boards (phase 1 of dist.sharded_pool_scan)."""
+        N = F16.shape[0]
+        pred = torch.empty(N, device=self.device, dtype=torch.int32)
+        p_pred = torch.empty(N, device=self.device, dtype=torch.float32)
+        probs = torch.empty(N, self.C, device=self.device, dtype=torch.float32)
+        rc = self.lib.gb_sim_softmax_argmax(self.ctx.h, ptr(F16), ptr(T16), float(scale), N, self.C, mode,
+                                            ptr(pred), ptr(p_pred), ptr(probs), stream_ptr(self.device))
+        self.ctx.check(rc, "gb_sim_softmax_argmax")
+        return pred, p_pred, probs
 
     def scan(self, F16, T16, scale, mode=0, idx0=0, rank=None, want_probs=False):
         """Fused similarity + softmax + argmax + board update over the rows of F16."""
@@ -325,7 +358,7 @@ class Leaderboard:
         probs = torch.empty(N, self.C, device=self.device, dtype=torch.float32) if want_probs else None
         rc = self.lib.gb_pseudolabel_scan(self.ctx.h, ptr(self.state), ptr(F16), ptr(T16), float(scale),
                                           N, self.C, self.k, mode, idx0, ptr(rank), ptr(pred),
-                                          ptr(p_pred), ptr(probs), stream_ptr())
+                                          ptr(p_pred), ptr(probs), stream_ptr(self.device))
         self.ctx.check(rc, "gb_pseudolabel_scan")
         return pred, p_pred, probs
 
@@ -335,7 +368,7 @@ class Leaderboard:
         ln = torch.empty(self.C, device=self.device, dtype=torch.int32)
         p = torch.empty(self.C, self.k, device=self.device, dtype=torch.float32) if want_p else None
         self.ctx.check(self.lib.gb_leaderboard_export(self.ctx.h, ptr(self.state), self.C, self.k,
-                                                      ptr(idx), ptr(ln), ptr(p), stream_ptr()),
+                                                      ptr(idx), ptr(ln), ptr(p), stream_ptr(self.device)),
                        "gb_leaderboard_export")
         return idx, ln, p
 
@@ -344,6 +377,9 @@ class Leaderboard:
         list order): utils/clip_pseudolabels.py:103-109."""
         idx, ln, _ = self.export()
         idx, ln = idx.cpu(), ln.cpu()
+        if bool((ln < 0).any()):
+            raise GripB200Error(f"leaderboard state was not written for C={self.C}, k={self.k} "
+                                "(resumed / handed-off state with another geometry)")
         out_idx, out_lab = [], []
         for j in range(self.C):
             n = int(ln[j])

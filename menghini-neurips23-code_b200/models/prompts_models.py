@@ -69,7 +69,8 @@ class UPTModel(nn.Module):
         self.image_encoder = image_encoder
         self.text_encoder = text_encoder
 
-    def forward(self, x, classes):
+    def prompt_embeddings(self):
+        """The coupled prompts (coop_embs [1,Pt,512], vpt_embs [1,Pv,768]) the two towers receive: :131-145."""
         coop_embds = self.proj_coop_pre(self.coop_embeddings).to(self.device)          # :131-132
         vpt_embds = self.proj_vpt_pre(self.vpt_embeddings).to(self.device)             # :135
         # :138 — dim 0 (coop | vpt) is what the transformer treats as the sequence
@@ -78,6 +79,10 @@ class UPTModel(nn.Module):
         n = len(self.coop_embeddings)
         coop_embs = self.proj_coop_post(output_seq[:n].to(self.dtype)).reshape(-1, self.coop_length, self.coop_dim)
         vpt_embs = self.proj_vpt_post(output_seq[n:].to(self.dtype)).reshape(-1, self.vpt_length, self.vpt_dim)
+        return coop_embs, vpt_embs
+
+    def forward(self, x, classes):
+        coop_embs, vpt_embs = self.prompt_embeddings()
         text_out = self.text_encoder(coop_embs, classes)                               # :148
         visual_out = self.image_encoder(x, vpt_embs)                                   # :150
         return text_out, visual_out

@@ -98,7 +98,7 @@ class CoOpStep:
         from ._lib import ptr, stream_ptr
 
         eng = self.engine
-        lib, h, chk, st = eng.lib, eng.ctx.h, eng.ctx.check, stream_ptr()
+        lib, h, chk, st = eng.lib, eng.ctx.h, eng.ctx.check, stream_ptr(eng.device)
         prefix = self.model.prefix.data
         chk(lib.gb_text_forward(h, ptr(self._ids), self._ids.stride(0), ptr(self._eot), ptr(prefix), self._C,
                                 self._P, self._Lt, ptr(self._text), None, ptr(self._tape), st), "gb_text_forward")
@@ -146,3 +146,90 @@ class CoOpStep:
                     self._graph = g
         self.steps += 1
         return self._loss, (self._pred if want_pred else None)
+
+
+class VPTStep:
+    """Visual prompt tuning step (methods/semi_supervised_learning/visual_prompt.py:115-145) with the glue on the
+    device: image tower with tape → `gb_ce_image_grad` (cosine-logit CE + gradient w.r.t. the image features) →
+    prompt-only backward → `gb_sgd_step`.  `text_features` are the frozen prompts of the epoch ([C,512], any
+    scale: they are normalised on the device, :115-118); nothing is read back to the host."""
+
+    def __init__(self, image_prefix_model, text_features: torch.Tensor, lr: float, weight_decay: float = 0.0,
+                 momentum: float = 0.0, warmup_epochs: int = 0, epochs: int = 1, world: int = 1):
+        self.model = image_prefix_model
+        self.engine = image_prefix_model.image_encoder.visual._vt._owner().engine
+        self.text = text_features.detach().to(self.engine.device, torch.float32).contiguous()
+        self.base_lr, self.wd, self.mu = float(lr), float(weight_decay), float(momentum)
+        self.warmup, self.epochs, self.epoch = int(warmup_epochs), int(epochs), 0
+        self.world = world
+        self.buf = torch.zeros_like(self.model.prefix.data, dtype=torch.float32)
+        self.steps = 0
+
+    @property
+    def lr(self) -> float:
+        return self.engine.warmup_cosine_lr(self.base_lr, self.warmup, self.epochs, self.epoch)
+
+    def update_scheduler(self):
+        self.epoch += 1
+
+    def step(self, img: torch.Tensor, labels: torch.Tensor, coef: Optional[torch.Tensor] = None,
+             want_pred: bool = False):
+        """One optimisation step on a batch of images (fp32 / fp16 normalised or uint8 pixels).  Returns
+        (loss [1], image features fp32 [B,512], pred | None), all on the device."""
+        eng = self.engine
+        prefix = self.model.prefix
+        if prefix.dtype != torch.float32 or not prefix.data.is_contiguous():
+            raise ValueError("VPTStep needs a contiguous fp32 prefix parameter")
+        with torch.no_grad():
+            p2 = prefix.data.reshape(-1, 768)
+            feat, _, tape = eng.vit_forward(img, p2, tape=True)
+            loss, dimage, _, pred = eng.ce_image_grad(feat, self.text, labels, coef, want_pred=want_pred)
+            dprefix = eng.vit_backward_prefix(dimage, p2, tape)
+            del tape
+            if self.world > 1:
+                _dist.allreduce_mean_(dprefix)
+            eng.sgd_step(prefix.data, dprefix, self.buf, self.lr, self.mu, self.wd, first_step=False)
+        self.steps += 1
+        return loss, feat, pred
+
+
+class UPTStep:
+    """Unified prompt tuning step (methods/semi_supervised_learning/multimodal_prompt.py:103-127): the 0.5 M
+    parameter coupling head stays a torch module (its graph is 2×4 tokens wide); both towers run with tape, the
+    loss and BOTH feature gradients come from one `gb_ce_image_grad` call, the two prompt-only backward passes
+    hand d loss / d coop_embs and d loss / d vpt_embs to the head's autograd graph, and `optimizer` (the caller's
+    torch optimiser over the head and the two prompt tensors) takes the step."""
+
+    def __init__(self, upt_model, optimizer, world: int = 1):
+        self.model = upt_model
+        self.opt = optimizer
+        self.enc = upt_model.text_encoder
+        self.engine = self.enc.clip_model.engine
+        self.world = world
+
+    def step(self, img, labels, classes=None, coef=None, want_pred: bool = False):
+        eng = self.engine
+        classes = self.model.classes if classes is None else classes
+        coop_embs, vpt_embs = self.model.prompt_embeddings()
+        Pt = coop_embs.shape[1]
+        ids = self.enc._prompt_ids(Pt, classes)
+        with torch.no_grad():
+            c2 = coop_embs.detach().reshape(-1, 512).float()
+            v2 = vpt_embs.detach().reshape(-1, 768).float()
+            tfeat, _, tsaved = eng.text_forward(ids, c2, tape=True)
+            ifeat, _, tape = eng.vit_forward(img, v2, tape=True)
+            loss, dimage, dtext, pred = eng.ce_image_grad(ifeat, tfeat, labels, coef, want_dtext=True,
+                                                          want_pred=want_pred)
+            dcoop = eng.text_backward_prefix(dtext, Pt, tsaved)
+            dvpt = eng.vit_backward_prefix(dimage, v2, tape)
+            del tape, tsaved
+        self.opt.zero_grad(set_to_none=True)
+        torch.autograd.backward([coop_embs, vpt_embs],
+                                [dcoop.reshape(coop_embs.shape).to(coop_embs.dtype),
+                                 dvpt.reshape(vpt_embs.shape).to(vpt_embs.dtype)])
+        if self.world > 1:
+            for p in self.model.parameters():
+                if p.grad is not None:
+                    _dist.allreduce_mean_(p.grad)
+        self.opt.step()
+        return loss, (tfeat, ifeat), pred

@@ -51,6 +51,14 @@ class PyBoard:
         self.boards.feed(probs, pred, rank.tolist(), idx0)
         self._store()
 
+    def similarity(self, feats, protos, scale, mode=0):
+        _, probs, pred = leaderboard_ref.softmax_argmax(feats.numpy(), protos.numpy(), scale)
+        return pred, None, probs
+
+    def update(self, probs, pred, rank=None, idx0=0):
+        self.boards.feed(probs, pred, rank.tolist(), idx0)
+        self._store()
+
     def result(self):
         return self.boards.result()
 

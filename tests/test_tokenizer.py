@@ -107,3 +107,27 @@ def test_preprocess_u8_is_the_transform_without_its_normalisation_tail():
     raw = clip.preprocess_u8()(img)
     assert raw.dtype == torch.uint8 and tuple(raw.shape) == (3, 224, 224)
     assert torch.equal(clip.normalize_u8(raw), full)
+
+
+@pytest.mark.parametrize("size", [(500, 375), (640, 480), (375, 500), (333, 517), (224, 224), (1024, 683),
+                                  (225, 224), (300, 301)])
+def test_preprocess_matches_torchvision_clip_transform(size):
+    """clip.load()'s preprocess = openai/CLIP's torchvision pipeline Resize(224, bicubic) → CenterCrop(224) → RGB →
+    ToTensor → Normalize, pixel for pixel (the long side is truncated, the crop origin rounded)."""
+    import importlib
+
+    import numpy as np
+    from PIL import Image
+    tv = pytest.importorskip("torchvision.transforms")
+
+    clip = importlib.import_module("menghini-neurips23-code_b200.clip")
+    rng = np.random.default_rng(size[0] * 1000 + size[1])
+    img = Image.fromarray(rng.integers(0, 256, (size[1], size[0], 3), dtype=np.uint8))
+    want = tv.Compose([
+        tv.Resize(224, interpolation=tv.InterpolationMode.BICUBIC), tv.CenterCrop(224),
+        lambda im: im.convert("RGB"), tv.ToTensor(),
+        tv.Normalize((0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711))])(img)
+    got = clip._preprocess()(img)
+    assert got.shape == want.shape == (3, 224, 224)
+    assert torch.allclose(got, want, atol=1e-6, rtol=0)
+    assert torch.equal(clip.normalize_u8(clip.preprocess_u8()(img)), got)
