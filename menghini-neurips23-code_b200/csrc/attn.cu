@@ -149,7 +149,10 @@ attn_fwd_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int L,
   __half* Qs = reinterpret_cast<__half*>(attn_smem);
   __half* Ks = Qs + Lp * kQKld;
   __half* Vs = Ks + Lp * kQKld;
-  const int h = blockIdx.x, b = blockIdx.y;
+  // Samples are visited from the LAST one down: the in-proj GEMM in front of this kernel writes its rows in
+  // ascending order, so the rows it wrote last (still in the 126 MB L2) are the ones read first here — and this
+  // kernel's own last writes (sample 0 …) are what the out-proj GEMM behind it reads first.
+  const int h = blockIdx.x, b = gridDim.y - 1 - blockIdx.y;
   stage_qkv<NT>(qkv, L, D, b, h, Qs, Ks, Vs);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -218,7 +221,7 @@ attn_bwd_kernel(const __half* __restrict__ qkv, const __half* __restrict__ dout,
   __half* dOs = Vs + Lp * kQKld;
   __half* Ps = dOs + Lp * kQKld;                       // [Lp, ldp]  P  (query-major)
   __half* dSs = Ps + Lp * ldp;                         // [Lp, ldp]  dS (query-major)
-  const int h = blockIdx.x, b = blockIdx.y;
+  const int h = blockIdx.x, b = gridDim.y - 1 - blockIdx.y;   // last sample first (see attn_fwd_kernel)
   const size_t ld = (size_t)3 * D;
   {
     // one round trip: every 16-byte chunk of Q, K, V, dO is requested before the first store; all

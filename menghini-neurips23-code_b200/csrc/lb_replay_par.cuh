@@ -50,7 +50,7 @@ __device__ __forceinline__ int lbp_block_excl_scan(int v, int32_t* s_warp, int& 
 
 inline size_t lb_replay_par_smem_bytes(int C, int k) {
   return (size_t)3 * C * 4 + (size_t)C * k * 8 + (size_t)C * 4 + (size_t)kLbpWarps * 3 * (k + 1) * 4 +
-         (size_t)kLbpRound * 4 + (size_t)kLbpWarps * (kLbpRound / 32) * 4 + (size_t)(kLbpWarps + 4) * 4 +
+         (size_t)kLbpRound * 4 + (size_t)kLbpWarps * (kLbpRound / 32) * 4 + (size_t)(kLbpWarps + 4 + 8) * 4 +
          kLbpRound + 16;
 }
 
@@ -83,9 +83,12 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
   uint32_t* rel = reinterpret_cast<uint32_t*>(slots + kLbpRound);    // [32][kLbpRound/32]
   int32_t* s_warp = reinterpret_cast<int32_t*>(rel + kLbpWarps * (kLbpRound / 32));  // [32] scan scratch
   int32_t* s_bc = s_warp + kLbpWarps;                                // [4] n, cursor, boards still filling
-  volatile uint8_t* dec = reinterpret_cast<volatile uint8_t*>(s_bc + 4);  // [kLbpRound] 0 pending, 1 accepted, 2 rejected
+  int32_t* s_dbg = s_bc + 4;                                         // [8] diagnostics (→ header words 3..7)
+  volatile uint8_t* dec = reinterpret_cast<volatile uint8_t*>(s_dbg + 8);  // [kLbpRound] 0 pending, 1 accepted, 2 rejected
   constexpr int kRelLd = kLbpRound / 32;
 
+  if (tid < 8) s_dbg[tid] = 0;
+  const long long t_start = clock64();
   for (int i = tid; i < C * k; i += kLbpThreads) { v.ep[i] = g.ep[i]; v.ei[i] = g.ei[i]; }
   for (int j = tid; j < C; j += kLbpThreads) {
     v.srt[j] = g.srt[j];
@@ -154,6 +157,7 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
       }
     }
     if (n == 0) break;
+    if (tid == 0) { s_dbg[2] += n; s_dbg[5] += 1; }
     // ---- (b) clear the relevance masks and the decisions of this round ----
     const int n_words = (n + 31) >> 5;
     for (int i = tid; i < kLbpWarps * n_words; i += kLbpThreads) rel[(i / n_words) * kRelLd + (i % n_words)] = 0u;
@@ -199,6 +203,7 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
         const float p_mine = lane == 0 ? v0 : lane == 1 ? v1 : lane == 2 ? v2 : v3;
         const bool known_rej = !(p_own > s_lb[own]);  // at or below the bound: rejected whatever happened since
         bool rejected;
+        if (lane == 0) atomicAdd(&s_dbg[0], 1);
         if ((own & 31) == warp) {
           // this warp owns the arg-max board: utils/clip_pseudolabels.py:73-82
           const int c_own = s_cnt[own];
@@ -228,7 +233,8 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
             rejected = true;
           } else {
             uint8_t d;
-            while ((d = dec[s]) == 0) {}
+            if (lane == 0) atomicAdd(&s_dbg[1], 1);
+            while ((d = dec[s]) == 0) __nanosleep(32);
             rejected = d == 2;
           }
         }
@@ -250,6 +256,7 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
             const int l = __ffs(nm) - 1;
             nm &= nm - 1;
             const float pj = l == 0 ? v0 : l == 1 ? v1 : l == 2 ? v2 : v3;
+            if (lane == 0) atomicAdd(&s_dbg[3], 1);
             lb_admit(v, warp + 32 * l, pj, idx, p.rank, s_last, lane);
           }
           __syncwarp();
@@ -259,6 +266,12 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
     __syncthreads();
   }
   __syncthreads();
+  if (tid == 0) {  // diagnostics, accumulated over the launches of a scan: header words 3..7 =
+                   // events walked, decisions waited for, flagged rows, spill admissions, kernel clocks / 1024
+    int32_t* hdr = reinterpret_cast<int32_t*>(p.state);
+    hdr[3] += s_dbg[0]; hdr[4] += s_dbg[1]; hdr[5] += s_dbg[2]; hdr[6] += s_dbg[3];
+    hdr[7] += (int32_t)((clock64() - t_start) >> 10);
+  }
   for (int i = tid; i < C * k; i += kLbpThreads) { g.ep[i] = v.ep[i]; g.ei[i] = v.ei[i]; }
   for (int j = tid; j < C; j += kLbpThreads) {
     g.srt[j] = v.srt[j];

@@ -40,20 +40,23 @@ def path_ranks(paths):
     return torch.tensor(rank, dtype=torch.int32)
 
 
-def encode_pool(clip_model, filepaths, transform, device, batch=ENCODE_BATCH, loader=None):
+def encode_pool(clip_model, filepaths, transform, device, batch=ENCODE_BATCH, loader=None, prefix=None):
     """Unit-norm fp16 image features [N,512] of the whole pool, encoded in batches.
 
     The reference decodes and encodes one image at a time (:55-61).  Here a background thread decodes chunk
     i+1 (PIL releases the GIL) into pinned memory while the device encodes chunk i; when `transform` is this
     package's CLIP transform its `raw_u8` twin is used — resize + centre crop on the host, ToTensor +
-    Normalize on the device, bit-identical features."""
+    Normalize on the device, bit-identical features.  `prefix` ([P,768] / [1,P,768]): visual prompt
+    rows every image is encoded with (the VPT / UPT strategies' assign_pseudo_labels, visual_fpl.py:262-268)."""
     from concurrent.futures import ThreadPoolExecutor
 
     from PIL import Image
 
     eng = clip_model.engine
+    if prefix is not None:
+        prefix = prefix.detach().reshape(-1, prefix.shape[-1]).float()
     if not batch:
-        batch = type(eng).wave_aligned_batch(2048, L=50, sms=148)
+        batch = type(eng).wave_aligned_batch(2048, L=50 + (0 if prefix is None else prefix.shape[0]), sms=148)
     feats = torch.empty(len(filepaths), 512, device=eng.device, dtype=torch.float16)
     tf = getattr(transform, "raw_u8", None) or transform
 
@@ -72,7 +75,7 @@ def encode_pool(clip_model, filepaths, transform, device, batch=ENCODE_BATCH, lo
             if i + 1 < len(starts):
                 fut = pool.submit(load, filepaths[starts[i + 1]:starts[i + 1] + batch])
             imgs = imgs.to(eng.device, non_blocking=True)
-            _, fn, _ = eng.vit_forward(imgs, None, want_feat=False, want_featn=True)
+            _, fn, _ = eng.vit_forward(imgs, prefix, want_feat=False, want_featn=True)
             feats[s:s + imgs.shape[0]] = fn
     return feats
 

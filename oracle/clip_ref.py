@@ -305,6 +305,16 @@ def _identity_transform(img):
     return img
 
 
+def clip_transform():
+    """openai/CLIP's `_transform(224)`: Resize(224, bicubic) → CenterCrop(224) → RGB → ToTensor → Normalize, through
+    torchvision (what the third-party package itself uses)."""
+    import torchvision.transforms as tv
+
+    return tv.Compose([tv.Resize(224, interpolation=tv.InterpolationMode.BICUBIC), tv.CenterCrop(224),
+                       lambda im: im.convert("RGB"), tv.ToTensor(),
+                       tv.Normalize((0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711))])
+
+
 def load(name: str = "ViT-B/32", device="cpu", jit: bool = False, seed: int = 1234):
     """`clip.load` on CPU: (fp32 eval model, preprocess).  Only ViT-B/32 shapes exist offline."""
     if name.replace("/", "").replace("-", "").lower() != "vitb32":
