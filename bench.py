@@ -340,6 +340,47 @@ def extras_single_gpu(a, model, dev, pk):
     del ustep, upt, img, lab
     torch.cuda.empty_cache()
 
+    # ---- N2: the host half of the input pipeline — JPEG files → multi-threaded decode + bicubic resize + crop →
+    # pinned uint8 staging → device normalise + image tower (utils.encode_pool) ----
+    try:
+        import shutil
+        import tempfile
+
+        import numpy as np
+        from PIL import Image
+
+        utils_b200 = importlib.import_module(PKG + ".utils")
+        tmp = tempfile.mkdtemp(prefix="gripb200_jpeg_")
+        rng = np.random.default_rng(0)
+        n_img = 2048
+        base = np.kron(rng.integers(0, 256, size=(12, 16, 3)), np.ones((32, 32, 1))).astype(np.float32)  # 384 x 512
+        paths = []
+        for i in range(64):     # 64 distinct files, linked 32 times each: the decode cost is what matters
+            arr = np.clip(base * rng.uniform(0.6, 1.0) + rng.normal(0, 12, size=base.shape), 0, 255).astype(np.uint8)
+            pth = os.path.join(tmp, f"img_{i}.jpg")
+            Image.fromarray(arr).save(pth, quality=90)
+            paths.append(pth)
+        paths = [paths[i % 64] for i in range(n_img)]
+        transform = clip._preprocess()
+        cores = os.cpu_count() or 1
+        utils_b200.encode_pool(model, paths[:256], transform, dev)      # warm-up (thread pools, staging, arenas)
+        torch.cuda.synchronize()
+        res = {}
+        for wk in (1, cores):
+            t0 = time.perf_counter()
+            utils_b200.encode_pool(model, paths if wk > 1 else paths[:256], transform, dev, workers=wk)
+            torch.cuda.synchronize()
+            res[wk] = (n_img if wk > 1 else 256) / (time.perf_counter() - t0)
+        shutil.rmtree(tmp, ignore_errors=True)
+        out["decode_pipeline"] = {"config": f"{n_img} JPEG files (512x384, quality 90) → utils.encode_pool: decode + bicubic "
+                                            f"resize + centre crop on {cores} host threads into pinned uint8 staging, "
+                                            f"ToTensor + Normalize + image tower on the device",
+                                  "images_per_s": res[cores], "images_per_s_one_thread": res[1], "host_threads": cores,
+                                  "note": "the reference decodes on one thread at batch 1 (utils/clip_pseudolabels.py:55-57); "
+                                          "host decode, not the tower, bounds a real pool"}
+    except Exception as e:   # PIL without a JPEG codec etc.: an extra, never fatal
+        out["decode_pipeline"] = {"unavailable": repr(e)}
+
     # ---- the reference's own BATCH_SIZE: CoOp, B = 16, C = 10, P = 16 ----
     P, C, B = 16, 10, 16
     classes = make_classes(C, seed=1)

@@ -441,9 +441,14 @@ int launch_bwd(gb_ctx* c, const void* qkv, const void* dout, void* dqkv, int B, 
 
 }  // namespace
 
+// attn_tc.cu: the tcgen05 / TMEM / TMA forward (default); GB_ATTN_LEGACY=1 keeps the mma.sync kernel below
+bool gb_attn_tc_enabled();
+int gb_launch_attn_fwd_tc(gb_ctx* c, const void* qkv, void* out, int B, int L, int D, int causal, cudaStream_t st);
+
 int gb_launch_attn_fwd(gb_ctx* c, const void* qkv, void* out, int B, int L, int D, int causal,
                        cudaStream_t st) {
   if (B <= 0) return GB_OK;
+  if (gb_attn_tc_enabled() && L <= 128 && D % kDh == 0) return gb_launch_attn_fwd_tc(c, qkv, out, B, L, D, causal, st);
   if (L < 1 || L > 96 || D % kDh != 0)
     return gb_fail(c, GB_ERR_ARG, "attention: L=%d (1..96) D=%d (multiple of 64) unsupported", L, D);
   const int lp = (L + 15) / 16;

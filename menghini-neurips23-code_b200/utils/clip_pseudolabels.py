@@ -40,14 +40,19 @@ def path_ranks(paths):
     return torch.tensor(rank, dtype=torch.int32)
 
 
-def encode_pool(clip_model, filepaths, transform, device, batch=ENCODE_BATCH, loader=None, prefix=None):
+def encode_pool(clip_model, filepaths, transform, device, batch=ENCODE_BATCH, loader=None, prefix=None,
+                workers=None):
     """Unit-norm fp16 image features [N,512] of the whole pool, encoded in batches.
 
-    The reference decodes and encodes one image at a time (:55-61).  Here a background thread decodes chunk
-    i+1 (PIL releases the GIL) into pinned memory while the device encodes chunk i; when `transform` is this
-    package's CLIP transform its `raw_u8` twin is used — resize + centre crop on the host, ToTensor +
-    Normalize on the device, bit-identical features.  `prefix` ([P,768] / [1,P,768]): visual prompt
-    rows every image is encoded with (the VPT / UPT strategies' assign_pseudo_labels, visual_fpl.py:262-268)."""
+    The reference decodes and encodes one image at a time on one thread (:55-61; data/dataset.py:64-79 even applies
+    the transform three times per sample).  Here `workers` host threads (default: every core; PIL's decoders and
+    resampling release the GIL) decode + resize + crop the images of chunk i+1 straight into a pinned staging
+    buffer while the device encodes chunk i; two staging buffers alternate, the H2D copy is asynchronous.  When
+    `transform` is this package's CLIP transform its `raw_u8` twin is used — resize + centre crop on the host,
+    ToTensor + Normalize on the device: a quarter of the staging and PCIe bytes, bit-identical features
+    (SURVEY §8f N2).  `prefix` ([P,768] / [1,P,768]): visual prompt rows every image is encoded with (the VPT / UPT
+    strategies' assign_pseudo_labels, visual_fpl.py:262-268).  `loader(chunk) -> tensor` replaces decoding."""
+    import os
     from concurrent.futures import ThreadPoolExecutor
 
     from PIL import Image
@@ -57,26 +62,53 @@ def encode_pool(clip_model, filepaths, transform, device, batch=ENCODE_BATCH, lo
         prefix = prefix.detach().reshape(-1, prefix.shape[-1]).float()
     if not batch:
         batch = type(eng).wave_aligned_batch(2048, L=50 + (0 if prefix is None else prefix.shape[0]), sms=148)
-    feats = torch.empty(len(filepaths), 512, device=eng.device, dtype=torch.float16)
+    n = len(filepaths)
+    feats = torch.empty(n, 512, device=eng.device, dtype=torch.float16)
+    if n == 0:
+        return feats
     tf = getattr(transform, "raw_u8", None) or transform
+    workers = max(1, min(int(workers or os.cpu_count() or 1), 64))
 
-    def load(chunk):
-        if loader is not None:
-            imgs = loader(chunk)
-        else:
-            imgs = torch.stack([tf(Image.open(p).convert("RGB")) for p in chunk])
-        return imgs.pin_memory() if imgs.device.type == "cpu" else imgs
+    def decode(path):
+        return tf(Image.open(path).convert("RGB"))
 
-    starts = list(range(0, len(filepaths), batch))
-    with ThreadPoolExecutor(max_workers=1) as pool:
-        fut = pool.submit(load, filepaths[starts[0]:starts[0] + batch]) if starts else None
+    starts = list(range(0, n, batch))
+    staging = [None, None]       # pinned, allocated once the first decoded image tells shape and dtype
+    consumed = [None, None]      # event: the device has finished reading staging[b]
+
+    with ThreadPoolExecutor(max_workers=workers) as dec_pool, ThreadPoolExecutor(max_workers=1) as chunk_pool:
+
+        def load(ci):
+            chunk = filepaths[starts[ci]:starts[ci] + batch]
+            if loader is not None:
+                imgs = loader(chunk)
+                return imgs.pin_memory() if imgs.device.type == "cpu" and not imgs.is_pinned() else imgs
+            b = ci % 2
+            first = decode(chunk[0])
+            if staging[b] is None or staging[b].dtype != first.dtype or staging[b].shape[1:] != first.shape:
+                staging[b] = torch.empty((batch,) + tuple(first.shape), dtype=first.dtype).pin_memory()
+            if consumed[b] is not None:
+                consumed[b].synchronize()
+            buf = staging[b]
+            buf[0].copy_(first)
+
+            def put(i):
+                buf[i].copy_(decode(chunk[i]))
+
+            list(dec_pool.map(put, range(1, len(chunk))))
+            return buf[:len(chunk)]
+
+        fut = chunk_pool.submit(load, 0)
         for i, s in enumerate(starts):
             imgs = fut.result()
             if i + 1 < len(starts):
-                fut = pool.submit(load, filepaths[starts[i + 1]:starts[i + 1] + batch])
-            imgs = imgs.to(eng.device, non_blocking=True)
-            _, fn, _ = eng.vit_forward(imgs, prefix, want_feat=False, want_featn=True)
-            feats[s:s + imgs.shape[0]] = fn
+                fut = chunk_pool.submit(load, i + 1)
+            dev = imgs.to(eng.device, non_blocking=True)
+            if loader is None:
+                consumed[i % 2] = torch.cuda.Event()
+                consumed[i % 2].record(torch.cuda.current_stream(eng.device))
+            _, fn, _ = eng.vit_forward(dev, prefix, want_feat=False, want_featn=True)
+            feats[s:s + dev.shape[0]] = fn
     return feats
 
 

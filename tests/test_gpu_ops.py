@@ -123,7 +123,9 @@ def _attn_ref(qkv, B, L, D, causal):
 
 @pytest.mark.parametrize("B,L,D,causal", [(3, 50, 768, 0), (2, 54, 768, 0), (5, 66, 768, 0),
                                           (4, 77, 512, 1), (7, 24, 512, 1), (2, 9, 512, 1),
-                                          (1, 16, 512, 0), (2, 96, 768, 0), (3, 33, 512, 1)])
+                                          (1, 16, 512, 0), (2, 96, 768, 0), (3, 33, 512, 1),
+                                          (301, 50, 768, 0), (200, 66, 768, 0), (150, 77, 512, 1), (1, 128, 512, 1),
+                                          (64, 64, 768, 1)])
 def test_attention_forward(ctx, B, L, D, causal):
     g = torch.Generator(device="cuda").manual_seed(L)
     qkv = torch.randn(B * L, 3 * D, device="cuda", generator=g).half()
