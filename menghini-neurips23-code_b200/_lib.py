@@ -11,7 +11,8 @@ import re
 from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_size_t, c_uint64, c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgripb200.so")
+# GRIPB200_LIB names another build of the same library (A/B measurements of build-time switches)
+LIB_PATH = os.environ.get("GRIPB200_LIB") or os.path.join(_HERE, "libgripb200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "gripb200.h")
 
 

@@ -14,10 +14,13 @@
 //                     K-major swizzled 128×128 tile whose off-diagonal quadrants are zero
 //   O = P·V           one 128×64×128 chain; V is consumed in place as an MN-major B operand (keys = K dimension)
 //   O → fp16 → swizzled staging tile → TMA store of L rows per sample into a[B·L, D]
-// Persistent CTAs, warp specialised: warp 0 TMA producer (2-stage ring of Q|K|V), warp 1 MMA issuer, warp 2 TMEM
+// Persistent CTAs, warp specialised: warp 0 TMA producer (3-stage ring of Q|K|V: the loads run two items ahead of
+// the P·V that frees a stage — with two stages the next item's load could only start when the previous item was
+// completely done and the kernel ran at the latency of one load per item), warp 1 MMA issuer, warp 2 TMEM
 // allocator, two soft-max warpgroups that take alternate items (each owns its S and O accumulators and its P
-// tile), so one group's soft-max overlaps the other's MMAs and stores.  Samples are visited from the last one
-// down (see attn.cu: the in-proj GEMM's most recent rows are still in L2).
+// tile), so one group's soft-max overlaps the other's MMAs and stores.  The fp16 output tile is staged in the first
+// atom of the group's own P tile (P is dead once P·V has completed), which is what leaves room for the third stage.
+// Samples are visited from the last one down (see attn.cu: the in-proj GEMM's most recent rows are still in L2).
 // Algorithmic HBM traffic: 8·D bytes per token (read q, k, v, write o); no other global access.
 #include <stdlib.h>
 
@@ -28,12 +31,12 @@ using namespace gb;
 
 namespace {
 
-constexpr int kAtStages = 2;
+constexpr int kAtStages = 3;
 constexpr int kAtTile = 128 * 128;            // one 128-row × 64-half tile, bytes
 constexpr int kAtStageBytes = 3 * kAtTile;    // Q | K | V
 constexpr int kAtPBytes = 2 * kAtTile;        // P: two 64-key atoms of 128 rows
 constexpr int kAtThreads = 128 + 2 * 128;     // TMA, MMA, TMEM-alloc, idle + two soft-max warpgroups
-constexpr int kAtSmem = kAtStages * kAtStageBytes + 2 * kAtPBytes + 2 * kAtTile + 1024 + 256;
+constexpr int kAtSmem = kAtStages * kAtStageBytes + 2 * kAtPBytes + 1024 + 256;
 
 struct AttnTcParams {
   int B, L, H, D;
@@ -67,9 +70,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_qkv = smem;                                        // [stage][Q|K|V][128][128 B]
-  uint8_t* smem_p = smem_qkv + kAtStages * kAtStageBytes;          // [wg][atom][128][128 B]
-  uint8_t* smem_o = smem_p + 2 * kAtPBytes;                        // [wg][128][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + 2 * kAtTile);
+  uint8_t* smem_p = smem_qkv + kAtStages * kAtStageBytes;          // [wg][atom][128][128 B]; atom 0 doubles as the O staging tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_p + 2 * kAtPBytes);
   uint64_t* full_bar = bars;                  // [kAtStages]
   uint64_t* empty_bar = bars + kAtStages;     // [kAtStages]
   uint64_t* sfull_bar = bars + 2 * kAtStages; // [2] S of warpgroup w complete
@@ -181,7 +183,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     const uint32_t t_s = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + w * 256 + (G == 2 ? j * 64 : 0);
     const uint32_t t_o = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + w * 256 + 128;
     const uint32_t p_row = smem_u32(smem_p + w * kAtPBytes) + r * 128;     // + atom·16 KB + swizzled chunk
-    uint8_t* o_tile = smem_o + w * kAtTile;
+    uint8_t* o_tile = smem_p + w * kAtPBytes;
     const uint32_t o_row = smem_u32(o_tile) + r * 128;
     const bool causal = p.causal != 0;
     int n = 0;
@@ -214,6 +216,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         sum += e;
       }
       const float inv = 1.0f / sum;
+      // P goes where this warpgroup's previous output tile was staged: its TMA stores must have read it
+      if (threadIdx.x == 128 + w * 128) tma_store_wait_read<0>();
+      wg_barrier(1 + w);
+      if (G == 2 && j == 1) {   // the staging tile covered atom 0 of every row: sample 1 has no keys there
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) sts128(p_row + ((c8 ^ (r & 7)) << 4), make_uint4(0, 0, 0, 0));
+      }
 #pragma unroll
       for (int c8 = 0; c8 < kCols / 8; ++c8) {
         uint4 o;
@@ -232,12 +241,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       tc_fence_after();
       uint32_t ov[64];
       tmem_ld_32x64(t_o, ov);
-      // the staging tile is free once the stores of this warpgroup's previous item have read it
-      if (threadIdx.x == 128 + w * 128) tma_store_wait_read<0>();
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&odone_bar[w]);
-      wg_barrier(1 + w);
+      // P·V has completed (ofull), so the P tile is dead: its first atom is the staging tile
 #pragma unroll
       for (int c8 = 0; c8 < 8; ++c8) {
         uint4 o;

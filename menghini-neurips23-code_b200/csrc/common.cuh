@@ -394,6 +394,18 @@ __device__ __forceinline__ void quick_gelu2(float& a, float& b) {
   b *= r * ea;
 }
 
+// QuickGELU on a pair of fp16 values, in fp16 like the reference's own CUDA path (clip.model.QuickGELU on fp16
+// tensors rounds every intermediate to fp16): x·σ(1.702x) = x/2 + (x/2)·tanh(0.851x) — one MUFU (tanh.approx.f16x2)
+// and three packed-half instructions per PAIR, against ≈9.5 fp32 instructions per element of the ex2/rcp form.
+__device__ __forceinline__ uint32_t quick_gelu_h2(uint32_t x2) {
+  uint32_t a, t, hx, y;
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(a) : "r"(x2), "r"(0x3acf3acfu));   // 0.851 (fp16 0x3acf = 0.85107)
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(a));
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(hx) : "r"(x2), "r"(0x38003800u));  // 0.5
+  asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(y) : "r"(hx), "r"(t));
+  return y;
+}
+
 __device__ __forceinline__ float quick_gelu_grad(float x) {
   // d/dx [x·σ(1.702x)] = σ + 1.702·x·σ·(1−σ)
   const float s = fast_rcp(1.0f + fast_exp2(-2.4554669595930157f * x));

@@ -338,6 +338,9 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 #ifndef GB_GELU_SHARE
 #define GB_GELU_SHARE 4  // QuickGELUs per shared reciprocal (1, 2 or 4)
 #endif
+#ifndef GB_GELU_H2
+#define GB_GELU_H2 1  // CTA-pair kernel: QuickGELU on the fp16-rounded pre-activation in packed fp16 (quick_gelu_h2)
+#endif
 
 // Epilogue geometry of the CTA-pair kernel: GB_EPI_WARPS epilogue warps (8 or 16) — TMEM lane quadrant
 // warp % 4, column group (warp − 4) / 4 of 256 / (GB_EPI_WARPS / 4) columns.  Measured on B200 (same box,
@@ -516,7 +519,26 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
         f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
       }
     }
+    uint32_t act_h2[(kGelu && GB_GELU_H2) ? 16 : 1];   // packed fp16 activations (GB_GELU_H2)
     if constexpr (kGelu) {
+#if GB_GELU_H2
+      // pre-activation → fp16 once (it is what the tape keeps and what the reference's fp16 path feeds the
+      // activation), QuickGELU in packed fp16
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          h[t] = __floats2half2_rn(f[8 * j + 2 * t], f[8 * j + 2 * t + 1]);
+        if (p.aux != nullptr && row_ok)
+          reinterpret_cast<uint4*>(p.aux + (size_t)row * p.ldo + col0)[j] = o;
+        act_h2[4 * j + 0] = quick_gelu_h2(o.x);
+        act_h2[4 * j + 1] = quick_gelu_h2(o.y);
+        act_h2[4 * j + 2] = quick_gelu_h2(o.z);
+        act_h2[4 * j + 3] = quick_gelu_h2(o.w);
+      }
+#else
       if (p.aux != nullptr && row_ok) {
         uint4* a4 = reinterpret_cast<uint4*>(p.aux + (size_t)row * p.ldo + col0);
 #pragma unroll
@@ -538,6 +560,7 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
 #else
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
+#endif
 #endif
     } else if (kAct2 && has_pre) {
 #pragma unroll
@@ -570,7 +593,8 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
       __half2* h = reinterpret_cast<__half2*>(&o);
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        h[t] = __floats2half2_rn(f[8 * j + 2 * t], f[8 * j + 2 * t + 1]);
+        if constexpr (kGelu && GB_GELU_H2) reinterpret_cast<uint32_t*>(&o)[t] = act_h2[4 * j + t];
+        else h[t] = __floats2half2_rn(f[8 * j + 2 * t], f[8 * j + 2 * t + 1]);
         if (kMode == kEpiResid && p.stats_out != nullptr) {  // statistics of the values as stored (fp16-rounded)
           const float2 r = __half22float2(h[t]);
           if (c == 0 && j == 0 && t == 0) st_x0 = r.x;

@@ -13,6 +13,16 @@
 // (p_own ≤ bound ⇒ rejected).  A warp waits only on rows ≤ the one it is at, whose owner never waits at that
 // row: no cycle, and all 32 warps are resident (one CTA).  Every board sees exactly the operation sequence of
 // the single-warp replay, so the result is bit-identical to it.
+//
+// kSet = true is the same walk for boards too large for shared memory (GRIP grows k to N/C,
+// methods/semi_supervised_learning/pseudo_iterative.py:62-75): the boards stay in the caller's state (global
+// memory / L2) and a FULL board is kept as an unordered SET.  That is exact because the reference's
+// `sorted(board + [new], reverse=True)[:k]` (:78-82) always drops the smallest (p, path) of the k+1 items and the
+// new item is never that one (it was admitted because own[-1].p < p), on the first admission of a board as well as
+// on every later one — so an admission is "replace the set's minimum", the only thing that distinguishes the
+// never-sorted state from the sorted one is the threshold (p of the k-th ARRIVAL, which never moves in the set
+// layout, vs. the set's minimum p), and the list ORDER the reference would show is recovered by one sort at the end
+// of the scan call (lb_set_sort_kernel): no O(k²) one-time sort and no O(k) shifting inside the sequential walk.
 #pragma once
 
 constexpr int kLbpThreads = 1024;
@@ -48,12 +58,125 @@ __device__ __forceinline__ int lbp_block_excl_scan(int v, int32_t* s_warp, int& 
   return base + x - v;
 }
 
-inline size_t lb_replay_par_smem_bytes(int C, int k) {
-  return (size_t)3 * C * 4 + (size_t)C * k * 8 + (size_t)C * 4 + (size_t)kLbpWarps * 3 * (k + 1) * 4 +
-         (size_t)kLbpRound * 4 + (size_t)kLbpWarps * (kLbpRound / 32) * 4 + (size_t)(kLbpWarps + 4 + 8) * 4 +
-         kLbpRound + 16;
+inline size_t lb_replay_par_smem_bytes(int C, int k, bool set_mode = false) {
+  const size_t boards = set_mode ? 0 : (size_t)C * k * 8 + (size_t)C * 4 + (size_t)kLbpWarps * 3 * (k + 1) * 4;
+  return (size_t)5 * C * 4 + boards + (size_t)kLbpRound * 4 + (size_t)kLbpWarps * (kLbpRound / 32) * 4 +
+         (size_t)(kLbpWarps + 4 + 8) * 4 + kLbpRound + 16;
+}
+// kSet: minima of every group of 32 consecutive board slots, [C][ceil(k/32)] floats, when they fit beside the rest
+// (C·k ≲ 1.4 M entries): an admission then reads one or two 128-byte groups instead of the whole board.
+constexpr size_t kLbpSmemMax = 200 * 1024;
+inline int lb_set_groups(int C, int k) {
+  const int G = (k + 31) / 32;
+  return lb_replay_par_smem_bytes(C, k, true) + (size_t)C * G * 4 <= kLbpSmemMax ? G : 0;
 }
 
+__device__ __forceinline__ float lbp_warp_min(float m) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  return m;
+}
+
+// Set-mode admission with group minima gm[0..G) of board j in shared memory: the smallest p of the board is the
+// smallest group minimum; the entry that leaves is, among the entries that carry it (one group unless p ties
+// exactly), the one with the lowest path rank.
+__device__ void lb_admit_set_gm(const LbView& v, int j, float pj, int idx, const int32_t* rank, float* s_last,
+                                float* gm, int G, int lane) {
+  const int k = v.k;
+  float* ep = v.ep + (size_t)j * k;
+  int32_t* ei = v.ei + (size_t)j * k;
+  __syncwarp();
+  float m = INFINITY;
+  for (int g = lane; g < G; g += 32) m = fminf(m, gm[g]);
+  m = lbp_warp_min(m);
+  int best_r = 0x7fffffff, best_pos = -1;
+  for (int g0 = 0; g0 < G; g0 += 32) {
+    const int g = g0 + lane;
+    uint32_t bal = __ballot_sync(0xffffffffu, g < G && gm[g] == m);
+    while (bal) {
+      const int t = __ffs(bal) - 1;
+      bal &= bal - 1;
+      const int e = (g0 + t) * 32 + lane;
+      const float pe = e < k ? ep[e] : INFINITY;
+      int r = 0x7fffffff, pos = e;
+      if (pe == m) {
+        const int ie = ei[e];
+        r = rank ? rank[ie] : ie;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const int orr = __shfl_xor_sync(0xffffffffu, r, o);
+        const int opos = __shfl_xor_sync(0xffffffffu, pos, o);
+        if (orr < r || (orr == r && opos < pos)) { r = orr; pos = opos; }
+      }
+      if (best_pos < 0 || r < best_r) { best_r = r; best_pos = pos; }
+    }
+  }
+  const int gb = best_pos >> 5;
+  const int e = gb * 32 + lane;
+  float pe = e < k ? ep[e] : INFINITY;
+  if (e == best_pos) pe = pj;
+  const float gnew = lbp_warp_min(pe);
+  if (lane == 0) {
+    ep[best_pos] = pj;
+    ei[best_pos] = idx;
+    gm[gb] = gnew;
+    v.srt[j] = 1;
+  }
+  __syncwarp();
+  m = INFINITY;
+  for (int g = lane; g < G; g += 32) m = fminf(m, gm[g]);
+  m = lbp_warp_min(m);
+  if (lane == 0) s_last[j] = m;
+  __syncwarp();
+}
+
+// Admission of (pj, idx) into FULL board j kept as a set (kSet): the entry that is smallest by (p, path rank) leaves,
+// the new one takes its slot; the board's threshold becomes the smallest p that is left.  Warp-cooperative, one
+// pass over the k entries (coalesced; ranks are looked at only on exact ties of p).
+__device__ void lb_admit_set(const LbView& v, int j, float pj, int idx, const int32_t* rank, float* s_last,
+                             int lane) {
+  const int k = v.k;
+  float* ep = v.ep + (size_t)j * k;
+  int32_t* ei = v.ei + (size_t)j * k;
+  __syncwarp();
+  float m1p = INFINITY, m2p = INFINITY;   // smallest (p, rank) seen by this lane; smallest p among its other entries
+  int m1r = 0x7fffffff, m1pos = -1;
+  for (int e = lane; e < k; e += 32) {
+    const float pe = ep[e];
+    bool less = pe < m1p;
+    int re = 0;
+    if (pe == m1p) {
+      const int ie = ei[e];
+      re = rank ? rank[ie] : ie;
+      less = re < m1r;
+    } else if (less) {
+      const int ie = ei[e];
+      re = rank ? rank[ie] : ie;
+    }
+    if (less) { m2p = m1p; m1p = pe; m1r = re; m1pos = e; }
+    else m2p = fminf(m2p, pe);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float op = __shfl_xor_sync(0xffffffffu, m1p, o);
+    const int orr = __shfl_xor_sync(0xffffffffu, m1r, o);
+    const int opos = __shfl_xor_sync(0xffffffffu, m1pos, o);
+    const float o2 = __shfl_xor_sync(0xffffffffu, m2p, o);
+    const bool other_wins = op < m1p || (op == m1p && (orr < m1r || (orr == m1r && opos >= 0 && (m1pos < 0 || opos < m1pos))));
+    if (other_wins) { m2p = fminf(fminf(m2p, o2), m1p); m1p = op; m1r = orr; m1pos = opos; }
+    else m2p = fminf(fminf(m2p, o2), op);
+  }
+  if (lane == 0) {
+    ep[m1pos] = pj;
+    ei[m1pos] = idx;
+    v.srt[j] = 1;
+    s_last[j] = fminf(m2p, pj);
+  }
+  __syncwarp();
+}
+
+template <bool kSet>
 __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbReplayParams p) {
   extern __shared__ uint8_t lb_smem[];
   const int C = p.C, k = p.k;
@@ -67,59 +190,103 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nb = (C + 31) >> 5;  // boards per warp (≤ 4): lane l < nb of warp w ↔ board w + 32·l
   // ---- shared memory carve-up (every region is a multiple of 4 bytes) ----
-  float* s_last = reinterpret_cast<float*>(lb_smem);                 // [C] p of the last list entry
+  float* s_last = reinterpret_cast<float*>(lb_smem);                 // [C] acceptance threshold: p of the last list entry
   int32_t* s_cnt = reinterpret_cast<int32_t*>(s_last + C);           // [C]
   float* s_lb = reinterpret_cast<float*>(s_cnt + C);                 // [C] lower bounds of this round
+  float* s_min = s_lb + C;                                           // [C] kSet: running minimum of a never-sorted board
+  int32_t* s_ka = reinterpret_cast<int32_t*>(s_min + C);             // [C] own arrivals of this round are sure to be appended
   const LbView g = lb_view(p.state, C, k);
   LbView v = g;
-  v.ep = s_lb + C;
-  v.ei = reinterpret_cast<int32_t*>(v.ep + (size_t)C * k);
-  v.srt = v.ei + (size_t)C * k;
-  float* scratch = reinterpret_cast<float*>(v.srt + C);              // [32 warps][3][k+1] one-time sort scratch
-  v.sp = scratch + (size_t)warp * 3 * (k + 1);
-  v.si = reinterpret_cast<int32_t*>(v.sp + k + 1);
-  v.sr = v.si + k + 1;
-  int32_t* slots = reinterpret_cast<int32_t*>(scratch + (size_t)kLbpWarps * 3 * (k + 1));  // [kLbpRound]
+  float* carve = reinterpret_cast<float*>(s_ka + C);
+  if constexpr (!kSet) {
+    v.ep = carve;
+    v.ei = reinterpret_cast<int32_t*>(v.ep + (size_t)C * k);
+    v.srt = v.ei + (size_t)C * k;
+    float* scratch = reinterpret_cast<float*>(v.srt + C);            // [32 warps][3][k+1] one-time sort scratch
+    v.sp = scratch + (size_t)warp * 3 * (k + 1);
+    v.si = reinterpret_cast<int32_t*>(v.sp + k + 1);
+    v.sr = v.si + k + 1;
+    carve = scratch + (size_t)kLbpWarps * 3 * (k + 1);
+  }
+  int32_t* slots = reinterpret_cast<int32_t*>(carve);                // [kLbpRound]
   uint32_t* rel = reinterpret_cast<uint32_t*>(slots + kLbpRound);    // [32][kLbpRound/32]
   int32_t* s_warp = reinterpret_cast<int32_t*>(rel + kLbpWarps * (kLbpRound / 32));  // [32] scan scratch
-  int32_t* s_bc = s_warp + kLbpWarps;                                // [4] n, cursor, boards still filling
+  int32_t* s_bc = s_warp + kLbpWarps;                                // [4] n, cursor, boards still filling, … nearly full
   int32_t* s_dbg = s_bc + 4;                                         // [8] diagnostics (→ header words 3..7)
   volatile uint8_t* dec = reinterpret_cast<volatile uint8_t*>(s_dbg + 8);  // [kLbpRound] 0 pending, 1 accepted, 2 rejected
   constexpr int kRelLd = kLbpRound / 32;
+  const int G = kSet ? p.set_groups : 0;    // group minima of the set-mode boards ([C][G]; 0: not kept)
+  float* s_gm = reinterpret_cast<float*>(
+      lb_smem + ((reinterpret_cast<uint8_t*>(s_dbg + 8) - lb_smem + kLbpRound + 15) & ~size_t(15)));
 
   if (tid < 8) s_dbg[tid] = 0;
   const long long t_start = clock64();
-  for (int i = tid; i < C * k; i += kLbpThreads) { v.ep[i] = g.ep[i]; v.ei[i] = g.ei[i]; }
-  for (int j = tid; j < C; j += kLbpThreads) {
-    v.srt[j] = g.srt[j];
-    const int c = g.cnt[j];
-    s_cnt[j] = c;
-    s_last[j] = c > 0 ? g.ep[(size_t)j * k + c - 1] : 0.f;
+  if constexpr (kSet) {
+    // boards stay in global memory; a board's threshold is the k-th arrival's p until its first admission and the
+    // minimum of the set afterwards (entries of an already sorted board may arrive in any order)
+    for (int j = warp; j < C; j += kLbpWarps) {
+      const int c = g.cnt[j];
+      float m = INFINITY;
+      if (G > 0) {
+#pragma unroll 4
+        for (int gq = 0; gq < G; ++gq) {
+          const int e = gq * 32 + lane;
+          const float gmin = lbp_warp_min(e < c ? g.ep[(size_t)j * k + e] : INFINITY);
+          if (lane == 0) s_gm[(size_t)j * G + gq] = gmin;
+          m = fminf(m, gmin);
+        }
+      } else {
+        for (int e = lane; e < c; e += 32) m = fminf(m, g.ep[(size_t)j * k + e]);
+        m = lbp_warp_min(m);
+      }
+      if (lane == 0) {
+        s_cnt[j] = c;
+        s_min[j] = m;
+        s_last[j] = (c >= k && g.srt[j]) ? m : (c > 0 ? g.ep[(size_t)j * k + c - 1] : 0.f);
+      }
+    }
+  } else {
+    for (int i = tid; i < C * k; i += kLbpThreads) { v.ep[i] = g.ep[i]; v.ei[i] = g.ei[i]; }
+    for (int j = tid; j < C; j += kLbpThreads) {
+      v.srt[j] = g.srt[j];
+      const int c = g.cnt[j];
+      s_cnt[j] = c;
+      s_last[j] = c > 0 ? g.ep[(size_t)j * k + c - 1] : 0.f;
+    }
   }
   __syncthreads();
 
   const int word_end = (p.row_end + 31) >> 5;
   int cursor = p.row_begin >> 5;  // uniform over the CTA
+  long long t_ph = t_start, c_a = 0, c_c = 0, c_d = 0;
   while (true) {
     // ---- lower bounds of this round from the live boards; is any board still filling? ----
-    if (tid == 0) s_bc[2] = 0;
+    if (tid == 0) { s_bc[2] = 0; s_bc[3] = 0; }
     __syncthreads();
     for (int j = tid; j < C; j += kLbpThreads) {
       float lbv = -INFINITY;
-      if (s_cnt[j] >= k) {
+      const int room = k - s_cnt[j];
+      if (room <= 0) {
         if (v.srt[j]) {
-          lbv = v.ep[(size_t)j * k + k - 1];
+          lbv = kSet ? s_last[j] : v.ep[(size_t)j * k + k - 1];
+        } else if (kSet) {
+          lbv = s_min[j];
         } else {
           lbv = INFINITY;
           for (int e = 0; e < k; ++e) lbv = fminf(lbv, v.ep[(size_t)j * k + e]);
         }
       } else {
         atomicAdd(&s_bc[2], 1);
+        if (room < kLbpRound) atomicAdd(&s_bc[3], 1);
       }
       s_lb[j] = lbv;
     }
     __syncthreads();
-    const int cap = s_bc[2] > 0 ? kLbpFillRound : kLbpRound;
+    // While a board is about to fill up every row may matter to it: short rounds refresh the bounds sooner.  A board
+    // with room for a whole round appends every own arrival of the round whatever else happens (its count grows by at
+    // most one per row), so those rows concern nobody but the board's owner: s_ka.
+    const int cap = s_bc[3] > 0 ? kLbpFillRound : kLbpRound;
+    for (int j = tid; j < C; j += kLbpThreads) s_ka[j] = (k - s_cnt[j]) >= cap;
     // ---- (a) the next ≤ cap flagged rows of [row_begin,row_end), in index order ----
     int n = 0;
     while (n < cap && cursor < word_end) {
@@ -163,15 +330,32 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
     for (int i = tid; i < kLbpWarps * n_words; i += kLbpThreads) rel[(i / n_words) * kRelLd + (i % n_words)] = 0u;
     for (int i = tid; i < n; i += kLbpThreads) dec[i] = 0;
     __syncthreads();
+    if (p.diag == 2) { const long long t = clock64(); c_a += t - t_ph; t_ph = t; }
     // ---- (c) relevance: bit s of rel[w] ⇔ row slots[s] beats the bound of some board owned by warp w ----
-    for (int s = warp; s < n; s += kLbpWarps) {
-      const float* prow = p.rows + (size_t)(slots[s] - p.rows_row0) * C;
-      for (int gq = 0; gq < nb; ++gq) {
-        const int j = lane + 32 * gq;      // the owner warp of board j is j % 32 == lane
-        if (j < C && prow[j] > s_lb[j]) atomicOr(&rel[lane * kRelLd + (s >> 5)], 1u << (s & 31));
+    for (int s0 = warp * 32; s0 < n; s0 += kLbpWarps * 32) {
+      const int s = s0 + lane;
+      int row_s = 0;
+      bool ka = false;
+      if (s < n) {
+        row_s = slots[s];
+        const int own_s = p.pred[row_s];
+        ka = s_ka[own_s] != 0;   // sure to be appended to its own board: nobody else is offered this row
+        if (ka) atomicOr(&rel[(own_s & 31) * kRelLd + (s >> 5)], 1u << (s & 31));
+      }
+      uint32_t todo = __ballot_sync(0xffffffffu, s < n && !ka);
+      while (todo) {
+        const int e = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int ss = s0 + e;
+        const float* prow = p.rows + (size_t)(__shfl_sync(0xffffffffu, row_s, e) - p.rows_row0) * C;
+        for (int gq = 0; gq < nb; ++gq) {
+          const int j = lane + 32 * gq;      // the owner warp of board j is j % 32 == lane
+          if (j < C && prow[j] > s_lb[j]) atomicOr(&rel[lane * kRelLd + (ss >> 5)], 1u << (ss & 31));
+        }
       }
     }
     __syncthreads();
+    if (p.diag == 2) { const long long t = clock64(); c_c += t - t_ph; t_ph = t; }
     // ---- (d) replay: every warp walks its relevant rows in index order ----
     const int my_board = warp + 32 * lane;            // meaningful for lane < nb
     const bool have_board = lane < nb && my_board < C;
@@ -203,26 +387,35 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
         const float p_mine = lane == 0 ? v0 : lane == 1 ? v1 : lane == 2 ? v2 : v3;
         const bool known_rej = !(p_own > s_lb[own]);  // at or below the bound: rejected whatever happened since
         bool rejected;
-        if (lane == 0) atomicAdd(&s_dbg[0], 1);
+        if (p.diag == 1 && lane == 0) atomicAdd(&s_dbg[0], 1);
         if ((own & 31) == warp) {
           // this warp owns the arg-max board: utils/clip_pseudolabels.py:73-82
           const int c_own = s_cnt[own];
-          bool acc = true;
-          if (c_own < k) {
+          const bool fill = c_own < k;
+          const bool acc = fill || s_last[own] < p_own;
+          // the verdict first, the bookkeeping after: the warps that wait for it are the critical path
+          if (!known_rej && lane == 0) dec[s] = acc ? 1 : 2;
+          if (fill) {
             __syncwarp();
             if (lane == 0) {
               v.ep[(size_t)own * k + c_own] = p_own;
               v.ei[(size_t)own * k + c_own] = idx;
               s_cnt[own] = c_own + 1;
               s_last[own] = p_own;
+              if constexpr (kSet) {
+                s_min[own] = fminf(s_min[own], p_own);
+                if (G > 0) s_gm[(size_t)own * G + (c_own >> 5)] = fminf(s_gm[(size_t)own * G + (c_own >> 5)], p_own);
+              }
             }
             __syncwarp();
-          } else if (s_last[own] < p_own) {
-            lb_admit(v, own, p_own, idx, p.rank, s_last, lane);
-          } else {
-            acc = false;
+          } else if (acc) {
+            if constexpr (kSet) {
+              if (G > 0) lb_admit_set_gm(v, own, p_own, idx, p.rank, s_last, s_gm + (size_t)own * G, G, lane);
+              else lb_admit_set(v, own, p_own, idx, p.rank, s_last, lane);
+            } else {
+              lb_admit(v, own, p_own, idx, p.rank, s_last, lane);
+            }
           }
-          if (!known_rej && lane == 0) dec[s] = acc ? 1 : 2;
           rejected = !acc;
         } else {
           // would any of my boards take this row if it is offered?  (live state: exact)
@@ -233,8 +426,8 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
             rejected = true;
           } else {
             uint8_t d;
-            if (lane == 0) atomicAdd(&s_dbg[1], 1);
-            while ((d = dec[s]) == 0) __nanosleep(32);
+            if (p.diag == 1 && lane == 0) atomicAdd(&s_dbg[1], 1);
+            while ((d = dec[s]) == 0) { if (p.spin_sleep) __nanosleep(p.spin_sleep); }
             rejected = d == 2;
           }
         }
@@ -247,6 +440,10 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
               v.ei[(size_t)my_board * k + cj] = idx;
               s_cnt[my_board] = cj + 1;
               s_last[my_board] = p_mine;
+              if constexpr (kSet) {
+                s_min[my_board] = fminf(s_min[my_board], p_mine);
+                if (G > 0) s_gm[(size_t)my_board * G + (cj >> 5)] = fminf(s_gm[(size_t)my_board * G + (cj >> 5)], p_mine);
+              }
             } else if (s_last[my_board] < p_mine) {
               need = true;
             }
@@ -256,31 +453,45 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
             const int l = __ffs(nm) - 1;
             nm &= nm - 1;
             const float pj = l == 0 ? v0 : l == 1 ? v1 : l == 2 ? v2 : v3;
-            if (lane == 0) atomicAdd(&s_dbg[3], 1);
-            lb_admit(v, warp + 32 * l, pj, idx, p.rank, s_last, lane);
+            if (p.diag == 1 && lane == 0) atomicAdd(&s_dbg[3], 1);
+            if constexpr (kSet) {
+              const int jb = warp + 32 * l;
+              if (G > 0) lb_admit_set_gm(v, jb, pj, idx, p.rank, s_last, s_gm + (size_t)jb * G, G, lane);
+              else lb_admit_set(v, jb, pj, idx, p.rank, s_last, lane);
+            } else {
+              lb_admit(v, warp + 32 * l, pj, idx, p.rank, s_last, lane);
+            }
           }
           __syncwarp();
         }
       }
     }
     __syncthreads();
+    if (p.diag == 2) { const long long t = clock64(); c_d += t - t_ph; t_ph = t; }
   }
   __syncthreads();
+  if (p.diag == 2 && tid == 0) {   // phase clocks / 1024 instead of the event counters: collect+bounds, relevance, walk, rounds
+    s_dbg[0] = (int32_t)(c_a >> 10); s_dbg[1] = (int32_t)(c_c >> 10); s_dbg[3] = (int32_t)(c_d >> 10); s_dbg[2] = s_dbg[5];
+  }
   if (tid == 0) {  // diagnostics, accumulated over the launches of a scan: header words 3..7 =
                    // events walked, decisions waited for, flagged rows, spill admissions, kernel clocks / 1024
     int32_t* hdr = reinterpret_cast<int32_t*>(p.state);
     hdr[3] += s_dbg[0]; hdr[4] += s_dbg[1]; hdr[5] += s_dbg[2]; hdr[6] += s_dbg[3];
     hdr[7] += (int32_t)((clock64() - t_start) >> 10);
   }
-  for (int i = tid; i < C * k; i += kLbpThreads) { g.ep[i] = v.ep[i]; g.ei[i] = v.ei[i]; }
+  if constexpr (!kSet) {
+    for (int i = tid; i < C * k; i += kLbpThreads) { g.ep[i] = v.ep[i]; g.ei[i] = v.ei[i]; }
+  }
   for (int j = tid; j < C; j += kLbpThreads) {
-    g.srt[j] = v.srt[j];
+    if constexpr (!kSet) g.srt[j] = v.srt[j];
     const int c = s_cnt[j];
     g.cnt[j] = c;
     float lbv = -INFINITY;
     if (c >= k) {
       if (v.srt[j]) {
-        lbv = v.ep[(size_t)j * k + k - 1];
+        lbv = kSet ? s_last[j] : v.ep[(size_t)j * k + k - 1];
+      } else if (kSet) {
+        lbv = s_min[j];
       } else {
         lbv = INFINITY;
         for (int e = 0; e < k; ++e) lbv = fminf(lbv, v.ep[(size_t)j * k + e]);
@@ -288,4 +499,45 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
     }
     g.lb[j] = lbv;
   }
+}
+
+// kSet boards → the list order the reference shows (descending (p, path), utils/clip_pseudolabels.py:78-82): every
+// entry of a board that has had an admission counts the entries in front of it (tiles of the board through shared
+// memory; keys are distinct) and lands at that position of the scratch copy, which lb_set_copy_kernel moves back.
+// Grid (ceil(k / 256), C).
+__global__ void __launch_bounds__(256) lb_set_sort_kernel(void* state, int C, int k, const int32_t* __restrict__ rank,
+                                                          float* __restrict__ out_p, int32_t* __restrict__ out_i) {
+  const LbView v = lb_view(state, C, k);
+  const int j = blockIdx.y;
+  if (!v.srt[j] || v.cnt[j] < k) return;   // arrival order stands
+  __shared__ float t_p[256];
+  __shared__ int32_t t_r[256];
+  const float* ep = v.ep + (size_t)j * k;
+  const int32_t* ei = v.ei + (size_t)j * k;
+  const int a = blockIdx.x * 256 + threadIdx.x;
+  float pa = 0.f;
+  int ia = 0, ra = 0;
+  if (a < k) { pa = ep[a]; ia = ei[a]; ra = rank ? rank[ia] : ia; }
+  int before = 0;
+  for (int t0 = 0; t0 < k; t0 += 256) {
+    const int b = t0 + threadIdx.x;
+    if (b < k) {
+      const int ib = ei[b];
+      t_p[threadIdx.x] = ep[b];
+      t_r[threadIdx.x] = rank ? rank[ib] : ib;
+    }
+    __syncthreads();
+    const int nt = min(256, k - t0);
+    for (int b2 = 0; b2 < nt; ++b2) before += lb_before(t_p[b2], t_r[b2], pa, ra) ? 1 : 0;
+    __syncthreads();
+  }
+  if (a < k) { out_p[(size_t)j * k + before] = pa; out_i[(size_t)j * k + before] = ia; }
+}
+__global__ void __launch_bounds__(256) lb_set_copy_kernel(void* state, int C, int k, const float* __restrict__ in_p,
+                                                          const int32_t* __restrict__ in_i) {
+  const LbView v = lb_view(state, C, k);
+  const int j = blockIdx.y;
+  if (!v.srt[j] || v.cnt[j] < k) return;
+  const int a = blockIdx.x * 256 + threadIdx.x;
+  if (a < k) { v.ep[(size_t)j * k + a] = in_p[(size_t)j * k + a]; v.ei[(size_t)j * k + a] = in_i[(size_t)j * k + a]; }
 }

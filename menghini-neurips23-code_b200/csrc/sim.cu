@@ -408,6 +408,9 @@ struct LbReplayParams {
   const uint32_t* flags;  // global bitmask (bit i%32 of word i/32) or nullptr (every row)
   int row_begin, row_end;
   int idx0;               // global image index of local row 0 (boards and rank[] use global indices)
+  int set_groups = 0;     // set-mode boards: group minima per board kept in shared memory (0: none)
+  int diag = 0;           // count events / waits / spill admissions into the state header (GB_LB_DIAG=1)
+  int spin_sleep = 32;    // ns a warp sleeps between polls of another warp's decision (GB_LB_SPIN_NS; 0 = busy poll)
 };
 
 __device__ void lb_admit(const LbView& v, int j, float pj, int idx, const int32_t* rank,
@@ -824,15 +827,42 @@ int sim_chunked(gb_ctx* c, const void* F, const void* T, float scale, int N, int
   return GB_OK;
 }
 
+// Which replay a (C, k) geometry gets — a property of the state's geometry, the same for every launch on it:
+//   0  serial single-warp kernel (C > 128, or GB_LB_SERIAL=1)
+//   1  boards of warps, boards in shared memory as sorted lists (k ≤ 64 and C·k ≤ 8192)
+//   2  boards of warps, boards in global memory as sets (any k); lb_set_finalize restores the list order
+int lb_replay_path(int C, int k) {
+  if (C > kLbpMaxC || !lb_parallel_enabled()) return 0;
+  return (k <= kLbpMaxK && (size_t)C * k <= kLbSmemEntries) ? 1 : 2;
+}
+inline size_t lb_set_sort_bytes(int C, int k) {
+  return lb_replay_path(C, k) == 2 ? (((size_t)C * k * 8 + 255) & ~size_t(255)) : 0;
+}
+// End of a scan call on set-mode boards: back to the reference's list order.  `scratch` holds lb_set_sort_bytes.
+int lb_set_finalize(gb_ctx* c, void* state, int C, int k, const int32_t* rank, void* scratch, cudaStream_t st) {
+  if (lb_replay_path(C, k) != 2) return GB_OK;
+  float* sp = reinterpret_cast<float*>(scratch);
+  int32_t* si = reinterpret_cast<int32_t*>(sp + (size_t)C * k);
+  const dim3 grid((k + 255) / 256, C);
+  lb_set_sort_kernel<<<grid, 256, 0, st>>>(state, C, k, rank, sp, si);
+  GB_LAUNCH_CHECK(c);
+  lb_set_copy_kernel<<<grid, 256, 0, st>>>(state, C, k, sp, si);
+  GB_LAUNCH_CHECK(c);
+  return GB_OK;
+}
+
 int launch_replay(gb_ctx* c, void* state, int C, int k, const float* rows, int rows_row0,
                   const int32_t* pred, const int32_t* rank, const uint32_t* flags, int row_begin,
                   int row_end, int idx0, cudaStream_t st) {
   if (row_end <= row_begin) return GB_OK;
-  if (C <= kLbpMaxC && k <= kLbpMaxK && (size_t)C * k <= kLbSmemEntries && lb_parallel_enabled()) {
+  const int path = lb_replay_path(C, k);
+  if (path != 0) {
     static bool par_attr_set[16] = {false};
     if (!par_attr_set[c->device & 15]) {
-      GB_CUDA(c, cudaFuncSetAttribute(lb_replay_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      GB_CUDA(c, cudaFuncSetAttribute(lb_replay_par_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)lb_replay_par_smem_bytes(kLbpMaxC, kLbpMaxK)));
+      GB_CUDA(c, cudaFuncSetAttribute(lb_replay_par_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kLbpSmemMax + 64));
       par_attr_set[c->device & 15] = true;
     }
     LbReplayParams q;
@@ -840,7 +870,24 @@ int launch_replay(gb_ctx* c, void* state, int C, int k, const float* rows, int r
     q.rows = rows; q.rows_row0 = rows_row0;
     q.pred = pred; q.rank = rank; q.flags = flags;
     q.row_begin = row_begin; q.row_end = row_end; q.idx0 = idx0;
-    lb_replay_par_kernel<<<1, kLbpThreads, lb_replay_par_smem_bytes(C, k), st>>>(q);
+    static int spin_ns = -1;
+    if (spin_ns < 0) {
+      const char* e = getenv("GB_LB_SPIN_NS");
+      spin_ns = e ? atoi(e) : 32;
+    }
+    q.spin_sleep = spin_ns;
+    static int diag = -1;
+    if (diag < 0) {
+      const char* e = getenv("GB_LB_DIAG");
+      diag = e ? atoi(e) : 0;
+    }
+    q.diag = diag;
+    if (path == 1) lb_replay_par_kernel<false><<<1, kLbpThreads, lb_replay_par_smem_bytes(C, k), st>>>(q);
+    else {
+      q.set_groups = lb_set_groups(C, k);
+      const size_t smem = lb_replay_par_smem_bytes(C, k, true) + (size_t)C * q.set_groups * 4 + 32;
+      lb_replay_par_kernel<true><<<1, kLbpThreads, smem, st>>>(q);
+    }
     GB_LAUNCH_CHECK(c);
     return GB_OK;
   }
@@ -907,13 +954,19 @@ extern "C" int gb_leaderboard_update(gb_ctx* c, void* state, int C, int k, const
     return gb_fail(c, GB_ERR_ARG, "leaderboard_update: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   if (row_end <= row_begin) return GB_OK;
-  if (!prefilter)
-    return launch_replay(c, state, C, k, probs, 0, pred, rank, nullptr, row_begin, row_end, idx0, st);
+  // scratch: [pre-filter flags | set-mode sort copy]
+  const size_t flag_b = ((((size_t)(row_end + 31) / 32) * 4 + 256) + 255) & ~size_t(255);
+  int rc = gb_ws_reserve(c, gb_ctx::kWsScan, flag_b + lb_set_sort_bytes(C, k));
+  if (rc) return rc;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(c->ws[gb_ctx::kWsScan]);
+  if (!prefilter) {
+    rc = launch_replay(c, state, C, k, probs, 0, pred, rank, nullptr, row_begin, row_end, idx0, st);
+    if (rc) return rc;
+    return lb_set_finalize(c, state, C, k, rank, ws + flag_b, st);
+  }
   // chunked: filter against the bounds left by the previous chunk, then replay the survivors
   const LbView v = lb_view(state, C, k);
-  int rc = gb_ws_reserve(c, gb_ctx::kWsScan, ((size_t)(row_end + 31) / 32) * 4 + 256);
-  if (rc) return rc;
-  uint32_t* flags = reinterpret_cast<uint32_t*>(c->ws[gb_ctx::kWsScan]);
+  uint32_t* flags = reinterpret_cast<uint32_t*>(ws);
   int chunk = 4096;
   for (int r0 = row_begin; r0 < row_end;) {
     const int r1 = min(r0 + chunk, row_end);
@@ -924,7 +977,7 @@ extern "C" int gb_leaderboard_update(gb_ctx* c, void* state, int C, int k, const
     r0 = r1;
     if (chunk < (1 << 18)) chunk *= 2;
   }
-  return GB_OK;
+  return lb_set_finalize(c, state, C, k, rank, ws + flag_b, st);
 }
 
 extern "C" int gb_leaderboard_export(gb_ctx* c, const void* state, int C, int k, int32_t* out_idx,
@@ -968,12 +1021,14 @@ extern "C" int gb_pseudolabel_scan(gb_ctx* c, void* state, const void* F, const 
     return gb_leaderboard_update(c, state, C, k, pr, pred, rank, 0, N, idx0, 1, stream);
   }
   const int chunk_cap = 1 << 18;
-  const size_t flag_bytes = (((size_t)N + 127) / 128) * 16 + 256;
-  const size_t cand_bytes = probs ? 0 : (size_t)(N < chunk_cap ? ((N + 127) & ~127) : chunk_cap) * C * 4;
-  int rc = gb_ws_reserve(c, gb_ctx::kWsScan, flag_bytes + cand_bytes);
+  const size_t flag_bytes = ((((size_t)N + 127) / 128) * 16 + 256 + 255) & ~size_t(255);
+  const size_t cand_bytes =
+      probs ? 0 : (((size_t)(N < chunk_cap ? ((N + 127) & ~127) : chunk_cap) * C * 4 + 255) & ~size_t(255));
+  int rc = gb_ws_reserve(c, gb_ctx::kWsScan, flag_bytes + cand_bytes + lb_set_sort_bytes(C, k));
   if (rc) return rc;
   uint32_t* flags = reinterpret_cast<uint32_t*>(c->ws[gb_ctx::kWsScan]);
   float* cand = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(c->ws[gb_ctx::kWsScan]) + flag_bytes);
+  void* sort_scratch = reinterpret_cast<uint8_t*>(c->ws[gb_ctx::kWsScan]) + flag_bytes + cand_bytes;
   int chunk = 4096;
   for (int r0 = 0; r0 < N;) {
     const int r1 = min(r0 + chunk, N);
@@ -986,5 +1041,5 @@ extern "C" int gb_pseudolabel_scan(gb_ctx* c, void* state, const void* F, const 
     r0 = r1;
     if (chunk < chunk_cap) chunk *= 2;
   }
-  return GB_OK;
+  return lb_set_finalize(c, state, C, k, rank, sort_scratch, st);
 }

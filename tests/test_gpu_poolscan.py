@@ -113,7 +113,10 @@ def test_leaderboard_golden_bit_exact(eng_mod, golden_dir, prefilter):
 
 @pytest.mark.parametrize("N,C,k,peaked", [(5000, 10, 16, 0.3), (20000, 45, 16, 0.1), (30000, 100, 16, 0.0),
                                           (4000, 7, 64, 0.2), (3000, 5, 600, 0.3), (2000, 3, 1, 0.5),
-                                          (10000, 102, 4, 0.05), (6000, 200, 8, 0.1), (3000, 397, 3, 0.1)])
+                                          (10000, 102, 4, 0.05), (6000, 200, 8, 0.1), (3000, 397, 3, 0.1),
+                                          # boards too large for shared memory: kept as sets in global memory
+                                          (20000, 100, 150, 0.05), (12000, 45, 266, 0.1), (8000, 10, 800, 0.3),
+                                          (9000, 128, 65, 0.0), (5000, 2, 2500, 0.2)])
 def test_leaderboard_random_matches_oracle(eng_mod, sim, N, C, k, peaked):
     f, t = synth.pool(N, C, peaked=peaked)
     F, T = f.half().cuda(), t.half().cuda()
@@ -148,6 +151,51 @@ def test_leaderboard_ties_fp16_grid(eng_mod):
         lb.update(probs_t.cuda(), pred_t.to(torch.int32).cuda(),
                   torch.from_numpy(rank_np).to(torch.int32).cuda(), prefilter=prefilter)
         assert lb.result() == want
+
+
+@pytest.mark.parametrize("k", [100, 750, 2000])
+def test_leaderboard_ties_large_k(eng_mod, k):
+    # the set-mode boards (k > 64): exact ties everywhere, so which entry leaves a full board and the final list
+    # order are decided by the path ranks
+    rng = np.random.RandomState(11)
+    N, C = 6000, 8
+    lg = rng.choice(np.linspace(0, 3, 5), size=(N, C)).astype(np.float32)
+    probs_t = torch.softmax(torch.from_numpy(lg), dim=1)
+    pred_t = probs_t.argmax(1)
+    rank_np = synth.path_ranks(N, seed=4)
+    want = leaderboard_ref.leaderboard(probs_t.numpy(), pred_t.numpy(), k, rank_np)
+    for prefilter in (False, True):
+        lb = eng_mod.Leaderboard(C, k, "cuda:0")
+        lb.update(probs_t.cuda(), pred_t.to(torch.int32).cuda(),
+                  torch.from_numpy(rank_np).to(torch.int32).cuda(), prefilter=prefilter)
+        assert lb.result() == want, (k, prefilter)
+    # and without a rank array the image index is the tie-break key
+    want = leaderboard_ref.leaderboard(probs_t.numpy(), pred_t.numpy(), k, list(range(N)))
+    lb = eng_mod.Leaderboard(C, k, "cuda:0")
+    lb.update(probs_t.cuda(), pred_t.to(torch.int32).cuda(), None, prefilter=True)
+    assert lb.result() == want, k
+
+
+def test_leaderboard_sharded_handoff_large_k(eng_mod, sim):
+    """Hand-off of set-mode boards (GRIP's late iterations, k ≈ N/C): every shard's scan call ends by restoring the
+    list order, the next shard resumes from it — identical to one scan and to the oracle."""
+    N, C, k = 16000, 18, 700
+    f, t = synth.pool(N, C, peaked=0.1)
+    F, T = f.half().cuda(), t.half().cuda()
+    rank_np = synth.path_ranks(N)
+    rank = torch.from_numpy(rank_np).to(torch.int32).cuda()
+    one = eng_mod.Leaderboard(C, k, "cuda:0")
+    pred, _, probs = one.scan(F, T, 100.0, rank=rank, want_probs=True)
+    want = one.result()
+    assert want == leaderboard_ref.leaderboard(probs.cpu().numpy(), pred.cpu().numpy(), k, rank_np)
+    for shards in (2, 5):
+        bounds = [N * s // shards for s in range(shards + 1)]
+        state = None
+        for s in range(shards):
+            lb = eng_mod.Leaderboard(C, k, "cuda:0", state=state)
+            lb.scan(F[bounds[s]:bounds[s + 1]], T, 100.0, idx0=bounds[s], rank=rank)
+            state = lb.state.clone()
+        assert lb.result() == want, shards
 
 
 def test_leaderboard_sharded_handoff_is_identical(eng_mod, sim):
