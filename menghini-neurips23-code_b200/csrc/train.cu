@@ -111,18 +111,33 @@ text_unit_kernel(const float* __restrict__ T, float* __restrict__ tn, float* __r
   if (lane == 0) inv_norm[row] = inv;
 }
 
-// One block (512 threads) per prompt j: dTn[j,d] = scale·Σ_i dz[i,j]·I[i,d] summed over the rows in index
-// order, then back through the normalisation: dT_j = (dTn_j − tn_j·⟨tn_j, dTn_j⟩)/|T_j|.  Block 0 also adds
-// up the per-row losses in index order.
+// dTn[j,d] = scale·Σ_i dz[i,j]·I[i,d] in two deterministic stages: block (j, s) adds up the rows of segment s
+// (kCeSeg consecutive rows, index order) into part[s][j][d]; ce_text_grad_kernel then adds the segments in index
+// order.  (One block per prompt walking all B rows was 256 µs at B = 1966, C = 10: ten CTAs, a serial chain of
+// dependent loads each.)
+constexpr int kCeSeg = 64;
 template <typename TI>
 __global__ void __launch_bounds__(512)
-ce_text_grad_kernel(const float* __restrict__ dlogits, const TI* __restrict__ imfn, const float* __restrict__ tn,
+ce_text_part_kernel(const float* __restrict__ dlogits, const TI* __restrict__ imfn, int B, int C,
+                    float* __restrict__ part) {
+  const int j = blockIdx.x, s = blockIdx.y, d = threadIdx.x;
+  const int i0 = s * kCeSeg, i1 = min(B, i0 + kCeSeg);
+  float acc = 0.f;
+#pragma unroll 8
+  for (int i = i0; i < i1; ++i) acc = fmaf(__ldg(dlogits + (size_t)i * C + j), to_f32(imfn[(size_t)i * 512 + d]), acc);
+  part[((size_t)s * C + j) * 512 + d] = acc;
+}
+
+// One block (512 threads) per prompt j: dTn_j from the segment partials, then back through the normalisation:
+// dT_j = (dTn_j − tn_j·⟨tn_j, dTn_j⟩)/|T_j|.  Block 0 also adds up the per-row losses in index order.
+__global__ void __launch_bounds__(512)
+ce_text_grad_kernel(const float* __restrict__ part, int nseg, const float* __restrict__ tn,
                     const float* __restrict__ inv_norm, const float* __restrict__ loss_rows, float scale, int B,
                     int C, float* __restrict__ dT, float* __restrict__ loss) {
   __shared__ float red[16];
   const int j = blockIdx.x, d = threadIdx.x;
   float acc = 0.f;
-  for (int i = 0; i < B; ++i) acc = fmaf(dlogits[(size_t)i * C + j], to_f32(imfn[(size_t)i * 512 + d]), acc);
+  for (int s = 0; s < nseg; ++s) acc += part[((size_t)s * C + j) * 512 + d];
   acc *= scale;
   const float t = tn[(size_t)j * 512 + d];
   float dot = warp_sum(t * acc);
@@ -253,8 +268,9 @@ extern "C" int gb_ce_text_grad(gb_ctx* c, const void* imfn16, const float* text,
   if (!imfn16 || !text || !labels || !dtext || B <= 0 || C <= 0)
     return gb_fail(c, GB_ERR_ARG, "ce_text_grad: bad arguments (B=%d C=%d)", B, C);
   cudaStream_t st = (cudaStream_t)stream;
-  // scratch: tn [C,512] | inv_norm [C] | dlogits [B,C] | loss_rows [B]
-  const size_t need = ((size_t)C * 512 + C + (size_t)B * C + B) * 4 + 64;
+  // scratch: tn [C,512] | inv_norm [C] | dlogits [B,C] | loss_rows [B] | segment partials [nseg][C][512]
+  const int nseg = (B + kCeSeg - 1) / kCeSeg;
+  const size_t need = ((size_t)C * 512 + C + (size_t)B * C + B + 16 + (size_t)nseg * C * 512) * 4 + 64;
   int rc = gb_ws_reserve(c, gb_ctx::kWsTrain, need);
   if (rc) return rc;
   float* tn = reinterpret_cast<float*>(c->ws[gb_ctx::kWsTrain]);
@@ -266,8 +282,10 @@ extern "C" int gb_ce_text_grad(gb_ctx* c, const void* imfn16, const float* text,
   ce_rows_kernel<__half><<<(int)(((size_t)B * 32 + 255) / 256), 256, 0, st>>>(
       (const __half*)imfn16, tn, labels, coef, 1.0f / (float)B, logit_scale_exp, B, C, dz, loss_rows, pred);
   GB_LAUNCH_CHECK(c);
-  ce_text_grad_kernel<__half><<<C, 512, 0, st>>>(dz, (const __half*)imfn16, tn, inv_norm, loss_rows,
-                                                 logit_scale_exp, B, C, dtext, loss);
+  float* part = loss_rows + ((B + 3) & ~3);
+  ce_text_part_kernel<__half><<<dim3(C, nseg), 512, 0, st>>>(dz, (const __half*)imfn16, B, C, part);
+  GB_LAUNCH_CHECK(c);
+  ce_text_grad_kernel<<<C, 512, 0, st>>>(part, nseg, tn, inv_norm, loss_rows, logit_scale_exp, B, C, dtext, loss);
   GB_LAUNCH_CHECK(c);
   return GB_OK;
 }
@@ -280,8 +298,10 @@ extern "C" int gb_ce_image_grad(gb_ctx* c, const float* image, const float* text
   if (!image || !text || !labels || (!dimage && !dtext) || B <= 0 || C <= 0)
     return gb_fail(c, GB_ERR_ARG, "ce_image_grad: bad arguments (B=%d C=%d)", B, C);
   cudaStream_t st = (cudaStream_t)stream;
-  // scratch: tn [C,512] | inv_t [C] | in [B,512] | inv_i [B] | dlogits [B,C] | loss_rows [B]
-  const size_t need = ((size_t)C * 512 + C + 4 + (size_t)B * 512 + B + 4 + (size_t)B * C + 4 + B) * 4 + 64;
+  // scratch: tn [C,512] | inv_t [C] | in [B,512] | inv_i [B] | dlogits [B,C] | loss_rows [B] | segment partials
+  const int nseg = (B + kCeSeg - 1) / kCeSeg;
+  const size_t need = ((size_t)C * 512 + C + 4 + (size_t)B * 512 + B + 4 + (size_t)B * C + 4 + B + 16 +
+                       (dtext ? (size_t)nseg * C * 512 : 0)) * 4 + 64;
   int rc = gb_ws_reserve(c, gb_ctx::kWsTrain, need);
   if (rc) return rc;
   float* tn = reinterpret_cast<float*>(c->ws[gb_ctx::kWsTrain]);
@@ -305,7 +325,10 @@ extern "C" int gb_ce_image_grad(gb_ctx* c, const float* image, const float* text
   // the text-side kernel also adds up the per-row losses; without a text gradient a 1-prompt launch of it
   // would not do: run it on all prompts into the scratch tail only when asked, else sum the loss alone
   if (dtext) {
-    ce_text_grad_kernel<float><<<C, 512, 0, st>>>(dz, in, tn, inv_t, loss_rows, logit_scale_exp, B, C, dtext, loss);
+    float* part = loss_rows + ((B + 3) & ~3);
+    ce_text_part_kernel<float><<<dim3(C, nseg), 512, 0, st>>>(dz, in, B, C, part);
+    GB_LAUNCH_CHECK(c);
+    ce_text_grad_kernel<<<C, 512, 0, st>>>(part, nseg, tn, inv_t, loss_rows, logit_scale_exp, B, C, dtext, loss);
     GB_LAUNCH_CHECK(c);
   } else if (loss) {
     loss_sum_kernel<<<1, 512, 0, st>>>(loss_rows, B, loss);
