@@ -121,23 +121,18 @@ im2col_patch32_kernel(const InT* __restrict__ img, __half* __restrict__ out, int
 
 // Same re-index for raw uint8 pixels [B,3,224,224], with the reference's preprocessing tail fused in:
 // torchvision ToTensor (x/255 in fp32) followed by Normalize with CLIP's mean / std ((x − mean)/std,
-// clip.load's `_transform`; used by the reference at data/dataset.py:64-79).  The three fp32 operations
-// are the ones torch performs, in the same order and rounding, so the fp16 operand written here is
-// bit-identical to feeding the host-normalised fp32 tensor — at a quarter of the host→device bytes.
-// A pixel has 256 possible values per channel, so each block first tabulates the 3 x 256 results (with
-// exactly those IEEE operations) in shared memory and then only looks pixels up — the per-pixel
-// divisions made the kernel ALU-bound at a third of the HBM rate.
+// clip.load's `_transform`; used by the reference at data/dataset.py:64-79), rounded to the fp16 GEMM operand.
+// A pixel has 256 possible values per channel, so "the same bits as torch's three fp32 operations followed by the
+// fp16 rounding" is a finite statement: fp16(fma(x, a_c, b_c)) with a_c = fp32(1/(255·std_c)), b_c = fp32(−mean_c/std_c)
+// (constants formed in double) gives the identical fp16 value for all 3 × 256 inputs — checked exhaustively
+// (tests/test_tokenizer.py::test_u8_normalise_fma_is_exhaustively_exact on the host, test_uint8_pixels_match_… on
+// the device) — so the kernel needs neither the two IEEE divisions per pixel (ALU-bound at a third of the HBM rate)
+// nor the per-block shared-memory table it used before (building 768 entries cost more than the 4 KB of pixels the
+// block then looked up, and the random 2-byte lookups conflicted in the banks: 43 % of HBM peak in ncu).
+// byte → float without the quarter-rate I2F: 0x4B000000 | byte is the float 2^23 + byte.
 __global__ void __launch_bounds__(256)
 im2col_patch32_u8_kernel(const uint8_t* __restrict__ img, __half* __restrict__ out, int B) {
   pdl_launch_dependents();
-  __shared__ __half lut[3 * 256];
-  for (int i = threadIdx.x; i < 3 * 256; i += 256) {
-    const int c = i >> 8;
-    const float mean = c == 0 ? 0.48145466f : (c == 1 ? 0.4578275f : 0.40821073f);
-    const float sd = c == 0 ? 0.26862954f : (c == 1 ? 0.26130258f : 0.27577711f);
-    lut[i] = __float2half_rn(__fdiv_rn(__fsub_rn(__fdiv_rn((float)(i & 255), 255.0f), mean), sd));
-  }
-  __syncthreads();
   // one thread per 16 consecutive kx: total = B*3*224*14 groups
   const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)B * 3 * 224 * 14;
@@ -146,13 +141,22 @@ im2col_patch32_u8_kernel(const uint8_t* __restrict__ img, __half* __restrict__ o
   const int y = (gid / 14) % 224;
   const int c = (gid / (14 * 224)) % 3;
   const int b = gid / (14 * 224 * 3);
+  constexpr float kA0 = (float)(1.0 / (255.0 * (double)0.26862954f)), kB0 = (float)(-(double)0.48145466f / (double)0.26862954f);
+  constexpr float kA1 = (float)(1.0 / (255.0 * (double)0.26130258f)), kB1 = (float)(-(double)0.4578275f / (double)0.26130258f);
+  constexpr float kA2 = (float)(1.0 / (255.0 * (double)0.27577711f)), kB2 = (float)(-(double)0.40821073f / (double)0.27577711f);
+  const float ka = c == 0 ? kA0 : (c == 1 ? kA1 : kA2);
+  const float kb = c == 0 ? kB0 : (c == 1 ? kB1 : kB2);
   const uint4 u = __ldg(reinterpret_cast<const uint4*>(img + (((size_t)b * 3 + c) * 224 + y) * 224 + x16 * 16));
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-  const __half* l = lut + c * 256;
   uint4 o[2];
-  __half* h = reinterpret_cast<__half*>(o);
+  __half2* h = reinterpret_cast<__half2*>(o);
 #pragma unroll
-  for (int t = 0; t < 16; ++t) h[t] = l[(w[t >> 2] >> ((t & 3) * 8)) & 0xffu];
+  for (int t = 0; t < 8; ++t) {
+    const uint32_t word = w[t >> 1];
+    const float f0 = __uint_as_float(__byte_perm(word, 0x4B000000u, (t & 1) ? 0x7652 : 0x7650)) - 8388608.0f;
+    const float f1 = __uint_as_float(__byte_perm(word, 0x4B000000u, (t & 1) ? 0x7653 : 0x7651)) - 8388608.0f;
+    h[t] = __floats2half2_rn(__fmaf_rn(f0, ka, kb), __fmaf_rn(f1, ka, kb));
+  }
   const int py = y >> 5, ky = y & 31, px = (x16 * 16) >> 5, kx = (x16 * 16) & 31;
   uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)b * 49 + py * 7 + px) * 3072 + c * 1024 + ky * 32 + kx);
   dst[0] = o[0];
@@ -167,6 +171,11 @@ im2col_patch32_u8_kernel(const uint8_t* __restrict__ img, __half* __restrict__ o
 //   x[b*L + l] = ln_pre(row)            (fp16 residual stream)
 // Reference: models/clip_encoders.py:135-157 (prefix inserted after pos-emb, before ln_pre).
 // ---------------------------------------------------------------------------------------------
+// A warp owns token position l of kAsmRows consecutive images: the positional row (or the prefix row) and the
+// ln_pre affine of its 24 columns per lane are read ONCE and stay in registers, so per row only the 1.5 KB patch row
+// comes in and the 1.5 KB token row goes out (one warp per row re-read 9 KB of parameters per row through L2: 17 % of
+// the HBM peak in ncu).  Per-row arithmetic is unchanged.
+constexpr int kAsmRows = 8;
 __global__ void __launch_bounds__(256)
 vit_assemble_lnpre_kernel(const __half* __restrict__ patch, const float* __restrict__ cls,
                           const float* __restrict__ pos, const float* __restrict__ prefix, int P,
@@ -175,40 +184,65 @@ vit_assemble_lnpre_kernel(const __half* __restrict__ patch, const float* __restr
   pdl_launch_dependents();
   constexpr int D = 768, V = 3;
   const int L = 50 + P;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= B * L) return;
-  const int b = warp / L, l = warp % L;
-  float f[V * 8];
+  const int chunks = (B + kAsmRows - 1) / kAsmRows;
+  if (wid >= chunks * L) return;
+  const int l = wid % L, b0 = (wid / L) * kAsmRows;
+  const int b1 = min(B, b0 + kAsmRows);
+  // what every image shares at this position: the additive row and the affine
+  float base[V * 8], gm[V * 8], bt[V * 8];
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     const int col = (v * 32 + lane) * 8;
-    float a[8];
-    if (l >= 1 && l <= P) {
-      const float4 p0 = __ldg(reinterpret_cast<const float4*>(prefix + (size_t)(l - 1) * D + col));
-      const float4 p1 = __ldg(reinterpret_cast<const float4*>(prefix + (size_t)(l - 1) * D + col + 4));
-      a[0] = p0.x; a[1] = p0.y; a[2] = p0.z; a[3] = p0.w; a[4] = p1.x; a[5] = p1.y; a[6] = p1.z; a[7] = p1.w;
-    } else {
-      const int pl = (l == 0) ? 0 : l - P;  // positional row
-      const float4 p0 = __ldg(reinterpret_cast<const float4*>(pos + (size_t)pl * D + col));
-      const float4 p1 = __ldg(reinterpret_cast<const float4*>(pos + (size_t)pl * D + col + 4));
-      a[0] = p0.x; a[1] = p0.y; a[2] = p0.z; a[3] = p0.w; a[4] = p1.x; a[5] = p1.y; a[6] = p1.z; a[7] = p1.w;
-      if (l == 0) {
-        const float4 c0 = __ldg(reinterpret_cast<const float4*>(cls + col));
-        const float4 c1 = __ldg(reinterpret_cast<const float4*>(cls + col + 4));
-        a[0] += c0.x; a[1] += c0.y; a[2] += c0.z; a[3] += c0.w; a[4] += c1.x; a[5] += c1.y; a[6] += c1.z; a[7] += c1.w;
-      } else {
-        const uint4 u = *reinterpret_cast<const uint4*>(patch + ((size_t)b * 49 + (l - 1 - P)) * D + col);
-        const __half2* h = reinterpret_cast<const __half2*>(&u);
+    const float* src = (l >= 1 && l <= P) ? prefix + (size_t)(l - 1) * D : pos + (size_t)((l == 0) ? 0 : l - P) * D;
+    const float4 p0 = __ldg(reinterpret_cast<const float4*>(src + col));
+    const float4 p1 = __ldg(reinterpret_cast<const float4*>(src + col + 4));
+    float* a = base + v * 8;
+    a[0] = p0.x; a[1] = p0.y; a[2] = p0.z; a[3] = p0.w; a[4] = p1.x; a[5] = p1.y; a[6] = p1.z; a[7] = p1.w;
+    if (l == 0) {
+      const float4 c0 = __ldg(reinterpret_cast<const float4*>(cls + col));
+      const float4 c1 = __ldg(reinterpret_cast<const float4*>(cls + col + 4));
+      a[0] += c0.x; a[1] += c0.y; a[2] += c0.z; a[3] += c0.w; a[4] += c1.x; a[5] += c1.y; a[6] += c1.z; a[7] += c1.w;
+    }
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+    const float4 e0 = __ldg(reinterpret_cast<const float4*>(beta + col)), e1 = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
+    float* gg = gm + v * 8;
+    float* bb = bt + v * 8;
+    gg[0] = g0.x; gg[1] = g0.y; gg[2] = g0.z; gg[3] = g0.w; gg[4] = g1.x; gg[5] = g1.y; gg[6] = g1.z; gg[7] = g1.w;
+    bb[0] = e0.x; bb[1] = e0.y; bb[2] = e0.z; bb[3] = e0.w; bb[4] = e1.x; bb[5] = e1.y; bb[6] = e1.z; bb[7] = e1.w;
+  }
+  const bool has_patch = l > P;
+  uint4 nxt[V];   // the next image's patch row is requested before this one is worked on
+  if (has_patch) {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float2 e = __half22float2(h[t]);
-          a[2 * t] += e.x; a[2 * t + 1] += e.y;
-        }
+    for (int v = 0; v < V; ++v)
+      nxt[v] = *reinterpret_cast<const uint4*>(patch + ((size_t)b0 * 49 + (l - 1 - P)) * D + (v * 32 + lane) * 8);
+  }
+  for (int b = b0; b < b1; ++b) {
+  const int warp = b * L + l;   // token row
+  float f[V * 8];
+  uint4 cur[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) cur[v] = nxt[v];
+  if (has_patch && b + 1 < b1) {
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+      nxt[v] = *reinterpret_cast<const uint4*>(patch + ((size_t)(b + 1) * 49 + (l - 1 - P)) * D + (v * 32 + lane) * 8);
+  }
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[v * 8 + i] = base[v * 8 + i];
+    if (has_patch) {
+      const uint4 u = cur[v];
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 e = __half22float2(h[t]);
+        f[v * 8 + 2 * t] += e.x; f[v * 8 + 2 * t + 1] += e.y;
       }
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) f[v * 8 + i] = a[i];
   }
   float s = 0.f;
 #pragma unroll
@@ -226,9 +260,8 @@ vit_assemble_lnpre_kernel(const __half* __restrict__ patch, const float* __restr
     __half2* h = reinterpret_cast<__half2*>(&u);
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-      const int c0 = col + 2 * t;
-      const float o0 = (f[v * 8 + 2 * t] - mean) * rstd * __ldg(gamma + c0) + __ldg(beta + c0);
-      const float o1 = (f[v * 8 + 2 * t + 1] - mean) * rstd * __ldg(gamma + c0 + 1) + __ldg(beta + c0 + 1);
+      const float o0 = (f[v * 8 + 2 * t] - mean) * rstd * gm[v * 8 + 2 * t] + bt[v * 8 + 2 * t];
+      const float o1 = (f[v * 8 + 2 * t + 1] - mean) * rstd * gm[v * 8 + 2 * t + 1] + bt[v * 8 + 2 * t + 1];
       h[t] = __floats2half2_rn(o0, o1);
       const float2 r = __half22float2(h[t]);
       f[v * 8 + 2 * t] = r.x;  // keep the stored (rounded) values for the statistics below
@@ -245,6 +278,7 @@ vit_assemble_lnpre_kernel(const __half* __restrict__ patch, const float* __restr
     const float r2 = rsqrtf(warp_sum(st_sq) * (1.0f / D) + eps);
     if (lane == 0) *reinterpret_cast<float2*>(stats + (size_t)warp * 2) = make_float2(m2 * r2, r2);
   }
+  }  // images of this warp
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -543,7 +577,7 @@ int gb_launch_vit_assemble(gb_ctx* c, const void* patch, const float* cls, const
                            const float* prefix, int P, const float* gamma, const float* beta,
                            void* x, int B, cudaStream_t st, float* stats) {
   if (B <= 0) return GB_OK;
-  vit_assemble_lnpre_kernel<<<warps_grid((long long)B * (50 + P)), 256, 0, st>>>(
+  vit_assemble_lnpre_kernel<<<warps_grid((long long)((B + kAsmRows - 1) / kAsmRows) * (50 + P)), 256, 0, st>>>(
       (const __half*)patch, cls, pos, prefix, P, gamma, beta, (__half*)x, B, 1e-5f, stats);
   GB_LAUNCH_CHECK(c);
   return GB_OK;

@@ -131,3 +131,21 @@ def test_preprocess_matches_torchvision_clip_transform(size):
     assert got.shape == want.shape == (3, 224, 224)
     assert torch.allclose(got, want, atol=1e-6, rtol=0)
     assert torch.equal(clip.normalize_u8(clip.preprocess_u8()(img)), got)
+
+
+def test_u8_normalise_fma_is_exhaustively_exact():
+    """csrc/rowops.cu im2col_patch32_u8_kernel: fp16(fma(x, a_c, b_c)) with a_c = fp32(1/(255·std_c)),
+    b_c = fp32(−mean_c/std_c) (constants formed in double) is, for every one of the 3 × 256 (channel, pixel value)
+    pairs, the same fp16 number as torch's ToTensor (x/255) → Normalize ((· − mean)/std) in fp32 followed by the
+    rounding to the fp16 GEMM operand."""
+    import numpy as np
+    import torch
+    x = torch.arange(256, dtype=torch.float32)
+    for mean, std in ((0.48145466, 0.26862954), (0.4578275, 0.26130258), (0.40821073, 0.27577711)):
+        m, s = torch.tensor(mean, dtype=torch.float32), torch.tensor(std, dtype=torch.float32)
+        want = ((x / 255.0 - m) / s).half()                       # torch's own operation order, then fp16
+        a = np.float32(1.0 / (255.0 * float(s)))
+        b = np.float32(-float(m) / float(s))
+        # fp32 fma: the double product of two fp32 numbers is exact, the double sum is rounded once more to fp32
+        got = (x.numpy().astype(np.float64) * np.float64(a) + np.float64(b)).astype(np.float32)
+        assert np.array_equal(got.astype(np.float16).view(np.uint16), want.numpy().view(np.uint16)), (mean, std)
