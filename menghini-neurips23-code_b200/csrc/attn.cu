@@ -462,9 +462,13 @@ int gb_launch_attn_fwd(gb_ctx* c, const void* qkv, void* out, int B, int L, int 
   }
 }
 
+int gb_launch_attn_bwd_tc(gb_ctx* c, const void* qkv, const void* dout, void* dqkv, int B, int L, int D, int causal,
+                          cudaStream_t st);
+
 int gb_launch_attn_bwd(gb_ctx* c, const void* qkv, const void* dout, void* dqkv, int B, int L,
                        int D, int causal, cudaStream_t st) {
   if (B <= 0) return GB_OK;
+  if (gb_attn_tc_enabled() && L <= 96 && D % kDh == 0) return gb_launch_attn_bwd_tc(c, qkv, dout, dqkv, B, L, D, causal, st);
   if (L < 1 || L > 96 || D % kDh != 0)
     return gb_fail(c, GB_ERR_ARG, "attention: L=%d (1..96) D=%d (multiple of 64) unsupported", L, D);
   const int lp = (L + 15) / 16;

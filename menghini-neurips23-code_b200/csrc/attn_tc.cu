@@ -61,11 +61,25 @@ __device__ __forceinline__ void wg_barrier(int id) {
   asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
 }
 
-template <int G>
+// 16 consecutive accumulator columns into 16 registers (no wait: issued back to back, one wait for the row)
+__device__ __forceinline__ void at_tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// G samples per item; NB = ceil(L / 16): blocks of 16 key columns a query row looks at (the soft-max and the P·V chain
+// skip the rest: at L = 66 that is 80 of 128 columns)
+template <int G, int NB>
 __global__ void __launch_bounds__(kAtThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmO,
                    const AttnTcParams p) {
-  constexpr int kCols = G == 2 ? 64 : 128;    // key columns a query row looks at
+  constexpr int kCols = 16 * NB;              // key columns a query row looks at
+  static_assert(G == 2 ? NB <= 4 : (NB > 4 && NB <= 8), "G = 2 packs samples of up to 64 rows");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -149,7 +163,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         const uint32_t va = smem_u32(smem_qkv + s * kAtStageBytes + 2 * kAtTile);
         const uint32_t tmem_o = tmem_base + w * 256 + 128;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {             // 16 keys per instruction
+        for (int kk = 0; kk < 8; ++kk) {             // 16 keys per instruction; blocks without a key are skipped
+          if ((G == 2 ? (kk & 3) : kk) >= NB) continue;
           const uint64_t adesc = umma_desc_k_sw128(pa + (kk >> 2) * kAtTile) + 2 * (kk & 3);
           const uint64_t bdesc = umma_desc_mn_sw128(va + kk * 2048);
           umma_f16(tmem_o, adesc, bdesc, idesc_pv, kk != 0);
@@ -197,7 +212,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       tc_fence_after();
       uint32_t v[kCols];
 #pragma unroll
-      for (int c = 0; c < kCols / 64; ++c) tmem_ld_32x64(t_s + 64 * c, v + 64 * c);
+      for (int c = 0; c < NB; ++c) at_tmem_ld16(t_s + 16 * c, v + 16 * c);
       tmem_ld_wait();
       // scores in log2 units: (q·k / 8)·log2(e); key kj is visible when kj < L (and kj ≤ qi under the causal mask)
       const int k_end = causal ? min(L, qi + 1) : L;
@@ -219,9 +234,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       // P goes where this warpgroup's previous output tile was staged: its TMA stores must have read it
       if (threadIdx.x == 128 + w * 128) tma_store_wait_read<0>();
       wg_barrier(1 + w);
-      if (G == 2 && j == 1) {   // the staging tile covered atom 0 of every row: sample 1 has no keys there
+      // the staging tile covered atom 0 of every row: what this row does not write there below must be zero again
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) sts128(p_row + ((c8 ^ (r & 7)) << 4), make_uint4(0, 0, 0, 0));
+      for (int c8 = 0; c8 < 8; ++c8) {
+        const bool mine = G == 2 ? (j == 0 && c8 < 2 * NB) : true;
+        if (!mine) sts128(p_row + ((c8 ^ (r & 7)) << 4), make_uint4(0, 0, 0, 0));
       }
 #pragma unroll
       for (int c8 = 0; c8 < kCols / 8; ++c8) {
@@ -273,16 +290,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   }
 }
 
-template <int G>
+template <int G, int NB>
 int launch_tc(gb_ctx* c, const CUtensorMap& tmQKV, const CUtensorMap& tmO, const AttnTcParams& p, cudaStream_t st) {
   static bool done[16] = {false};
   if (!done[c->device & 15]) {
-    GB_CUDA(c, cudaFuncSetAttribute(attn_fwd_tc_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+    GB_CUDA(c, cudaFuncSetAttribute(attn_fwd_tc_kernel<G, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
     done[c->device & 15] = true;
   }
   const int sms = gb_gemm_sms(c);
   const int grid = p.n_items < sms ? p.n_items : sms;
-  attn_fwd_tc_kernel<G><<<grid, kAtThreads, kAtSmem, st>>>(tmQKV, tmO, p);
+  attn_fwd_tc_kernel<G, NB><<<grid, kAtThreads, kAtSmem, st>>>(tmQKV, tmO, p);
   GB_LAUNCH_CHECK(c);
   return GB_OK;
 }
@@ -315,5 +332,14 @@ int gb_launch_attn_fwd_tc(gb_ctx* c, const void* qkv, void* out, int B, int L, i
   p.B = B; p.L = L; p.H = D / 64; p.D = D; p.causal = causal;
   p.n_groups = (B + G - 1) / G;
   p.n_items = p.n_groups * p.H;
-  return G == 2 ? launch_tc<2>(c, tmQKV, tmO, p, st) : launch_tc<1>(c, tmQKV, tmO, p, st);
+  switch ((L + 15) / 16) {
+    case 1: return launch_tc<2, 1>(c, tmQKV, tmO, p, st);
+    case 2: return launch_tc<2, 2>(c, tmQKV, tmO, p, st);
+    case 3: return launch_tc<2, 3>(c, tmQKV, tmO, p, st);
+    case 4: return launch_tc<2, 4>(c, tmQKV, tmO, p, st);
+    case 5: return launch_tc<1, 5>(c, tmQKV, tmO, p, st);
+    case 6: return launch_tc<1, 6>(c, tmQKV, tmO, p, st);
+    case 7: return launch_tc<1, 7>(c, tmQKV, tmO, p, st);
+    default: return launch_tc<1, 8>(c, tmQKV, tmO, p, st);
+  }
 }

@@ -43,7 +43,7 @@ def _worker(rank, world, port, n, c, k, q):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.parametrize("n,c,k", [(20000, 45, 16), (8000, 100, 16)])
+@pytest.mark.parametrize("n,c,k", [(20000, 45, 16), (8000, 100, 16), (16000, 18, 700)])  # the last: set-mode boards (GRIP-sized k)
 def test_sharded_scan_nccl_matches_single_gpu(n, c, k):
     import torch.multiprocessing as mp
 

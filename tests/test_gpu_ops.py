@@ -136,7 +136,9 @@ def test_attention_forward(ctx, B, L, D, causal):
 
 
 @pytest.mark.parametrize("B,L,D,causal", [(2, 50, 768, 0), (3, 66, 768, 0), (3, 77, 512, 1),
-                                          (4, 24, 512, 1), (2, 9, 512, 1), (1, 96, 768, 0)])
+                                          (4, 24, 512, 1), (2, 9, 512, 1), (1, 96, 768, 0),
+                                          (301, 50, 768, 0), (151, 66, 768, 0), (75, 77, 512, 1), (2, 96, 512, 1),
+                                          (3, 80, 768, 0), (65, 64, 768, 1), (333, 11, 512, 1), (5, 33, 768, 0)])
 def test_attention_backward(ctx, B, L, D, causal):
     g = torch.Generator(device="cuda").manual_seed(100 + L)
     qkv = torch.randn(B * L, 3 * D, device="cuda", generator=g).half()

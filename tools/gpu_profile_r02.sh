@@ -13,22 +13,22 @@ cap() {  # name regex skip cmd…
   $NCU --set full --import-source on --kernel-name-base demangled -k regex:"$re" --launch-skip $skip -c 1 -f -o $O/${TAG}_$name "$@" > $O/${TAG}_cap_$name.log 2>&1
 }
 if [ "$2" = "gemm" ]; then
-cap gemm_fc 'gemm_f16_tcgen05_2cta_kernel<1, 4>' 30 $COOP
-cap gemm_resid 'gemm_f16_tcgen05_2cta_kernel<1, 2>' 60 $COOP
-cap gemm_act2 'gemm_f16_tcgen05_2cta_kernel<1, 5>' 30 $VPT
-cap gemm_dgrad 'gemm_f16_tcgen05_2cta_kernel<1, 0>' 60 $VPT
+cap gemm_fc '2cta_kernel<.int.1, .int.4>' 30 $COOP
+cap gemm_resid '2cta_kernel<.int.1, .int.2>' 60 $COOP
+cap gemm_act2 '2cta_kernel<.int.1, .int.5>' 30 $VPT
+cap gemm_dgrad '2cta_kernel<.int.1, .int.0>' 60 $VPT
 ls -la $O/${TAG}_*.ncu-rep | awk '{print $5, $9}'
 exit 0
 fi
 cap attn_fwd_tc 'attn_fwd_tc_kernel' 30 $COOP
-cap gemm_fc 'gemm_f16_tcgen05_2cta_kernel<1, 4>' 30 $COOP
-cap gemm_resid 'gemm_f16_tcgen05_2cta_kernel<1, 2>' 60 $COOP
+cap gemm_fc '2cta_kernel<.int.1, .int.4>' 30 $COOP
+cap gemm_resid '2cta_kernel<.int.1, .int.2>' 60 $COOP
 cap replay_par 'lb_replay_par_kernel' 3 $COOP
 cap im2col_u8 'im2col_patch32_u8_kernel' 3 $COOP
 cap assemble 'vit_assemble_lnpre_kernel' 3 $COOP
 cap attn_bwd 'attn_bwd_kernel' 30 $VPT
 cap ln_bwd 'layernorm_bwd_kernel' 60 $VPT
-cap gemm_act2 'gemm_f16_tcgen05_2cta_kernel<1, 5>' 30 $VPT
-cap gemm_dgrad 'gemm_f16_tcgen05_2cta_kernel<1, 0>' 60 $VPT
+cap gemm_act2 '2cta_kernel<.int.1, .int.5>' 30 $VPT
+cap gemm_dgrad '2cta_kernel<.int.1, .int.0>' 60 $VPT
 cap prefix_grad 'prefix_grad_kernel' 2 $VPT
 ls -la $O/${TAG}_*.ncu-rep | awk '{print $5, $9}'
