@@ -757,25 +757,35 @@ def run_b200(a, rank, local_rank, world):
     main = torch.cuda.current_stream()
     side = side_stream if overlap else main_stream
 
+    NBUF = 3   # device staging buffers: a copy never has to wait for the side-stream tail of the step before last
+
     def run_e2e(host_img, dev_bufs):
-        copied = [torch.cuda.Event(), torch.cuda.Event()]
-        consumed = [torch.cuda.Event(), torch.cuda.Event()]
-        consumed_side = [torch.cuda.Event(), torch.cuda.Event()]  # labels are read by the side stream
+        # Three device buffers (two pinned host batches feed them alternately).  With two, the copy of batch i+1 had to wait
+        # until the side stream had finished step i-1 — whose text chain and scan run BESIDE image tower i on the few SMs
+        # the tower leaves free and end late in it — so the 296 MB copy finished just after tower i and tower i+1 waited
+        # for it (8 % of the step); the copies themselves do not slow the tower (measured with the copy switched off).
+        while len(dev_bufs) < NBUF:
+            dev_bufs.append(torch.empty_like(dev_bufs[0]))
+        labs = [torch.empty_like(dev_lab[0]) for _ in range(NBUF)]
+        copied = [torch.cuda.Event() for _ in range(NBUF)]
+        consumed = [torch.cuda.Event() for _ in range(NBUF)]
+        consumed_side = [torch.cuda.Event() for _ in range(NBUF)]  # labels are read by the side stream
 
         def prefetch(i):
-            b = i % 2
+            b = i % NBUF
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(consumed[b])
                 copy_stream.wait_event(consumed_side[b])
-                dev_bufs[b].copy_(host_img[b], non_blocking=True)
-                dev_lab[b].copy_(host_labels[b], non_blocking=True)
+                if os.environ.get("GB_E2E_DIAG_NOCOPY") != "1":   # diagnosis only: what the copies themselves cost
+                    dev_bufs[b].copy_(host_img[i % 2], non_blocking=True)
+                labs[b].copy_(host_labels[i % 2], non_blocking=True)
                 copied[b].record(copy_stream)
 
         def e2e_step(i):
-            b = i % 2
+            b = i % NBUF
             prefetch(i + 1)               # next batch streams in while this one computes
             main.wait_event(copied[b])
-            loss = step(dev_bufs[b], dev_lab[b])
+            loss = step(dev_bufs[b], labs[b])
             consumed[b].record(main)
             with torch.cuda.stream(side):
                 consumed_side[b].record(side)
@@ -784,7 +794,7 @@ def run_b200(a, rank, local_rank, world):
             # the caller reads loss / predictions every step: with the text chain overlapped the values read
             # here are those of the previous step (its side-stream work is what we wait for)
             if overlap:
-                if state.get("prev_done") is not None:
+                if state.get("prev_done") is not None and os.environ.get("GB_E2E_DIAG_NOSYNC") != "1":
                     state["prev_done"].synchronize()
                 state["prev_done"] = torch.cuda.Event()
                 state["prev_done"].record(side)
@@ -793,7 +803,7 @@ def run_b200(a, rank, local_rank, world):
 
         join()
         torch.cuda.synchronize()
-        for b in range(2):
+        for b in range(NBUF):
             consumed[b].record(main)
             consumed_side[b].record(main)
         prefetch(0)
@@ -809,7 +819,7 @@ def run_b200(a, rank, local_rank, world):
     d2h = 4 + B * 4
     # the same with the fp32 tensors the reference's DataLoader yields (4x the bytes over PCIe)
     host_f32 = [clip.normalize_u8(h).pin_memory() for h in host]
-    dev_f32 = [torch.empty(B, 3, 224, 224, device=dev) for _ in range(2)]
+    dev_f32 = [torch.empty(B, 3, 224, 224, device=dev) for _ in range(NBUF)]
     ms_e2e_f32 = run_e2e(host_f32, dev_f32)
     e2e_f32 = {"value": a.steps * B * world / (ms_e2e_f32 / 1e3), "unit": "images/s",
                "ms_per_step": ms_e2e_f32 / a.steps, "h2d_bytes_per_step": B * 3 * 224 * 224 * 4 + B * 8,
