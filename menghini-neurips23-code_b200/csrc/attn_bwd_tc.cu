@@ -28,6 +28,21 @@
 
 using namespace gb;
 
+// Optional stall accounting (build with -DGB_ATTN_STALLS; read back with gb_debug_attn_stalls): clocks per role spent
+// waiting on each barrier, summed over CTAs.  [0] MMA: operands, [1] MMA: S/dP free, [2] MMA: P/dS ready, [3] MMA: outputs
+// free, [4] MMA total; [5] soft-max wg: S/dP complete, [6] its P/dS region free, [7] its total; [8] output wg: outputs
+// complete, [9] its store-read wait, [10] its total; [11] producer: free stage; [12] items.
+#ifdef GB_ATTN_STALLS
+__device__ unsigned long long g_attn_stalls[16];
+#define AB_T(t) const long long t = clock64()
+#define AB_ADD(i, t) atomicAdd(&g_attn_stalls[i], (unsigned long long)(clock64() - t))
+#define AB_INC(i) atomicAdd(&g_attn_stalls[i], 1ull)
+#else
+#define AB_T(t)
+#define AB_ADD(i, t)
+#define AB_INC(i)
+#endif
+
 namespace {
 
 constexpr int kAbStages = 2;
@@ -35,7 +50,8 @@ constexpr int kAbTile = 128 * 128;             // one 128-row × 64-half tile, b
 constexpr int kAbStageBytes = 4 * kAbTile;     // Q | K | V | dO
 constexpr int kAbPBytes = 2 * kAbTile;         // P (and dS): two 64-key atoms of 128 rows
 constexpr int kAbThreads = 128 + 2 * 128;
-constexpr int kAbSmem = kAbStages * kAbStageBytes + 2 * kAbPBytes + 1024 + 256;
+constexpr int kAbStagingTiles = 2;             // fp16 output staging, ping-pong (the third stage of inputs does not fit)
+constexpr int kAbSmem = kAbStages * kAbStageBytes + 2 * kAbPBytes + kAbStagingTiles * kAbTile + 1024 + 256;
 constexpr uint32_t kColS = 0, kColdP = 128, kColdQ = 256, kColdK = 320, kColdV = 384;
 
 struct AttnBwdParams {
@@ -87,14 +103,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   uint8_t* smem_in = smem;                                        // [stage][Q|K|V|dO][128][128 B]
   uint8_t* smem_p = smem_in + kAbStages * kAbStageBytes;          // [atom][128][128 B]
   uint8_t* smem_ds = smem_p + kAbPBytes;                          // [atom][128][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_ds + kAbPBytes);
+  uint8_t* smem_stg = smem_ds + kAbPBytes;                        // [kAbStagingTiles][128][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stg + kAbStagingTiles * kAbTile);
   uint64_t* full_bar = bars;                    // [kAbStages]
   uint64_t* empty_bar = bars + kAbStages;       // [kAbStages]
   uint64_t* sdp_full = bars + 2 * kAbStages;    // S and dP complete
   uint64_t* sdp_free = sdp_full + 1;            // S and dP read out of TMEM
   uint64_t* pds_ready = sdp_free + 1;           // P and dS in shared memory
-  uint64_t* pds_free = pds_ready + 1;           // P/dS region (= output staging) free again
-  uint64_t* out_full = pds_free + 1;            // dQ, dK, dV complete
+  uint64_t* out_full = pds_ready + 1;           // dQ, dK, dV complete (and with them P, dS dead)
   uint64_t* out_free = out_full + 1;            // dQ, dK, dV read out of TMEM
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(out_free + 1);
 
@@ -110,7 +126,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     mbar_init(sdp_full, 1);
     mbar_init(sdp_free, 128);
     mbar_init(pds_ready, 128);
-    mbar_init(pds_free, 1);
     mbar_init(out_full, 1);
     mbar_init(out_free, 128);
     fence_barrier_init();
@@ -145,7 +160,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         const uint32_t ph = (it / kAbStages) & 1;
         const int grp = item / H, h = item % H;
         const int n_s = min(G, p.B - grp * G);
-        mbar_wait(&empty_bar[s], ph ^ 1);
+        { AB_T(t0); mbar_wait(&empty_bar[s], ph ^ 1); AB_ADD(11, t0); }
         mbar_expect_tx(&full_bar[s], 4u * n_s * L * 128u);
         uint8_t* st = smem_in + s * kAbStageBytes;
         for (int j = 0; j < n_s; ++j) {
@@ -163,26 +178,28 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       constexpr uint32_t idesc_t = umma_idesc_f16(128, 64) | (1u << 15) | (1u << 16);     // A, B MN-major
       constexpr uint32_t idesc_q = umma_idesc_f16(128, 64) | (1u << 16);                  // A K-major, B MN-major
       const uint32_t pa = smem_u32(smem_p), da = smem_u32(smem_ds);
-      int it = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+      const int n_mine = blockIdx.x < p.n_items ? (p.n_items - 1 - blockIdx.x) / (int)gridDim.x + 1 : 0;
+      AB_T(t_mma);
+      // first phase of item `it`: S = Q·Kᵀ and dP = dO·Vᵀ into their TMEM columns
+      auto issue_sdp = [&](int it) {
         const int s = it % kAbStages;
-        const uint32_t ph = (it / kAbStages) & 1;
         const uint32_t base = smem_u32(smem_in + s * kAbStageBytes);
-        const uint32_t qa = base, ka = base + kAbTile, va = base + 2 * kAbTile, oa = base + 3 * kAbTile;
-        mbar_wait(&full_bar[s], ph);
-        mbar_wait(sdp_free, (it & 1) ^ 1);          // the previous item's S / dP have been read
+        { AB_T(t0); mbar_wait(&full_bar[s], (it / kAbStages) & 1); AB_ADD(0, t0); }
+        { AB_T(t0); mbar_wait(sdp_free, (it & 1) ^ 1); AB_ADD(1, t0); }   // the previous item's S / dP have been read
         tc_fence_after();
-        {
-          const uint64_t aq = umma_desc_k_sw128(qa), bk = umma_desc_k_sw128(ka);
-          const uint64_t ao = umma_desc_k_sw128(oa), bv = umma_desc_k_sw128(va);
+        const uint64_t aq = umma_desc_k_sw128(base), bk = umma_desc_k_sw128(base + kAbTile);
+        const uint64_t ao = umma_desc_k_sw128(base + 3 * kAbTile), bv = umma_desc_k_sw128(base + 2 * kAbTile);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(tmem_base + kColS, aq + 2 * k, bk + 2 * k, idesc_s, k != 0);
+        for (int k = 0; k < 4; ++k) umma_f16(tmem_base + kColS, aq + 2 * k, bk + 2 * k, idesc_s, k != 0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(tmem_base + kColdP, ao + 2 * k, bv + 2 * k, idesc_s, k != 0);
-        }
+        for (int k = 0; k < 4; ++k) umma_f16(tmem_base + kColdP, ao + 2 * k, bv + 2 * k, idesc_s, k != 0);
         umma_commit(sdp_full);
-        mbar_wait(pds_ready, it & 1);               // P, dS are in shared memory
-        mbar_wait(out_free, (it & 1) ^ 1);          // the previous item's dQ / dK / dV have left TMEM
+      };
+      // second phase of item `it`: dV = Pᵀ·dO, dK = dSᵀ·Q, dQ = dS·K
+      auto issue_out = [&](int it) {
+        const int s = it % kAbStages;
+        const uint32_t base = smem_u32(smem_in + s * kAbStageBytes);
+        const uint32_t qa = base, ka = base + kAbTile, oa = base + 3 * kAbTile;
         tc_fence_after();
         // blocks of 16 rows that hold no token of any sample are skipped (their P / dS rows and columns are zero)
 #pragma unroll
@@ -201,7 +218,26 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         }
         umma_commit(out_full);
         umma_commit(&empty_bar[s]);                 // Q, K, V, dO of this item are no longer needed
+      };
+      // Issue order decided at run time: the second phase of item i as soon as its P / dS are in shared memory, the
+      // first phase of item i+1 as soon as its operands have landed — whichever is ready first.  (In program order
+      // "first phase of i+1, then second phase of i" the second phase waited for a load that, with two input stages,
+      // can only start when the second phase of i−1 has completed; the other way round the soft-max warpgroup idled
+      // through every second phase.)
+      int next_sdp = 0, next_out = 0;
+      while (next_out < n_mine) {
+        if (next_out < next_sdp && mbar_try_wait(pds_ready, next_out & 1) && mbar_try_wait(out_free, (next_out & 1) ^ 1)) {
+          AB_INC(12);
+          issue_out(next_out);
+          ++next_out;
+        } else if (next_sdp < n_mine && next_sdp <= next_out + 1 &&
+                   mbar_try_wait(&full_bar[next_sdp % kAbStages], (next_sdp / kAbStages) & 1) &&
+                   mbar_try_wait(sdp_free, (next_sdp & 1) ^ 1)) {
+          issue_sdp(next_sdp);
+          ++next_sdp;
+        }
       }
+      AB_ADD(4, t_mma);
     }
   } else if (warp >= 4 && warp < 8) {
     // ===================== soft-max / dS warpgroup (thread = query row) =====================
@@ -219,8 +255,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     const bool row_ok = qi < L;                     // padded query rows contribute nothing
     const int k_end = row_ok ? (causal ? min(L, qi + 1) : L) : 0;
     int it = 0;
+    AB_T(t_wg1);
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-      mbar_wait(sdp_full, it & 1);
+      { AB_T(t0); mbar_wait(sdp_full, it & 1); if (threadIdx.x == 128) AB_ADD(5, t0); }
       tc_fence_after();
       uint32_t v[kCols];   // raw scores → log2-domain scores → exponentials → probabilities, in place
       uint32_t dp[kCols];
@@ -257,18 +294,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
           delta = fmaf(pj, __uint_as_float(dp[kj]), delta);
         }
       }
-      // the P / dS tiles double as the previous item's output staging: its TMA stores must have read them
-      mbar_wait(pds_free, (it & 1) ^ 1);
-      // the staging tiles covered every row of both atoms: whatever this row does not write below must be zero
-#pragma unroll
-      for (int c8 = 0; c8 < 16; ++c8) {
-        const bool mine = G == 2 ? ((c8 >> 3) == j && (c8 & 7) < 2 * NB) : c8 < 2 * NB;
-        if (!mine) {
-          const uint32_t off = (c8 >> 3) * kAbTile + (((c8 & 7) ^ (r & 7)) << 4);
-          sts128(p_row + off, make_uint4(0, 0, 0, 0));
-          sts128(ds_row + off, make_uint4(0, 0, 0, 0));
-        }
-      }
+      // the previous item's second phase must have finished reading the P / dS tiles (what a row does not write
+      // below was zeroed at start-up and stays zero: nothing else ever writes these tiles)
+      { AB_T(t0); mbar_wait(out_full, (it & 1) ^ 1); if (threadIdx.x == 128) AB_ADD(6, t0); }
 #pragma unroll
       for (int c8l = 0; c8l < 2 * NB; ++c8l) {                    // 8-key chunks of this row
         uint4 op, od;
@@ -289,22 +317,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       fence_proxy_async();         // generic-proxy writes of P, dS → visible to the tensor core
       mbar_arrive(pds_ready);
     }
+    if (threadIdx.x == 128) AB_ADD(7, t_wg1);
   } else if (warp >= 8) {
     // ===================== output warpgroup (thread = output row) =====================
     reg_alloc<224>();
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    // staging: dQ → P atom 0, dK → P atom 1, dV → dS atom 0 (all dead once the second-phase MMAs have completed)
-    uint8_t* stage_q = smem_p;
-    uint8_t* stage_k = smem_p + kAbTile;
-    uint8_t* stage_v = smem_ds;
     const bool leader = threadIdx.x == 256;
     int it = 0;
+    uint32_t n_store = 0;   // output tiles staged so far: tile n uses staging buffer n & 1
+    AB_T(t_wg2);
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
       const int grp = item / H, h = item % H;
       const int n_s = min(G, p.B - grp * G);
-      mbar_wait(out_full, it & 1);
+      { AB_T(t0); mbar_wait(out_full, it & 1); if (leader) AB_ADD(8, t0); }
       tc_fence_after();
       uint32_t ov[3][64];
 #pragma unroll
@@ -314,9 +341,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       tc_fence_before();
       mbar_arrive(out_free);       // dQ, dK, dV are in registers: the next item's second phase may be issued
 #pragma unroll
-      for (int m = 0; m < 3; ++m) {
+      for (int m = 0; m < 3; ++m, ++n_store) {
+        uint8_t* stg = smem_stg + (n_store & 1) * kAbTile;
+        // the store that last used this staging buffer (two tiles ago) must have read it
+        if (leader) { AB_T(t0); tma_store_wait_read<1>(); AB_ADD(9, t0); }
+        ab_wg_barrier(2);
         const float sc = m == 2 ? 1.0f : 0.125f;
-        const uint32_t o_row = smem_u32(m == 0 ? stage_q : (m == 1 ? stage_k : stage_v)) + r * 128;
+        const uint32_t o_row = smem_u32(stg) + r * 128;
 #pragma unroll
         for (int c8 = 0; c8 < 8; ++c8) {
           uint4 o;
@@ -326,21 +357,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             hh[t] = __floats2half2_rn(__uint_as_float(ov[m][8 * c8 + 2 * t]) * sc, __uint_as_float(ov[m][8 * c8 + 2 * t + 1]) * sc);
           sts128(o_row + ((c8 ^ (r & 7)) << 4), o);
         }
-      }
-      fence_proxy_async();
-      ab_wg_barrier(2);
-      if (leader) {
-        for (int jj = 0; jj < n_s; ++jj) {
-          const int row0 = (grp * G + jj) * L;
-          tma_store_2d(&tmDQKV, stage_q + jj * 8192, h * 64, row0);
-          tma_store_2d(&tmDQKV, stage_k + jj * 8192, D + h * 64, row0);
-          tma_store_2d(&tmDQKV, stage_v + jj * 8192, 2 * D + h * 64, row0);
+        fence_proxy_async();
+        ab_wg_barrier(2);
+        if (leader) {
+          for (int jj = 0; jj < n_s; ++jj)
+            tma_store_2d(&tmDQKV, stg + jj * 8192, m * D + h * 64, (grp * G + jj) * L);
+          tma_store_commit();
         }
-        tma_store_commit();
-        tma_store_wait_read<0>();
-        mbar_arrive(pds_free);
       }
     }
+    if (leader) AB_ADD(10, t_wg2);
     if (leader) tma_store_wait_all<0>();
   }
 
@@ -397,3 +423,15 @@ int gb_launch_attn_bwd_tc(gb_ctx* c, const void* qkv, const void* dout, void* dq
     default: return launch_bwd_tc<1, 6>(c, tmQKV, tmDO, tmDQKV, p, st);
   }
 }
+
+#ifdef GB_ATTN_STALLS
+extern "C" int gb_debug_attn_stalls(unsigned long long* out16, int reset) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return GB_ERR_CUDA;
+  if (out16 && cudaMemcpyFromSymbol(out16, g_attn_stalls, 128) != cudaSuccess) return GB_ERR_CUDA;
+  if (reset) {
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyToSymbol(g_attn_stalls, z, 128) != cudaSuccess) return GB_ERR_CUDA;
+  }
+  return GB_OK;
+}
+#endif
