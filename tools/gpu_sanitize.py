@@ -35,5 +35,15 @@ lb = engine_mod.Leaderboard(45, 4, "cuda:0")
 lb.scan(f16, t16, 100.0, rank=torch.randperm(700).to(torch.int32).cuda())                    # sim + leaderboard
 t200 = torch.nn.functional.normalize(torch.randn(200, 512, device="cuda"), dim=1).half()
 eng.sim_softmax_argmax(f16, t200, 100.0, want_probs=True)                                    # class-chunked path
+# round 2: boards too large for shared memory (set mode + the order-restoring sort), a P = 16 visual prompt (L = 66: the
+# one-sample-per-item instantiations of the tcgen05 attention, forward and backward), image-side CE gradient
+lb2 = engine_mod.Leaderboard(45, 70, "cuda:0")
+lb2.scan(f16, t16, 100.0, rank=torch.randperm(700).to(torch.int32).cuda())
+lb2.result()
+ipm16 = models.ImagePrefixModel(((768 ** -0.5) * torch.randn(16, 768)).cuda(), cie, device="cuda:0")
+with torch.no_grad():
+    tfix = model.encode_text(clip.tokenize([f"a photo of a {c}" for c in classes])).float()
+vstep = training.VPTStep(ipm16, tfix, lr=1e-4)
+vstep.step(img, labels)
 torch.cuda.synchronize()
 print("sanitize pass done: loss", float(loss), "boards", sum(len(b) for b in lb.result()[0:1]))
