@@ -80,8 +80,11 @@ int gb_layernorm_f16(gb_ctx* ctx, const void* x, int ldx, const int32_t* row_idx
 int gb_l2norm512(gb_ctx* ctx, const float* x, void* y16, float* y32, int rows, void* stream);
 
 /* softmax(Q K^T / 8 [+ causal mask]) V per (sample, head) on the packed in-proj output
- * qkv fp16 [B*L, 3D] → out fp16 [B*L, D]; head dim 64, L <= 96.  nn.MultiheadAttention core of
- * clip.model.ResidualAttentionBlock.  _bwd: data gradient dqkv from dout (weights are frozen). */
+ * qkv fp16 [B*L, 3D] → out fp16 [B*L, D]; head dim 64; forward L <= 128, backward L <= 96 (CLIP's sequences are
+ * 50 + P <= 66 vision tokens and <= 77 text tokens).  nn.MultiheadAttention core of
+ * clip.model.ResidualAttentionBlock.  _bwd: data gradient dqkv from dout (weights are frozen).  Both run on the
+ * tcgen05 tensor cores (csrc/attn_tc.cu, csrc/attn_bwd_tc.cu; GB_ATTN_LEGACY=1 in the environment selects the
+ * round-1 mma.sync kernels, L <= 96). */
 int gb_attention_fwd(gb_ctx* ctx, const void* qkv, void* out, int B, int L, int D, int causal,
                      void* stream);
 int gb_attention_bwd(gb_ctx* ctx, const void* qkv, const void* dout, void* dqkv, int B, int L,
