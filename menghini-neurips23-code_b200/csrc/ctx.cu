@@ -76,6 +76,12 @@ int gb_make_tmap_2d_f16(gb_ctx* c, CUtensorMap* out, const void* ptr, uint64_t r
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   if (box_cols != 64 && box_cols != 32) return gb_fail(c, GB_ERR_ARG, "tensor map: box of %u columns", box_cols);
+  const gb_tmap_key key{ptr, rows, cols, ld_elems, box_rows, box_cols};
+  auto hit = c->tmaps.find(key);
+  if (hit != c->tmaps.end()) {
+    *out = hit->second;
+    return GB_OK;
+  }
   CUresult r = c->encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims,
                                strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
@@ -86,6 +92,8 @@ int gb_make_tmap_2d_f16(gb_ctx* c, CUtensorMap* out, const void* ptr, uint64_t r
                    "cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%llu cols=%llu ld=%llu box=%u",
                    (int)r, ptr, (unsigned long long)rows, (unsigned long long)cols,
                    (unsigned long long)ld_elems, box_rows);
+  if (c->tmaps.size() >= 4096) c->tmaps.clear();   // callers that stream through ever-new buffers: bounded memory
+  c->tmaps.emplace(key, *out);
   return GB_OK;
 }
 

@@ -7,6 +7,7 @@
 #include <stdio.h>
 
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/gripb200.h"
@@ -18,11 +19,34 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 struct gb_tower;  // tower.cu
 
+// Key of a 2-D fp16 tensor map: everything cuTensorMapEncodeTiled is given.  A tensor map is pure metadata (address,
+// extents, strides, box, swizzle), so a map encoded once for a key is valid for as long as the key is — whatever has
+// happened to the memory in between.
+struct gb_tmap_key {
+  const void* ptr; uint64_t rows, cols, ld; uint32_t box_rows, box_cols;
+  bool operator==(const gb_tmap_key& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && box_cols == o.box_cols;
+  }
+};
+struct gb_tmap_key_hash {
+  size_t operator()(const gb_tmap_key& k) const {
+    uint64_t h = reinterpret_cast<uint64_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+    h ^= (k.rows + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2));
+    h ^= (k.cols * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2));
+    h ^= (k.ld * 0x165667B19E3779F9ull + (h << 6) + (h >> 2));
+    h ^= ((static_cast<uint64_t>(k.box_rows) << 32 | k.box_cols) + (h << 6) + (h >> 2));
+    return static_cast<size_t>(h);
+  }
+};
+
 struct gb_ctx {
   int device = 0;
   int num_sms = 148;
   std::string err;
   PFN_encodeTiled encode_tiled = nullptr;
+  // cuTensorMapEncodeTiled costs ≈1 µs on the host and a GEMM launch needs three maps: at the reference's BATCH_SIZE
+  // the towers are launch-bound and the same few hundred (buffer, shape) pairs come back every step
+  std::unordered_map<gb_tmap_key, CUtensorMap, gb_tmap_key_hash> tmaps;
   uint64_t launches = 0;  // kernels launched through this ctx (bench.py reports it)
   // workspace owned by the ctx (grown on demand, never inside a timed region after warm-up)
   // One scratch arena per independent call family, so that the image tower, the text tower and the
