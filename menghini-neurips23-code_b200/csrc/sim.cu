@@ -884,7 +884,9 @@ int launch_replay(gb_ctx* c, void* state, int C, int k, const float* rows, int r
     q.diag = diag;
     if (path == 1) lb_replay_par_kernel<false><<<1, kLbpThreads, lb_replay_par_smem_bytes(C, k), st>>>(q);
     else {
-      q.set_groups = lb_set_groups(C, k);
+      // GB_LB_NO_GROUPS=1 (tests): the whole-board scan that boards beyond ≈1.4 M entries fall back to
+      const char* ng = getenv("GB_LB_NO_GROUPS");
+      q.set_groups = (ng && ng[0] == '1') ? 0 : lb_set_groups(C, k);
       const size_t smem = lb_replay_par_smem_bytes(C, k, true) + (size_t)C * q.set_groups * 4 + 32;
       lb_replay_par_kernel<true><<<1, kLbpThreads, smem, st>>>(q);
     }

@@ -176,6 +176,28 @@ def test_leaderboard_ties_large_k(eng_mod, k):
     assert lb.result() == want, k
 
 
+def test_leaderboard_set_mode_without_group_minima(eng_mod, sim, monkeypatch):
+    """Boards beyond ≈1.4 M entries do not get the shared-memory group minima and find the entry that leaves by
+    scanning the whole board: forced here at a size the oracle can check (random pool and an all-ties pool)."""
+    monkeypatch.setenv("GB_LB_NO_GROUPS", "1")
+    N, C, k = 9000, 12, 300
+    f, t = synth.pool(N, C, peaked=0.1)
+    F, T = f.half().cuda(), t.half().cuda()
+    rank_np = synth.path_ranks(N)
+    rank = torch.from_numpy(rank_np).to(torch.int32).cuda()
+    lb = eng_mod.Leaderboard(C, k, "cuda:0")
+    pred, _, probs = lb.scan(F, T, 100.0, rank=rank, want_probs=True)
+    assert lb.result() == leaderboard_ref.leaderboard(probs.cpu().numpy(), pred.cpu().numpy(), k, rank_np)
+    rng = np.random.RandomState(12)
+    lg = rng.choice(np.linspace(0, 3, 5), size=(5000, 6)).astype(np.float32)
+    probs_t = torch.softmax(torch.from_numpy(lg), dim=1)
+    pred_t = probs_t.argmax(1)
+    rk = synth.path_ranks(5000, seed=3)
+    lb = eng_mod.Leaderboard(6, 200, "cuda:0")
+    lb.update(probs_t.cuda(), pred_t.to(torch.int32).cuda(), torch.from_numpy(rk).to(torch.int32).cuda(), prefilter=True)
+    assert lb.result() == leaderboard_ref.leaderboard(probs_t.numpy(), pred_t.numpy(), 200, rk)
+
+
 def test_leaderboard_sharded_handoff_large_k(eng_mod, sim):
     """Hand-off of set-mode boards (GRIP's late iterations, k ≈ N/C): every shard's scan call ends by restoring the
     list order, the next shard resumes from it — identical to one scan and to the oracle."""
