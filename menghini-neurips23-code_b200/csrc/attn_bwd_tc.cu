@@ -16,7 +16,7 @@
 //   dQ = dS·K    128×64×128   A = dS K-major,  B = K MN-major                             → TMEM [256,320)
 // P and dS are fp16 128×128 tiles in shared memory whose off-diagonal 64×64 quadrants (query of one sample × key of
 // the other) are zero, which keeps the samples apart in all three products.
-// Warp-specialised persistent CTAs: warp 0 TMA producer (2-stage ring of Q|K|V|dO), warp 1 MMA issuer, warp 2 TMEM
+// Warp-specialised persistent CTAs: warp 0 TMA producer (2- or 3-stage ring of Q|K|V|dO), warp 1 MMA issuer, warp 2 TMEM
 // allocator; warpgroup 1 (thread = query row) turns S, dP into P, dS; warpgroup 2 (thread = output row) drains
 // dQ, dK, dV → fp16 → staging (the dead P/dS tiles) → TMA stores of L rows per sample.  The two accumulator groups
 // (S, dP | dQ, dK, dV) are disjoint, so item i+1's S/dP and its soft-max overlap item i's second-phase MMAs and stores.
@@ -45,13 +45,23 @@ __device__ unsigned long long g_attn_stalls[16];
 
 namespace {
 
-constexpr int kAbStages = 2;
 constexpr int kAbTile = 128 * 128;             // one 128-row × 64-half tile, bytes
-constexpr int kAbStageBytes = 4 * kAbTile;     // Q | K | V | dO
 constexpr int kAbPBytes = 2 * kAbTile;         // P (and dS): two 64-key atoms of 128 rows
+// Input ring geometry: four full 128-row tiles per stage, two stages (a third does not fit beside the P / dS tiles and the
+// output staging; tried with short tiles at one sample per item, where it fits — no gain: once the issue order is
+// dynamic the producer waits for a free stage most of the time, the soft-max warpgroup's arithmetic is what an item costs).
+template <int G, int NB>
+struct AbGeom {
+  static constexpr int kRows = 128;
+  static constexpr int kTile = kRows * 128;
+  static constexpr int kStageBytes = 4 * kTile;      // Q | K | V | dO
+  static constexpr int kStages = 2;
+  static constexpr int kKeys = 128;                  // N of the S / dP products
+  static constexpr int kSmem = kStages * kStageBytes + 2 * kAbPBytes + 2 * kAbTile + 1024 + 256;
+};
 constexpr int kAbThreads = 128 + 2 * 128;
-constexpr int kAbStagingTiles = 2;             // fp16 output staging, ping-pong (the third stage of inputs does not fit)
-constexpr int kAbSmem = kAbStages * kAbStageBytes + 2 * kAbPBytes + kAbStagingTiles * kAbTile + 1024 + 256;
+constexpr int kAbStagingTiles = 2;             // fp16 output staging, ping-pong
+static_assert(kAbStagingTiles == 2, "AbGeom::kSmem counts two staging tiles");
 constexpr uint32_t kColS = 0, kColdP = 128, kColdQ = 256, kColdK = 320, kColdV = 384;
 
 struct AttnBwdParams {
@@ -97,6 +107,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                    const __grid_constant__ CUtensorMap tmDQKV, const AttnBwdParams p) {
   constexpr int kCols = 16 * NB;              // key columns a query row looks at
   static_assert(G == 2 ? NB <= 4 : (NB > 4 && NB <= 6), "G = 2 packs samples of up to 64 rows; G = 1 up to 96");
+  using Geo = AbGeom<G, NB>;
+  constexpr int kAbStages = Geo::kStages;
+  constexpr int kAbStageBytes = Geo::kStageBytes;
+  constexpr int kInTile = Geo::kTile;         // bytes of one input tile (Q, K, V or dO) of a stage
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -166,15 +180,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         for (int j = 0; j < n_s; ++j) {
           const int row0 = (grp * G + j) * L;
           for (int m = 0; m < 3; ++m)
-            tma_load_2d(st + m * kAbTile + j * 8192, &tmQKV, &full_bar[s], m * D + h * 64, row0);
-          tma_load_2d(st + 3 * kAbTile + j * 8192, &tmDO, &full_bar[s], h * 64, row0);
+            tma_load_2d(st + m * kInTile + j * 8192, &tmQKV, &full_bar[s], m * D + h * 64, row0);
+          tma_load_2d(st + 3 * kInTile + j * 8192, &tmDO, &full_bar[s], h * 64, row0);
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_f16(128, 128);                              // A, B K-major
+      constexpr uint32_t idesc_s = umma_idesc_f16(128, Geo::kKeys);                       // A, B K-major
       constexpr uint32_t idesc_t = umma_idesc_f16(128, 64) | (1u << 15) | (1u << 16);     // A, B MN-major
       constexpr uint32_t idesc_q = umma_idesc_f16(128, 64) | (1u << 16);                  // A K-major, B MN-major
       const uint32_t pa = smem_u32(smem_p), da = smem_u32(smem_ds);
@@ -187,8 +201,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         { AB_T(t0); mbar_wait(&full_bar[s], (it / kAbStages) & 1); AB_ADD(0, t0); }
         { AB_T(t0); mbar_wait(sdp_free, (it & 1) ^ 1); AB_ADD(1, t0); }   // the previous item's S / dP have been read
         tc_fence_after();
-        const uint64_t aq = umma_desc_k_sw128(base), bk = umma_desc_k_sw128(base + kAbTile);
-        const uint64_t ao = umma_desc_k_sw128(base + 3 * kAbTile), bv = umma_desc_k_sw128(base + 2 * kAbTile);
+        const uint64_t aq = umma_desc_k_sw128(base), bk = umma_desc_k_sw128(base + kInTile);
+        const uint64_t ao = umma_desc_k_sw128(base + 3 * kInTile), bv = umma_desc_k_sw128(base + 2 * kInTile);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_f16(tmem_base + kColS, aq + 2 * k, bk + 2 * k, idesc_s, k != 0);
 #pragma unroll
@@ -199,7 +213,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       auto issue_out = [&](int it) {
         const int s = it % kAbStages;
         const uint32_t base = smem_u32(smem_in + s * kAbStageBytes);
-        const uint32_t qa = base, ka = base + kAbTile, oa = base + 3 * kAbTile;
+        const uint32_t qa = base, ka = base + kInTile, oa = base + 3 * kInTile;
         tc_fence_after();
         // blocks of 16 rows that hold no token of any sample are skipped (their P / dS rows and columns are zero)
 #pragma unroll
@@ -261,42 +275,53 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       tc_fence_after();
       uint32_t v[kCols];   // raw scores → log2-domain scores → exponentials → probabilities, in place
       uint32_t dp[kCols];
+      AB_T(t_ld);
 #pragma unroll
       for (int c = 0; c < NB; ++c) ab_tmem_ld16(t_s + 16 * c, v + 16 * c);
 #pragma unroll
       for (int c = 0; c < NB; ++c) ab_tmem_ld16(t_dp + 16 * c, dp + 16 * c);
       tmem_ld_wait();
+      if (threadIdx.x == 128) AB_ADD(13, t_ld);
+      AB_T(t_math);
       tc_fence_before();
       mbar_arrive(sdp_free);       // S and dP are in registers: the next item's may be issued
       float delta = 0.f;           // δ = Σ_j P_ij·dP_ij
       {
-        // scores in log2 units: (q·k / 8)·log2(e)
-        float mx = -INFINITY;
+        // scores in log2 units: (q·k / 8)·log2(e).  The row reductions run on four interleaved partial accumulators:
+        // a warpgroup has ONE warp per scheduler, so a single 64- or 80-long dependent chain of max / add / fma is
+        // pure latency (the soft-max math was 3.6 k of the 5.4 k clocks an item took).
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int kj = 0; kj < kCols; ++kj) {
           const float x = kj < k_end ? __uint_as_float(v[kj]) * 0.18033688011112042f : -INFINITY;
           v[kj] = __float_as_uint(x);
-          mx = fmaxf(mx, x);
+          m4[kj & 3] = fmaxf(m4[kj & 3], x);
         }
+        float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         if (!row_ok) mx = 0.f;
-        float sum = 0.f;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int kj = 0; kj < kCols; ++kj) {
           const float ex = fast_exp2(__uint_as_float(v[kj]) - mx);
           v[kj] = __float_as_uint(ex);
-          sum += ex;
+          s4[kj & 3] += ex;
         }
+        const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
         const float inv = row_ok ? 1.0f / sum : 0.f;
+        float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int kj = 0; kj < kCols; ++kj) {
           const float pj = __uint_as_float(v[kj]) * inv;          // P
           v[kj] = __float_as_uint(pj);
-          delta = fmaf(pj, __uint_as_float(dp[kj]), delta);
+          d4[kj & 3] = fmaf(pj, __uint_as_float(dp[kj]), d4[kj & 3]);
         }
+        delta = (d4[0] + d4[1]) + (d4[2] + d4[3]);
       }
+      if (threadIdx.x == 128) AB_ADD(14, t_math);
       // the previous item's second phase must have finished reading the P / dS tiles (what a row does not write
       // below was zeroed at start-up and stays zero: nothing else ever writes these tiles)
       { AB_T(t0); mbar_wait(out_full, (it & 1) ^ 1); if (threadIdx.x == 128) AB_ADD(6, t0); }
+      AB_T(t_st);
 #pragma unroll
       for (int c8l = 0; c8l < 2 * NB; ++c8l) {                    // 8-key chunks of this row
         uint4 op, od;
@@ -316,6 +341,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       }
       fence_proxy_async();         // generic-proxy writes of P, dS → visible to the tensor core
       mbar_arrive(pds_ready);
+      if (threadIdx.x == 128) AB_ADD(15, t_st);
     }
     if (threadIdx.x == 128) AB_ADD(7, t_wg1);
   } else if (warp >= 8) {
@@ -383,12 +409,12 @@ int launch_bwd_tc(gb_ctx* c, const CUtensorMap& tmQKV, const CUtensorMap& tmDO, 
                   const AttnBwdParams& p, cudaStream_t st) {
   static bool done[16] = {false};
   if (!done[c->device & 15]) {
-    GB_CUDA(c, cudaFuncSetAttribute(attn_bwd_tc_kernel<G, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAbSmem));
+    GB_CUDA(c, cudaFuncSetAttribute(attn_bwd_tc_kernel<G, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, AbGeom<G, NB>::kSmem));
     done[c->device & 15] = true;
   }
   const int sms = gb_gemm_sms(c);
   const int grid = p.n_items < sms ? p.n_items : sms;
-  attn_bwd_tc_kernel<G, NB><<<grid, kAbThreads, kAbSmem, st>>>(tmQKV, tmDO, tmDQKV, p);
+  attn_bwd_tc_kernel<G, NB><<<grid, kAbThreads, AbGeom<G, NB>::kSmem, st>>>(tmQKV, tmDO, tmDQKV, p);
   GB_LAUNCH_CHECK(c);
   return GB_OK;
 }

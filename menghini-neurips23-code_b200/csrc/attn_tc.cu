@@ -216,20 +216,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       tmem_ld_wait();
       // scores in log2 units: (q·k / 8)·log2(e); key kj is visible when kj < L (and kj ≤ qi under the causal mask)
       const int k_end = causal ? min(L, qi + 1) : L;
-      float mx = -INFINITY;
+      // four interleaved partial accumulators: one warp per scheduler cannot hide a 64-long dependent max / add chain
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int kj = 0; kj < kCols; ++kj) {
         const float x = kj < k_end ? __uint_as_float(v[kj]) * 0.18033688011112042f : -INFINITY;
         v[kj] = __float_as_uint(x);
-        mx = fmaxf(mx, x);
+        m4[kj & 3] = fmaxf(m4[kj & 3], x);
       }
-      float sum = 0.f;
+      const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int kj = 0; kj < kCols; ++kj) {
         const float e = fast_exp2(__uint_as_float(v[kj]) - mx);   // key 0 is always visible → mx finite
         v[kj] = __float_as_uint(e);
-        sum += e;
+        s4[kj & 3] += e;
       }
+      const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
       const float inv = 1.0f / sum;
       // P goes where this warpgroup's previous output tile was staged: its TMA stores must have read it
       if (threadIdx.x == 128 + w * 128) tma_store_wait_read<0>();

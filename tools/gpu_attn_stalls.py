@@ -15,7 +15,7 @@ lib = ctx.lib
 lib.gb_debug_attn_stalls.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
 lib.gb_debug_attn_stalls.restype = ctypes.c_int
 names = ["mma:operands", "mma:sdp_free", "mma:pds_ready", "mma:out_free", "mma:total", "sm:sdp_full", "sm:pds_free", "sm:total",
-         "out:out_full", "out:store_read", "out:total", "prod:empty", "items"]
+         "out:out_full", "out:store_read", "out:total", "prod:empty", "items", "sm:tmem_ld", "sm:math", "sm:store+fence"]
 for B, L, D, causal in ((1024, 50, 768, 0), (512, 66, 768, 0), (861, 66, 768, 0)):
     qkv = torch.randn(B * L, 3 * D, device="cuda").half()
     dout = torch.randn(B * L, D, device="cuda").half()
@@ -34,4 +34,4 @@ for B, L, D, causal in ((1024, 50, 768, 0), (512, 66, 768, 0), (861, 66, 768, 0)
     v = list(buf)
     items = max(v[12], 1)
     print(f"attn bwd B={B} L={L}: {e0.elapsed_time(e1) / n * 1e3:.1f} us; clocks per item: " +
-          "  ".join(f"{nm} {v[i] / items:.0f}" for i, nm in enumerate(names[:12])))
+          "  ".join(f"{nm} {v[i] / items:.0f}" for i, nm in enumerate(names) if i != 12))
