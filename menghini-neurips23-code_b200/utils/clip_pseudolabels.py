@@ -40,6 +40,30 @@ def path_ranks(paths):
     return torch.tensor(rank, dtype=torch.int32)
 
 
+# Features of a pool under the FROZEN image tower (no visual prompt rows) depend on nothing but the weights, the
+# transform and the files: GRIP's textual strategies call assign_pseudo_labels once per iteration on the same pool
+# (methods/semi_supervised_learning/textual_fpl.py:168-191, STEP_QUANTILE 10 → ten passes), and the reference decodes
+# and encodes every image again each time.  The cache key carries (path, mtime, size) of every file, so a pool whose
+# files changed is encoded again; GRIPB200_POOL_CACHE=0 switches it off.
+# The cache lives on the engine (it dies with the weights it belongs to) and keeps a reference to the transform it was
+# filled under.
+_POOL_CACHE_MAX = 4
+
+
+def _pool_cache_key(filepaths):
+    if os.environ.get("GRIPB200_POOL_CACHE") == "0":
+        return None
+    import hashlib
+    h = hashlib.blake2b(digest_size=16)
+    try:
+        for pth in filepaths:
+            st = os.stat(pth)
+            h.update(f"{pth}\0{st.st_mtime_ns}\0{st.st_size}\n".encode())
+    except OSError:
+        return None
+    return (len(filepaths), h.hexdigest())
+
+
 def encode_pool(clip_model, filepaths, transform, device, batch=ENCODE_BATCH, loader=None, prefix=None,
                 workers=None):
     """Unit-norm fp16 image features [N,512] of the whole pool, encoded in batches.
@@ -63,6 +87,13 @@ def encode_pool(clip_model, filepaths, transform, device, batch=ENCODE_BATCH, lo
     if not batch:
         batch = type(eng).wave_aligned_batch(2048, L=50 + (0 if prefix is None else prefix.shape[0]), sms=148)
     n = len(filepaths)
+    key = _pool_cache_key(filepaths) if (prefix is None and loader is None and n > 0) else None
+    if key is not None:
+        key = key + (id(transform),)   # the entry keeps the transform alive, so the id cannot be recycled
+    cache = eng.__dict__.setdefault("_pool_cache", {}) if key is not None else None
+    if key is not None and key in cache and cache[key][0] is transform:
+        log.info(f"[encode_pool] {n} pool features from the cache (frozen image tower, unchanged files)")
+        return cache[key][1]
     feats = torch.empty(n, 512, device=eng.device, dtype=torch.float16)
     if n == 0:
         return feats
@@ -109,6 +140,10 @@ def encode_pool(clip_model, filepaths, transform, device, batch=ENCODE_BATCH, lo
                 consumed[i % 2].record(torch.cuda.current_stream(eng.device))
             _, fn, _ = eng.vit_forward(dev, prefix, want_feat=False, want_featn=True)
             feats[s:s + dev.shape[0]] = fn
+    if key is not None:
+        while len(cache) >= _POOL_CACHE_MAX:
+            cache.pop(next(iter(cache)))
+        cache[key] = (transform, feats)
     return feats
 
 
