@@ -239,16 +239,27 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       // can only start when the second phase of i−1 has completed; the other way round the soft-max warpgroup idled
       // through every second phase.)
       int next_sdp = 0, next_out = 0;
+      uint32_t idle_polls = 0;
+      long long t_idle = 0;
       while (next_out < n_mine) {
         if (next_out < next_sdp && mbar_try_wait(pds_ready, next_out & 1) && mbar_try_wait(out_free, (next_out & 1) ^ 1)) {
           AB_INC(12);
           issue_out(next_out);
           ++next_out;
+          idle_polls = 0;
         } else if (next_sdp < n_mine && next_sdp <= next_out + 1 &&
                    mbar_try_wait(&full_bar[next_sdp % kAbStages], (next_sdp / kAbStages) & 1) &&
                    mbar_try_wait(sdp_free, (next_sdp & 1) ^ 1)) {
           issue_sdp(next_sdp);
           ++next_sdp;
+          idle_polls = 0;
+        } else if ((++idle_polls & 1023u) == 0) {   // bounded like mbar_wait: a pipeline bug must trap, not hang the GPU
+          const long long now = clock64();
+          if (idle_polls == 1024u) t_idle = now;
+          else if (now - t_idle > 8000000000LL) {
+            printf("gripb200: attention backward MMA thread stalled (block %d)\n", blockIdx.x);
+            __trap();
+          }
         }
       }
       AB_ADD(4, t_mma);
