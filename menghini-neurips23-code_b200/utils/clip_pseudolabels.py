@@ -147,11 +147,36 @@ def encode_pool(clip_model, filepaths, transform, device, batch=ENCODE_BATCH, lo
     return feats
 
 
-def scan_features(engine, feats16, protos16, k, paths, class_ids, mode=0, scale=None):
+def prob_dtype():
+    """"fp32" (default) or "fp16" ($GRIPB200_PROB_DTYPE).  The reference on CUDA holds `clip_model` in fp16, so what its
+    loop compares are fp16 probabilities of fp16 logits (`logit_scale.exp() * image_features @ text_features.t()` with
+    fp16 operands rounds the logits to fp16 — 1/16 apart near 100 — and `.softmax()` returns fp16; :59-62): they saturate
+    to 1.0 and tie, and ties are resolved by the strict `<` and the path order.  "fp16" reproduces THAT arithmetic — the
+    same two torch operations on the fp16 unit features — and replays the leaderboard exactly on those numbers; the
+    default keeps the fused kernel's fp32 soft-max, which is what the reference's CPU path (fp32 model) computes."""
+    v = os.environ.get("GRIPB200_PROB_DTYPE", "fp32").lower()
+    if v not in ("fp32", "fp16"):
+        raise ValueError(f"GRIPB200_PROB_DTYPE must be fp32 or fp16, not {v!r}")
+    return v
+
+
+def scan_features(engine, feats16, protos16, k, paths, class_ids, mode=0, scale=None, probs="auto"):
     """Leaderboard over precomputed unit-norm features.  Returns (image indices, labels) in the
-    reference's output order (:103-109)."""
+    reference's output order (:103-109).  `probs`: "fp32" | "fp16" | "auto" (= prob_dtype())."""
     n, c = feats16.shape[0], protos16.shape[0]
     scale = engine.logit_scale_exp if scale is None else scale
+    if probs == "auto":
+        probs = prob_dtype()
+    if probs == "fp16":
+        # the reference's CUDA arithmetic, operation for operation (third-party CLIP.forward + :62-64 / textual_fpl.py:228)
+        logits = (torch.tensor(scale, device=feats16.device) * feats16) @ protos16.t()      # fp16
+        p16 = logits.softmax(dim=-1)                                                        # fp16
+        pred = (p16 if mode == 0 else logits).argmax(dim=-1).to(torch.int32)
+        if k == ALL_UNLABELED_K:
+            return list(range(n)), [class_ids[j] for j in pred.cpu().tolist()]
+        board = Leaderboard(c, k, engine.device)
+        board.update(p16.float().contiguous(), pred, path_ranks(paths).to(engine.device), prefilter=True)
+        return board.result(class_ids)
     if k == ALL_UNLABELED_K:  # :27-44 — label every image with its arg-max
         pred, _, _ = engine.sim_softmax_argmax(feats16, protos16, scale, mode)
         pred = pred.cpu().tolist()

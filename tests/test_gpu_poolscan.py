@@ -306,6 +306,38 @@ def test_grip_schedule_with_learned_prompts(pkg):
     assert idx == list(range(N)) and lab == [class_ids[j] for j in pred.cpu().tolist()]
 
 
+def test_fp16_probability_mode_replays_the_references_cuda_arithmetic(pkg, monkeypatch):
+    """GRIPB200_PROB_DTYPE=fp16: logits and probabilities in fp16 as the reference's CUDA path holds them
+    (utils/clip_pseudolabels.py:59-64 with an fp16 clip_model) — many exact ties, saturation at 1.0 — and the exact
+    leaderboard on those numbers; the oracle replays the same fp16 probabilities."""
+    U = importlib.import_module("menghini-neurips23-code_b200.utils")
+
+    class _Eng:
+        device = torch.device("cuda", 0)
+        logit_scale_exp = 100.0
+
+    N, C, k = 12000, 10, 16
+    f, t = synth.pool(N, C, peaked=0.3)
+    F, T = f.half().cuda(), t.half().cuda()
+    paths = [f"img_{i:06d}.jpg" for i in np.random.RandomState(8).permutation(N)]
+    rank = U.path_ranks(paths).numpy()
+    logits = (torch.tensor(100.0, device="cuda") * F) @ T.t()
+    assert logits.dtype == torch.float16
+    p16 = logits.softmax(dim=-1)
+    ties = int((p16.max(dim=1).values == 1.0).sum())
+    assert ties > 50, ties     # the saturation the fp32 path never shows
+    for mode in (0, 1):
+        pred = (p16 if mode == 0 else logits).argmax(dim=-1)
+        want = leaderboard_ref.leaderboard(p16.float().cpu().numpy(), pred.cpu().numpy(), k, rank)
+        assert U.scan_features(_Eng(), F, T, k, paths, list(range(C)), mode=mode, probs="fp16") == want
+    monkeypatch.setenv("GRIPB200_PROB_DTYPE", "fp16")
+    pred0 = p16.argmax(dim=-1)
+    want0 = leaderboard_ref.leaderboard(p16.float().cpu().numpy(), pred0.cpu().numpy(), k, rank)
+    assert U.scan_features(_Eng(), F, T, k, paths, list(range(C)), mode=0) == want0
+    idx, lab = U.scan_features(_Eng(), F, T, leaderboard_ref.ALL_UNLABELED_K, paths, list(range(C)), mode=0)
+    assert idx == list(range(N)) and lab == pred0.cpu().tolist()
+
+
 def test_evaluation_path_matches_the_reference_loop():
     """fused similarity + arg-max over a pool vs the reference's per-batch
     `argmax(logit_scale.exp() * image_features @ text_features.t(), dim=1)` (textual_prompt.py:256-270) evaluated
