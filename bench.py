@@ -363,21 +363,32 @@ def extras_single_gpu(a, model, dev, pk):
         paths = [paths[i % 64] for i in range(n_img)]
         transform = clip._preprocess()
         cores = os.cpu_count() or 1
-        utils_b200.encode_pool(model, paths[:256], transform, dev)      # warm-up (thread pools, staging, arenas)
-        torch.cuda.synchronize()
+        os.environ["GRIPB200_POOL_CACHE"] = "0"      # every pass must really decode (the pool repeats 64 files)
         res = {}
-        for wk in (1, cores):
-            t0 = time.perf_counter()
-            utils_b200.encode_pool(model, paths if wk > 1 else paths[:256], transform, dev, workers=wk)
-            torch.cuda.synchronize()
-            res[wk] = (n_img if wk > 1 else 256) / (time.perf_counter() - t0)
-        shutil.rmtree(tmp, ignore_errors=True)
-        out["decode_pipeline"] = {"config": f"{n_img} JPEG files (512x384, quality 90) → utils.encode_pool: decode + bicubic "
-                                            f"resize + centre crop on {cores} host threads into pinned uint8 staging, "
-                                            f"ToTensor + Normalize + image tower on the device",
-                                  "images_per_s": res[cores], "images_per_s_one_thread": res[1], "host_threads": cores,
-                                  "note": "the reference decodes on one thread at batch 1 (utils/clip_pseudolabels.py:55-57); "
-                                          "host decode, not the tower, bounds a real pool"}
+        try:
+            for dr in (False, True):                 # resize + crop on the host threads | on the device (bit-identical)
+                for wk in (1, cores):
+                    utils_b200.encode_pool(model, paths[:256], transform, dev, workers=wk, device_resize=dr)   # warm-up: pools, arenas
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    utils_b200.encode_pool(model, paths if wk > 1 else paths[:256], transform, dev, workers=wk, device_resize=dr)
+                    torch.cuda.synchronize()
+                    res[(dr, wk)] = (n_img if wk > 1 else 256) / (time.perf_counter() - t0)
+        finally:
+            os.environ.pop("GRIPB200_POOL_CACHE", None)
+            shutil.rmtree(tmp, ignore_errors=True)
+            for r in model.engine.__dict__.pop("_device_resizers", {}).values():    # workers, pinned arenas, device mirrors
+                r.close()
+            model.engine.__dict__.pop("_device_resizer", None)
+        out["decode_pipeline"] = {"config": f"{n_img} JPEG files (512x384, quality 90) → utils.encode_pool: decode on {cores} host "
+                                            f"threads into pinned staging; Pillow's bicubic resize + centre crop bit for bit ON "
+                                            f"THE DEVICE (gb_resize_bicubic_crop_u8), ToTensor + Normalize + image tower on the device",
+                                  "images_per_s": res[(True, cores)], "images_per_s_one_thread": res[(True, 1)],
+                                  "images_per_s_host_resize": res[(False, cores)],
+                                  "images_per_s_host_resize_one_thread": res[(False, 1)], "host_threads": cores,
+                                  "note": "the reference decodes AND resizes on one thread at batch 1 (utils/clip_pseudolabels.py:55-57); "
+                                          "host JPEG decoding, not the tower, bounds a real pool; images_per_s = forked decoder "
+                                          "processes + resize on the device, *_host_resize = decoder threads + PIL resize on the host"}
     except Exception as e:   # PIL without a JPEG codec etc.: an extra, never fatal
         out["decode_pipeline"] = {"unavailable": repr(e)}
 

@@ -79,6 +79,22 @@ int gb_layernorm_f16(gb_ctx* ctx, const void* x, int ldx, const int32_t* row_idx
  * (methods/semi_supervised_learning/textual_prompt.py:98-103) → fp16 and/or fp32 unit rows. */
 int gb_l2norm512(gb_ctx* ctx, const float* x, void* y16, float* y32, int rows, void* stream);
 
+/* Pillow's bicubic Image.resize + CLIP's centre crop on the device, bit for bit, for n 8-bit RGB images of one size:
+ * image i = uint8 [H,W,3] at src + src_off[i] (src_off null: packed [n,H,W,3]) → out[slot] uint8 [3,224,224]
+ * (slot = out_index ? out_index[i] : i), i.e. what the reference's
+ * transform (clip.load's Resize(224, BICUBIC) → CenterCrop(224), data/dataset.py:64-79, utils/clip_pseudolabels.py:56)
+ * yields before ToTensor / Normalize — which gb_vit_forward(…, GB_IMG_U8) applies.  bx int32 [nw,2] (first source
+ * index, count) and kx int32 [nw,ksx] (22-bit fixed-point weights) describe the horizontal pass (null: width kept),
+ * by / ky / ksy the vertical one; left / top are the crop origin in the resized image; row0 / rows the source rows the
+ * vertical pass reads; tmp holds gb_resize_tmp_bytes(n, rows).  The tables come from
+ * menghini-neurips23-code_b200/utils/pil_resample.py::coeffs (checked against Pillow, tests/test_pil_resample.py). */
+size_t gb_resize_tmp_bytes(int n, int rows);
+int gb_resize_bicubic_crop_u8(gb_ctx* ctx, const uint8_t* src, const int64_t* src_off, int n, int H, int W,
+                              const int32_t* bx,
+                              const int32_t* kx, int ksx, int left, const int32_t* by, const int32_t* ky, int ksy,
+                              int top, int row0, int rows, const int32_t* out_index, uint8_t* tmp, uint8_t* out,
+                              void* stream);
+
 /* softmax(Q K^T / 8 [+ causal mask]) V per (sample, head) on the packed in-proj output
  * qkv fp16 [B*L, 3D] → out fp16 [B*L, D]; head dim 64; forward L <= 128, backward L <= 96 (CLIP's sequences are
  * 50 + P <= 66 vision tokens and <= 77 text tokens).  nn.MultiheadAttention core of

@@ -61,6 +61,7 @@ def _preprocess(raw: bool = False):
             return x.contiguous()
         return (x.float() / 255.0 - mean) / std
 
+    transform.is_clip_preprocess_u8 = bool(raw)   # utils.encode_pool may run exactly this resize + crop on the device
     if not raw:
         # the same transform without its ToTensor / Normalize tail: batched pool encoders use it and let the
         # device normalise (bit-identical features, a quarter of the host→device bytes)

@@ -65,7 +65,7 @@ def _pool_cache_key(filepaths):
 
 
 def encode_pool(clip_model, filepaths, transform, device, batch=ENCODE_BATCH, loader=None, prefix=None,
-                workers=None):
+                workers=None, device_resize=None):
     """Unit-norm fp16 image features [N,512] of the whole pool, encoded in batches.
 
     The reference decodes and encodes one image at a time on one thread (:55-61; data/dataset.py:64-79 even applies
@@ -74,7 +74,13 @@ def encode_pool(clip_model, filepaths, transform, device, batch=ENCODE_BATCH, lo
     buffer while the device encodes chunk i; two staging buffers alternate, the H2D copy is asynchronous.  When
     `transform` is this package's CLIP transform its `raw_u8` twin is used — resize + centre crop on the host,
     ToTensor + Normalize on the device: a quarter of the staging and PCIe bytes, bit-identical features
-    (SURVEY §8f N2).  `prefix` ([P,768] / [1,P,768]): visual prompt rows every image is encoded with (the VPT / UPT
+    (SURVEY §8f N2).  With that transform the resize and the crop move to the device as well (`device_resize`, default
+    on; $GRIPB200_DEVICE_RESIZE=0 keeps them on the host): Pillow's bicubic resampler is integer arithmetic on 22-bit
+    fixed-point weights, restated bit for bit in utils/pil_resample.py + csrc/resize.cu, so the host only DECODES
+    (≈2 ms of the ≈6 ms a 512×384 JPEG costs per core) and the image tower still sees exactly the reference's pixels;
+    on this route the decoders are `workers` forked PROCESSES writing into shared page-locked arenas (threads share the
+    GIL for everything PIL does in Python and stop scaling at ≈3 cores; $GRIPB200_DECODE_PROCESSES=0 keeps threads).
+    `prefix` ([P,768] / [1,P,768]): visual prompt rows every image is encoded with (the VPT / UPT
     strategies' assign_pseudo_labels, visual_fpl.py:262-268).  `loader(chunk) -> tensor` replaces decoding."""
     import os
     from concurrent.futures import ThreadPoolExecutor
@@ -99,9 +105,28 @@ def encode_pool(clip_model, filepaths, transform, device, batch=ENCODE_BATCH, lo
         return feats
     tf = getattr(transform, "raw_u8", None) or transform
     workers = max(1, min(int(workers or os.cpu_count() or 1), 64))
+    if device_resize is None:
+        device_resize = os.environ.get("GRIPB200_DEVICE_RESIZE", "1") != "0"
+    # only this package's own CLIP transform is known to be "Pillow bicubic resize → centre crop" and nothing else
+    device_resize = bool(device_resize) and loader is None and getattr(tf, "is_clip_preprocess_u8", False)
+    resizer = None
+    if device_resize:
+        import numpy as np
+
+        from .pil_resample import DeviceResizer
+        procs = workers if os.environ.get("GRIPB200_DECODE_PROCESSES", "1") != "0" else 0
+        procs = procs if procs > 1 else 0
+        resizers = eng.__dict__.setdefault("_device_resizers", {})     # one per decoder count: arenas and forked workers are kept
+        resizer = resizers.get(procs)
+        if resizer is None:
+            resizer = resizers[procs] = DeviceResizer(eng, processes=procs)
+        eng.__dict__["_device_resizer"] = resizer
 
     def decode(path):
         return tf(Image.open(path).convert("RGB"))
+
+    if device_resize:       # chunks sized for the pinned arenas (full-size decoded pixels), not for GEMM waves: this
+        batch = min(batch, 512)   # route is bound by the host's JPEG decoding either way
 
     starts = list(range(0, n, batch))
     staging = [None, None]       # pinned, allocated once the first decoded image tells shape and dtype
@@ -114,6 +139,13 @@ def encode_pool(clip_model, filepaths, transform, device, batch=ENCODE_BATCH, lo
             if loader is not None:
                 imgs = loader(chunk)
                 return imgs.pin_memory() if imgs.device.type == "cpu" and not imgs.is_pinned() else imgs
+            if device_resize:            # decoded RGB pixels of whatever size → pinned arena; resize + crop on the device
+                slot = ci % 2
+                resizer.begin(slot)
+                if resizer.processes:    # worker processes decode straight into the shared, page-locked arena
+                    return resizer.stage_paths(slot, chunk)
+                return list(dec_pool.map(
+                    lambda pth: resizer.put(slot, np.array(Image.open(pth).convert("RGB"), dtype=np.uint8)), chunk))
             b = ci % 2
             first = decode(chunk[0])
             if staging[b] is None or staging[b].dtype != first.dtype or staging[b].shape[1:] != first.shape:
@@ -134,10 +166,13 @@ def encode_pool(clip_model, filepaths, transform, device, batch=ENCODE_BATCH, lo
             imgs = fut.result()
             if i + 1 < len(starts):
                 fut = chunk_pool.submit(load, i + 1)
-            dev = imgs.to(eng.device, non_blocking=True)
-            if loader is None:
-                consumed[i % 2] = torch.cuda.Event()
-                consumed[i % 2].record(torch.cuda.current_stream(eng.device))
+            if device_resize:
+                dev = resizer.flush(i % 2, imgs, torch.empty(len(imgs), 3, 224, 224, dtype=torch.uint8, device=eng.device))
+            else:
+                dev = imgs.to(eng.device, non_blocking=True)
+                if loader is None:
+                    consumed[i % 2] = torch.cuda.Event()
+                    consumed[i % 2].record(torch.cuda.current_stream(eng.device))
             _, fn, _ = eng.vit_forward(dev, prefix, want_feat=False, want_featn=True)
             feats[s:s + dev.shape[0]] = fn
     if key is not None:
