@@ -104,7 +104,13 @@ def encode_pool(clip_model, filepaths, transform, device, batch=ENCODE_BATCH, lo
     if n == 0:
         return feats
     tf = getattr(transform, "raw_u8", None) or transform
-    workers = max(1, min(int(workers or os.cpu_count() or 1), 64))
+    if not workers:      # this rank's share of the cores this process may run on
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 1
+        workers = cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+    workers = max(1, min(int(workers), 64))
     if device_resize is None:
         device_resize = os.environ.get("GRIPB200_DEVICE_RESIZE", "1") != "0"
     # only this package's own CLIP transform is known to be "Pillow bicubic resize → centre crop" and nothing else
