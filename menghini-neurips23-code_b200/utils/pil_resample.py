@@ -203,6 +203,12 @@ class DeviceResizer:
                     except Exception:
                         pass
             self.arenas, self.mirror = [], [None, None]
+            for aid in self.arena_id:            # best effort: the mapping goes once nothing exports its buffer any more
+                m, _SHARED_ARENAS[aid] = _SHARED_ARENAS[aid], None
+                try:
+                    m.close()
+                except (BufferError, ValueError, AttributeError):
+                    pass
 
     def _table(self, in_size, out_size):
         key = (in_size, out_size)
