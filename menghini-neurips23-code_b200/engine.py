@@ -206,11 +206,27 @@ class Engine:
         """ids int [C,77] (host or device); prefix fp32 [P,512] or None.
         Positions after the last EOT are skipped unless full_context (exact either way: the causal
         mask keeps them from reaching any EOT row)."""
-        ids_h = ids.detach().cpu()
-        eot_h = ids_h.argmax(dim=-1)
-        Lt = CTX_LEN if full_context else int(eot_h.max().item()) + 1
-        ids_d = ids_h.to(self.device, torch.int32).contiguous()
-        eot_d = eot_h.to(self.device, torch.int32).contiguous()
+        # The callers tokenise once per (P, classes) and pass the same tensor every step (CustomTextEncoder._prompt_ids;
+        # the reference re-tokenises per batch, clip_encoders.py:54-60): the device copies of the ids / EOT positions are
+        # kept for the last few id tensors instead of two pageable host→device copies and a .item() per step.
+        import weakref
+        cache = self.__dict__.setdefault("_ids_cache", {})
+        key = (id(ids), ids.data_ptr(), ids._version, tuple(ids.shape), bool(full_context))
+        hit = cache.get(key)
+        if hit is not None and hit[0]() is ids:
+            _, ids_d, eot_d, Lt = hit
+        else:
+            ids_h = ids.detach().cpu()
+            eot_h = ids_h.argmax(dim=-1)
+            Lt = CTX_LEN if full_context else int(eot_h.max().item()) + 1
+            ids_d = ids_h.to(self.device, torch.int32).contiguous()
+            eot_d = eot_h.to(self.device, torch.int32).contiguous()
+            if len(cache) >= 16:
+                cache.pop(next(iter(cache)))
+            try:
+                cache[key] = (weakref.ref(ids), ids_d, eot_d, Lt)
+            except TypeError:
+                pass
         C = ids_d.shape[0]
         P = 0
         if prefix is not None:
