@@ -45,5 +45,13 @@ with torch.no_grad():
     tfix = model.encode_text(clip.tokenize([f"a photo of a {c}" for c in classes])).float()
 vstep = training.VPTStep(ipm16, tfix, lr=1e-4)
 vstep.step(img, labels)
+# device-side Pillow resize + crop (odd sizes: both passes, one pass, none)
+import numpy as np
+R = importlib.import_module(PKG + ".utils.pil_resample")
+rz = R.DeviceResizer(eng, arena_bytes=8 << 20)
+arrs = [np.random.randint(0, 256, (h, w, 3), dtype=np.uint8) for w, h in ((97, 61), (300, 224), (224, 224), (500, 375), (31, 67))]
+u8 = rz.run(arrs, torch.empty(len(arrs), 3, 224, 224, dtype=torch.uint8, device="cuda"))
+eng.vit_forward(u8, None, want_feat=True, want_featn=False)
+rz.close()
 torch.cuda.synchronize()
 print("sanitize pass done: loss", float(loss), "boards", sum(len(b) for b in lb.result()[0:1]))
