@@ -377,9 +377,7 @@ def extras_single_gpu(a, model, dev, pk):
         finally:
             os.environ.pop("GRIPB200_POOL_CACHE", None)
             shutil.rmtree(tmp, ignore_errors=True)
-            for r in model.engine.__dict__.pop("_device_resizers", {}).values():    # workers, pinned arenas, device mirrors
-                r.close()
-            model.engine.__dict__.pop("_device_resizer", None)
+            importlib.import_module(PKG + ".utils.pil_resample").close_resizers()   # workers, pinned arenas, device mirrors
         out["decode_pipeline"] = {"config": f"{n_img} JPEG files (512x384, quality 90) → utils.encode_pool: decode on {cores} host "
                                             f"threads into pinned staging; Pillow's bicubic resize + centre crop bit for bit ON "
                                             f"THE DEVICE (gb_resize_bicubic_crop_u8), ToTensor + Normalize + image tower on the device",

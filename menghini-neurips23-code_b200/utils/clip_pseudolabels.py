@@ -119,14 +119,9 @@ def encode_pool(clip_model, filepaths, transform, device, batch=ENCODE_BATCH, lo
     if device_resize:
         import numpy as np
 
-        from .pil_resample import DeviceResizer
+        from .pil_resample import get_resizer
         procs = workers if os.environ.get("GRIPB200_DECODE_PROCESSES", "1") != "0" else 0
-        procs = procs if procs > 1 else 0
-        resizers = eng.__dict__.setdefault("_device_resizers", {})     # one per decoder count: arenas and forked workers are kept
-        resizer = resizers.get(procs)
-        if resizer is None:
-            resizer = resizers[procs] = DeviceResizer(eng, processes=procs)
-        eng.__dict__["_device_resizer"] = resizer
+        resizer = get_resizer(eng, procs)
 
     def decode(path):
         return tf(Image.open(path).convert("RGB"))

@@ -312,3 +312,22 @@ class DeviceResizer:
         """Convenience (tests): stage, upload and resize a list of arrays in one call."""
         self.begin(0)
         return self.flush(0, [self.put(0, a) for a in arrays], out)
+
+
+# One resizer per (device, decoder count) for the whole process: arenas (2 × 320 MB page-locked), their device mirrors
+# and the forked decoders are worth keeping, and must not multiply with every model that is loaded.
+_RESIZERS = {}
+
+
+def get_resizer(engine, processes: int = 0) -> DeviceResizer:
+    key = (engine.device.index, int(processes) if processes and processes > 1 else 0)
+    r = _RESIZERS.get(key)
+    if r is None or not r.arenas:
+        r = _RESIZERS[key] = DeviceResizer(engine, processes=key[1])
+    return r
+
+
+def close_resizers():
+    for r in list(_RESIZERS.values()):
+        r.close()
+    _RESIZERS.clear()

@@ -64,10 +64,9 @@ def test_encode_pool_device_resize_is_bit_identical(pkg, tmp_path):
     model.engine.__dict__.pop("_pool_cache", None)
     dev = U.encode_pool(model, paths, transform, "cuda:0", device_resize=True, batch=4)     # worker processes
     assert torch.equal(host, dev)
-    assert model.engine._device_resizer.processes > 1
+    assert any(k[1] > 1 for k in R._RESIZERS)
     model.engine.__dict__.pop("_pool_cache", None)
     dev1 = U.encode_pool(model, paths, transform, "cuda:0", device_resize=True, batch=5, workers=1)   # one thread
     assert torch.equal(host, dev1)
-    assert model.engine._device_resizer.processes == 0
-    for r in model.engine._device_resizers.values():
-        r.close()
+    assert any(k[1] == 0 for k in R._RESIZERS)
+    R.close_resizers()
