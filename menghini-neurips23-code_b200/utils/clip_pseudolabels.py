@@ -120,7 +120,8 @@ def encode_pool(clip_model, filepaths, transform, device, batch=ENCODE_BATCH, lo
         import numpy as np
 
         from .pil_resample import get_resizer
-        procs = workers if os.environ.get("GRIPB200_DECODE_PROCESSES", "1") != "0" else 0
+        # forked decoders pay off from a few hundred files on; smaller pools are decoded by threads
+        procs = workers if (os.environ.get("GRIPB200_DECODE_PROCESSES", "1") != "0" and n >= 256) else 0
         resizer = get_resizer(eng, procs)
 
     def decode(path):

@@ -323,7 +323,8 @@ def get_resizer(engine, processes: int = 0) -> DeviceResizer:
     key = (engine.device.index, int(processes) if processes and processes > 1 else 0)
     r = _RESIZERS.get(key)
     if r is None or not r.arenas:
-        r = _RESIZERS[key] = DeviceResizer(engine, processes=key[1])
+        # the thread-mode resizer serves small pools (and single-decoder callers): a third of the staging is plenty
+        r = _RESIZERS[key] = DeviceResizer(engine, processes=key[1], arena_bytes=(320 << 20) if key[1] else (96 << 20))
     return r
 
 

@@ -62,8 +62,12 @@ def test_encode_pool_device_resize_is_bit_identical(pkg, tmp_path):
     paths.append(str(grey))
     host = U.encode_pool(model, paths, transform, "cuda:0", device_resize=False)
     model.engine.__dict__.pop("_pool_cache", None)
-    dev = U.encode_pool(model, paths, transform, "cuda:0", device_resize=True, batch=4)     # worker processes
+    dev = U.encode_pool(model, paths, transform, "cuda:0", device_resize=True, batch=4)     # small pool: decoder threads
     assert torch.equal(host, dev)
+    model.engine.__dict__.pop("_pool_cache", None)
+    many = paths * 24                                                                       # ≥ 256 files: forked decoders
+    devp = U.encode_pool(model, many, transform, "cuda:0", device_resize=True, batch=100, workers=4)
+    assert torch.equal(devp, host.repeat(24, 1))
     assert any(k[1] > 1 for k in R._RESIZERS)
     model.engine.__dict__.pop("_pool_cache", None)
     dev1 = U.encode_pool(model, paths, transform, "cuda:0", device_resize=True, batch=5, workers=1)   # one thread
