@@ -301,19 +301,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         // scores in log2 units: (q·k / 8)·log2(e).  The row reductions run on four interleaved partial accumulators:
         // a warpgroup has ONE warp per scheduler, so a single 64- or 80-long dependent chain of max / add / fma is
         // pure latency (the soft-max math was 3.6 k of the 5.4 k clocks an item took).
+        constexpr float kScale = 0.18033688011112042f;   // > 0: the arg-max is taken on the raw scores
         float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int kj = 0; kj < kCols; ++kj) {
-          const float x = kj < k_end ? __uint_as_float(v[kj]) * 0.18033688011112042f : -INFINITY;
+          const float x = kj < k_end ? __uint_as_float(v[kj]) : -INFINITY;
           v[kj] = __float_as_uint(x);
           m4[kj & 3] = fmaxf(m4[kj & 3], x);
         }
-        float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-        if (!row_ok) mx = 0.f;
+        float mxs = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * kScale;
+        if (!row_ok) mxs = 0.f;
         float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int kj = 0; kj < kCols; ++kj) {
-          const float ex = fast_exp2(__uint_as_float(v[kj]) - mx);
+          const float ex = fast_exp2(fmaf(__uint_as_float(v[kj]), kScale, -mxs));
           v[kj] = __float_as_uint(ex);
           s4[kj & 3] += ex;
         }

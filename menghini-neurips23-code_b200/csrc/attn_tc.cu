@@ -216,19 +216,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       tmem_ld_wait();
       // scores in log2 units: (q·k / 8)·log2(e); key kj is visible when kj < L (and kj ≤ qi under the causal mask)
       const int k_end = causal ? min(L, qi + 1) : L;
-      // four interleaved partial accumulators: one warp per scheduler cannot hide a 64-long dependent max / add chain
+      // four interleaved partial accumulators: one warp per scheduler cannot hide a 64-long dependent max / add chain.
+      // The arg-max is taken on the raw scores and the scale (1/8·log2 e > 0) goes into the exponent's FFMA.
+      constexpr float kScale = 0.18033688011112042f;
       float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int kj = 0; kj < kCols; ++kj) {
-        const float x = kj < k_end ? __uint_as_float(v[kj]) * 0.18033688011112042f : -INFINITY;
+        const float x = kj < k_end ? __uint_as_float(v[kj]) : -INFINITY;
         v[kj] = __float_as_uint(x);
         m4[kj & 3] = fmaxf(m4[kj & 3], x);
       }
-      const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      const float mxs = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * kScale;   // key 0 is always visible → finite
       float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int kj = 0; kj < kCols; ++kj) {
-        const float e = fast_exp2(__uint_as_float(v[kj]) - mx);   // key 0 is always visible → mx finite
+        const float e = fast_exp2(fmaf(__uint_as_float(v[kj]), kScale, -mxs));
         v[kj] = __float_as_uint(e);
         s4[kj & 3] += e;
       }
