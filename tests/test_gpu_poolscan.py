@@ -274,6 +274,41 @@ def test_large_pool_properties(eng_mod, sim):
     assert lb3.result() == lb.result()
 
 
+def test_large_pool_properties_grip_sized_k(eng_mod, sim):
+    """GRIP's last iteration at the full pool size (N = 1,048,576, C = 100, k = N/C = 10 485 — boards kept as sets in global
+    memory): the oracle would take hours, so the three device routes, which chunk and filter the pool differently, must
+    agree entry for entry — fused scan (similarity + pre-filter in growing chunks), replay of the full probability matrix
+    with the standalone pre-filter, and the unfiltered replay that visits every row in order — and the boards must have
+    the reference's shape: at most k entries, no image twice per board, sorted by (p, path) descending once admitted to."""
+    N, C = 1 << 20, 100
+    k = N // C
+    f, t = synth.pool(N, C, peaked=0.05)
+    F, T = f.half().cuda(), t.half().cuda()
+    rank = torch.from_numpy(synth.path_ranks(N)).to(torch.int32).cuda()
+    lb = eng_mod.Leaderboard(C, k, "cuda:0")
+    pred, pp, _ = lb.scan(F, T, 100.0, rank=rank)
+    idx, ln, p = lb.export(want_p=True)
+    assert int(ln.max()) <= k and int(ln.sum()) > N // 2
+    pred3, pp3, probs = sim(F, T, 100.0)
+    assert torch.equal(pred3, pred)
+    for j in (0, 17, 99):
+        n = int(ln[j])
+        ids = idx[j, :n]
+        assert ids.unique().numel() == n
+        # stored probabilities are the kernel's probabilities of (image, board class)
+        assert torch.equal(probs[ids.long(), j], p[j, :n])
+        if n == k:   # full boards that had an admission are sorted; (p, rank) descending
+            pj, rj = p[j, :n], rank[ids.long()]
+            srt = (pj[:-1] > pj[1:]) | ((pj[:-1] == pj[1:]) & (rj[:-1] > rj[1:]))
+            arrival = bool((ids[:-1] < ids[1:]).all())      # never admitted to: still in arrival order
+            assert bool(srt.all()) or arrival
+    want = lb.result()
+    for prefilter in (True, False):
+        lb2 = eng_mod.Leaderboard(C, k, "cuda:0")
+        lb2.update(probs, pred, rank, prefilter=prefilter)
+        assert lb2.result() == want, prefilter
+
+
 def test_grip_schedule_with_learned_prompts(pkg):
     """GRIP refresh (methods/semi_supervised_learning/pseudo_iterative.py:62-75,113-125 schedule;
     assign_pseudo_labels of textual_fpl.py:195-283): k grows from N/(10·C) towards N/C over the iterations
