@@ -9,6 +9,7 @@ forwards of models/clip_encoders.py:43-90,123-194 and autograd w.r.t. the prompt
 from __future__ import annotations
 
 import ctypes
+import os
 import weakref
 from typing import Optional
 
@@ -206,6 +207,20 @@ class Engine:
         """ids int [C,77] (host or device); prefix fp32 [P,512] or None.
         Positions after the last EOT are skipped unless full_context (exact either way: the causal
         mask keeps them from reaching any EOT row)."""
+        # Frozen text tower, no prompt rows, no tape: the features are a function of the ids alone.  The reference's zero-shot
+        # paths re-encode the same prompts for every batch (methods/clip_baseline.py:57-75 inside the batch loop,
+        # `clip_model(img, text)` per image at utils/clip_pseudolabels.py:59-61); the last few results are kept, keyed by the
+        # ids' contents, and handed out as copies ($GRIPB200_TEXT_CACHE=0 switches it off).
+        tkey = None
+        if prefix is None and not tape and os.environ.get("GRIPB200_TEXT_CACHE", "1") != "0":
+            import hashlib
+            ids_c = ids.detach().to("cpu", torch.int64).contiguous()
+            tkey = (tuple(ids_c.shape), hashlib.blake2b(ids_c.numpy().tobytes(), digest_size=16).digest(), bool(full_context))
+            tcache = self.__dict__.setdefault("_text_cache", {})
+            ent = tcache.get(tkey)
+            if ent is not None:
+                feat_c, featn_c, eot_c, Lt_c = ent
+                return (feat_c.clone() if want_feat else None, featn_c.clone() if want_featn else None, (None, eot_c, Lt_c))
         # The callers tokenise once per (P, classes) and pass the same tensor every step (CustomTextEncoder._prompt_ids;
         # the reference re-tokenises per batch, clip_encoders.py:54-60): the device copies of the ids / EOT positions are
         # kept for the last few id tensors instead of two pageable host→device copies and a .item() per step.
@@ -233,8 +248,9 @@ class Engine:
             prefix = prefix.detach().reshape(-1, T_WIDTH).to(self.device, torch.float32).contiguous()
             P = prefix.shape[0]
         Lt = max(Lt, P + 2)
-        feat = torch.empty(C, EMBED, device=self.device, dtype=torch.float32) if want_feat else None
-        featn = torch.empty(C, EMBED, device=self.device, dtype=torch.float16) if want_featn else None
+        keep = tkey is not None
+        feat = torch.empty(C, EMBED, device=self.device, dtype=torch.float32) if (want_feat or keep) else None
+        featn = torch.empty(C, EMBED, device=self.device, dtype=torch.float16) if (want_featn or keep) else None
         tp = None
         if tape:
             tp = torch.empty(self.tape_bytes(C, Lt, T_WIDTH), device=self.device, dtype=torch.uint8)
@@ -243,6 +259,12 @@ class Engine:
                                       ptr(prefix) if P else None, C, P, Lt, ptr(feat), ptr(featn),
                                       ptr(tp), stream_ptr(self.device))
         self.ctx.check(rc, "gb_text_forward")
+        if keep:
+            tcache = self.__dict__["_text_cache"]
+            if len(tcache) >= 8:
+                tcache.pop(next(iter(tcache)))
+            tcache[tkey] = (feat, featn, eot_d, Lt)
+            return (feat.clone() if want_feat else None, featn.clone() if want_featn else None, (None, eot_d, Lt))
         return feat, featn, (tp, eot_d, Lt)
 
     def text_backward_prefix(self, dfeat, P, saved):
