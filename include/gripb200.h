@@ -95,6 +95,12 @@ int gb_resize_bicubic_crop_u8(gb_ctx* ctx, const uint8_t* src, const int64_t* sr
                               int top, int row0, int rows, const int32_t* out_index, uint8_t* tmp, uint8_t* out,
                               void* stream);
 
+/* Two independent 64-bit multiply-sum checksums per row (out uint64 [rows][2]) of `rows` contiguous rows of `row_bytes`
+ * bytes (a multiple of 8, 8-byte aligned): how the host side recognises an image the frozen tower has already encoded
+ * (the reference re-encodes the same training images in every epoch, methods/semi_supervised_learning/
+ * textual_prompt.py:99-103). */
+int gb_checksum128(gb_ctx* ctx, const void* data, int rows, size_t row_bytes, uint64_t* out, void* stream);
+
 /* softmax(Q K^T / 8 [+ causal mask]) V per (sample, head) on the packed in-proj output
  * qkv fp16 [B*L, 3D] → out fp16 [B*L, D]; head dim 64; forward L <= 128, backward L <= 96 (CLIP's sequences are
  * 50 + P <= 66 vision tokens and <= 77 text tokens).  nn.MultiheadAttention core of

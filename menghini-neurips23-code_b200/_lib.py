@@ -66,6 +66,7 @@ _SIGNATURES = {
                             c_int, c_int, P]),
     "gb_layernorm_f16": (c_int, [P, P, c_int, P, c_int, P, P, P, c_int, c_int, c_int, c_int, P]),
     "gb_l2norm512": (c_int, [P, P, P, P, c_int, P]),
+    "gb_checksum128": (c_int, [P, P, c_int, c_size_t, P, P]),
     "gb_resize_tmp_bytes": (c_size_t, [c_int, c_int]),
     "gb_resize_bicubic_crop_u8": (c_int, [P, P, P, c_int, c_int, c_int, P, P, c_int, c_int, P, P, c_int, c_int, c_int,
                                           c_int, P, P, P, P]),

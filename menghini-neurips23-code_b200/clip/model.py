@@ -128,7 +128,7 @@ class CLIP(nn.Module):
     def _encode_image(self, image, prefix=None):
         image = image.to(self.visual.conv1.weight.device)
         if prefix is None:
-            return self._feat_dtype(self.engine.vit_forward(image, None)[0])
+            return self._feat_dtype(self.engine.frozen_image_features(image))
         return self._feat_dtype(_engine.vit_with_prefix(self.engine, image, prefix))
 
     def encode_image(self, image):

@@ -70,7 +70,49 @@ resize_v_kernel(const uint8_t* __restrict__ tmp, int rows, int row0, const int32
   dst[0] = clip8(s0); dst[224 * 224] = clip8(s1); dst[2 * 224 * 224] = clip8(s2);
 }
 
+// Two independent 64-bit multiply-sum checksums per row of `row_bytes` bytes (a multiple of 8): word i is multiplied by
+// odd, index-dependent 64-bit constants and everything is added modulo 2^64 (order-free, hence deterministic).  What
+// engine.frozen_image_features recognises an already encoded image by.
+__global__ void __launch_bounds__(256) checksum128_kernel(const uint64_t* __restrict__ data, size_t words_per_row,
+                                                          uint64_t* __restrict__ out) {
+  __shared__ uint64_t red[2][8];
+  const uint64_t* row = data + (size_t)blockIdx.x * words_per_row;
+  uint64_t h0 = 0, h1 = 0;
+  for (size_t i = threadIdx.x; i < words_per_row; i += 256) {
+    const uint64_t x = row[i];
+    const uint64_t m0 = ((i + 1) * 0x9E3779B97F4A7C15ull + 0x7F4A7C15ull) | 1ull;
+    const uint64_t m1 = ((i + 1) * 0xC2B2AE3D27D4EB4Full + 0x165667B1ull) | 1ull;
+    h0 += x * m0;
+    h1 += (x ^ (x >> 29)) * m1;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    h0 += __shfl_xor_sync(0xffffffffu, h0, o);
+    h1 += __shfl_xor_sync(0xffffffffu, h1, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = h0; red[1][threadIdx.x >> 5] = h1; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t a = 0, b = 0;
+    for (int w = 0; w < 8; ++w) { a += red[0][w]; b += red[1][w]; }
+    out[2 * blockIdx.x] = a;
+    out[2 * blockIdx.x + 1] = b;
+  }
+}
+
 }  // namespace
+
+// out[r] = two 64-bit checksums of row r (`row_bytes` bytes each, a multiple of 8; rows contiguous, 8-byte aligned).
+extern "C" int gb_checksum128(gb_ctx* c, const void* data, int rows, size_t row_bytes, uint64_t* out, void* stream) {
+  if (!c) return GB_ERR_ARG;
+  gb_dev_guard dev_guard(c);
+  if (rows <= 0) return GB_OK;
+  if (!data || !out || row_bytes == 0 || (row_bytes & 7) || (reinterpret_cast<uintptr_t>(data) & 7))
+    return gb_fail(c, GB_ERR_ARG, "checksum128: rows of a multiple of 8 bytes, 8-byte aligned");
+  checksum128_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint64_t*>(data), row_bytes / 8, out);
+  GB_LAUNCH_CHECK(c);
+  return GB_OK;
+}
 
 extern "C" size_t gb_resize_tmp_bytes(int n, int rows) {
   return n <= 0 || rows <= 0 ? 0 : (size_t)n * rows * 224 * 3;

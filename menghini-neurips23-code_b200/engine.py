@@ -202,6 +202,63 @@ class Engine:
         self.ctx.check(rc, "gb_vit_backward_prefix")
         return dprefix
 
+    # ---- frozen image features, remembered per image ----------------------------------------------------------------
+    def frozen_image_features(self, image: torch.Tensor) -> torch.Tensor:
+        """fp32 [B,512] features of the FROZEN image tower (no prompt rows) for small batches, remembering every image
+        it has encoded.  The reference's prompt-tuning loops re-encode the same (deterministically transformed) training
+        and validation images under no_grad in every one of 150 epochs (methods/semi_supervised_learning/
+        textual_prompt.py:99-103, :190-199); features do not depend on how images are batched (bit for
+        bit, tests/test_gpu_towers.py::test_batch_invariance), so a remembered row IS what the tower would return.
+        An image is recognised by two independent 64-bit multiply-sum checksums of its bits, computed on the device
+        (gb_checksum128; a chance collision needs ≈2⁻¹²⁸); $GRIPB200_IMAGE_CACHE=0 switches the memory off, and it switches itself off when
+        32 768 images in a row were all new (single-pass evaluation loops gain nothing from it)."""
+        B = image.shape[0]
+        st = self.__dict__.setdefault("_img_cache", {"map": {}, "feats": None, "n": 0, "lookups": 0, "hits": 0, "off": False})
+        x = None
+        if (not st["off"] and 0 < B <= 64 and image.dim() == 4 and os.environ.get("GRIPB200_IMAGE_CACHE", "1") != "0"
+                and image.dtype in (torch.float32, torch.float16, torch.uint8)):
+            x = image.to(self.device).contiguous()
+            if (x[0].numel() * x.element_size()) % 8 or x.data_ptr() % 8:
+                x = None
+        if x is None:
+            return self.vit_forward(image, None)[0]
+        sums = torch.empty(B, 2, device=self.device, dtype=torch.int64)
+        self.ctx.check(self.lib.gb_checksum128(self.ctx.h, ptr(x), B, x[0].numel() * x.element_size(), ptr(sums),
+                                               stream_ptr(self.device)), "gb_checksum128")
+        h = sums.cpu().tolist()
+        bits = x
+        tag = str(bits.dtype)
+        rows, miss = [], []
+        for i, (h0, h1) in enumerate(h):
+            r = st["map"].get((tag, h0, h1))
+            rows.append(r)
+            if r is None:
+                miss.append(i)
+        st["lookups"] += B
+        st["hits"] += B - len(miss)
+        max_rows = 1 << 17               # 256 MB of features: start over rather than grow without bound
+        if miss:
+            if st["n"] + len(miss) > max_rows:
+                st["map"].clear()
+                st["n"] = 0
+                rows, miss = [None] * B, list(range(B))
+            fm = self.vit_forward(x[miss] if len(miss) < B else x, None)[0]
+            need = st["n"] + len(miss)
+            if st["feats"] is None or need > st["feats"].shape[0]:
+                grown = torch.empty(min(max_rows, max(1024, 2 * need)), EMBED, device=self.device, dtype=torch.float32)
+                if st["feats"] is not None and st["n"]:
+                    grown[:st["n"]] = st["feats"][:st["n"]]
+                st["feats"] = grown
+            base = st["n"]
+            st["feats"][base:base + len(miss)] = fm
+            for j, i in enumerate(miss):
+                st["map"][(tag, h[i][0], h[i][1])] = base + j
+                rows[i] = base + j
+            st["n"] = need
+        if st["lookups"] >= 32768 and st["hits"] == 0:
+            st["off"] = True
+        return st["feats"][torch.tensor(rows, device=self.device)]
+
     def text_forward(self, ids: torch.Tensor, prefix: Optional[torch.Tensor] = None,
                      want_feat=True, want_featn=False, tape: bool = False, full_context=False):
         """ids int [C,77] (host or device); prefix fp32 [P,512] or None.
