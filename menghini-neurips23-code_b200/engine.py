@@ -530,8 +530,77 @@ def vit_with_prefix(engine: Engine, img, prefix):
     return engine.vit_forward(img, prefix)[0]
 
 
+class _TextGraphs:
+    """CUDA graphs of the taped text forward and of the prompt-only backward for ONE (prompt parameter, id tensor) pair —
+    what TextPrefixModel.forward → loss.backward() of the reference's training loop amounts to on every batch
+    (methods/semi_supervised_learning/textual_prompt.py:93-131): ≈160 launch-latency-bound kernels per step become two
+    graph submissions.  The parameter is read in place (the optimiser updates it in place), ids / EOT positions are the
+    engine's cached device copies, the tape, the features, the incoming and the outgoing gradient are static buffers.
+    `busy` guards the tape: a second forward before the backward of the first (gradient accumulation over several
+    forwards) takes the eager route."""
+
+    def __init__(self, engine, prefix, ids):
+        self.engine, self.busy = engine, False
+        self.P = prefix.reshape(-1, T_WIDTH).shape[0]
+        self.ptr, self.shape, self.dtype = prefix.data_ptr(), prefix.shape, prefix.dtype
+        eng = engine
+        with torch.no_grad():
+            p2 = prefix.detach().reshape(-1, T_WIDTH)
+            # eager once: sizes the library's scratch arenas (no allocation may happen inside a capture)
+            feat, _, saved = eng.text_forward(ids, p2, tape=True)
+            eng.text_backward_prefix(torch.zeros_like(feat), self.P, saved)
+            torch.cuda.synchronize(eng.device)
+            self.gen = int(eng.lib.gb_workspace_generation(eng.ctx.h))
+            self.fwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.fwd):
+                self.feat, _, self.saved = eng.text_forward(ids, p2, tape=True)
+            self.dfeat = torch.zeros_like(self.feat)
+            self.bwd = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.bwd, pool=self.fwd.pool()):
+                self.dprefix = eng.text_backward_prefix(self.dfeat, self.P, self.saved)
+
+    def valid(self, prefix):
+        return (prefix.data_ptr() == self.ptr and prefix.shape == self.shape and prefix.dtype == self.dtype
+                and int(self.engine.lib.gb_workspace_generation(self.engine.ctx.h)) == self.gen)
+
+
+class _TextPrefixGraphFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, prefix, graphs):
+        graphs.busy = True
+        graphs.fwd.replay()
+        ctx.graphs = graphs
+        return graphs.feat.clone()
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        g = ctx.graphs
+        g.dfeat.copy_(dfeat)
+        g.bwd.replay()
+        g.busy = False
+        return g.dprefix.clone().reshape(g.shape).to(g.dtype), None
+
+
 def text_with_prefix(engine: Engine, ids, prefix):
     """Differentiable (w.r.t. prefix) CustomTextEncoder.forward after tokenisation."""
     if prefix.requires_grad and torch.is_grad_enabled():
+        if (os.environ.get("GRIPB200_TEXT_GRAPH", "1") != "0" and prefix.dtype == torch.float32
+                and prefix.is_contiguous() and prefix.device == engine.device and not torch.cuda.is_current_stream_capturing()):
+            cache = engine.__dict__.setdefault("_text_graphs", {})
+            key = (prefix.data_ptr(), id(ids), ids.data_ptr(), ids._version, tuple(ids.shape))
+            g = cache.get(key)
+            if g is not None and not g.valid(prefix):
+                g = None
+            if g is None:
+                try:
+                    if len(cache) >= 4:
+                        cache.pop(next(iter(cache)))
+                    g = cache[key] = _TextGraphs(engine, prefix, ids)
+                    g._ids_ref = ids      # keeps the id tensor alive: its id() is part of the key
+                except Exception:
+                    cache.pop(key, None)
+                    g = None
+            if g is not None and not g.busy:
+                return _TextPrefixGraphFn.apply(prefix, g)
         return _TextPrefixFn.apply(prefix, ids, engine)
     return engine.text_forward(ids, prefix)[0]
