@@ -540,7 +540,7 @@ class _TextGraphs:
     forwards) takes the eager route."""
 
     def __init__(self, engine, prefix, ids):
-        self.engine, self.busy = engine, False
+        self.engine, self._pending = engine, None
         self.P = prefix.reshape(-1, T_WIDTH).shape[0]
         self.ptr, self.shape, self.dtype = prefix.data_ptr(), prefix.shape, prefix.dtype
         eng = engine
@@ -559,6 +559,11 @@ class _TextGraphs:
             with torch.cuda.graph(self.bwd, pool=self.fwd.pool()):
                 self.dprefix = eng.text_backward_prefix(self.dfeat, self.P, self.saved)
 
+    @property
+    def busy(self):
+        """The static tape still belongs to a forward whose output is alive and has not been back-propagated."""
+        return self._pending is not None and self._pending() is not None
+
     def valid(self, prefix):
         return (prefix.data_ptr() == self.ptr and prefix.shape == self.shape and prefix.dtype == self.dtype
                 and int(self.engine.lib.gb_workspace_generation(self.engine.ctx.h)) == self.gen)
@@ -567,17 +572,18 @@ class _TextGraphs:
 class _TextPrefixGraphFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, prefix, graphs):
-        graphs.busy = True
         graphs.fwd.replay()
         ctx.graphs = graphs
-        return graphs.feat.clone()
+        out = graphs.feat.clone()
+        graphs._pending = weakref.ref(out)
+        return out
 
     @staticmethod
     def backward(ctx, dfeat):
         g = ctx.graphs
         g.dfeat.copy_(dfeat)
         g.bwd.replay()
-        g.busy = False
+        g._pending = None
         return g.dprefix.clone().reshape(g.shape).to(g.dtype), None
 
 
@@ -587,19 +593,23 @@ def text_with_prefix(engine: Engine, ids, prefix):
         if (os.environ.get("GRIPB200_TEXT_GRAPH", "1") != "0" and prefix.dtype == torch.float32
                 and prefix.is_contiguous() and prefix.device == engine.device and not torch.cuda.is_current_stream_capturing()):
             cache = engine.__dict__.setdefault("_text_graphs", {})
-            key = (prefix.data_ptr(), id(ids), ids.data_ptr(), ids._version, tuple(ids.shape))
-            g = cache.get(key)
+            key = (id(ids), ids.data_ptr(), ids._version, tuple(ids.shape), tuple(prefix.shape))
+            ent = cache.get(key)
+            if ent is None:
+                if len(cache) >= 4:
+                    cache.pop(next(iter(cache)))
+                ent = cache[key] = {"g": None, "captures": 0, "ids": ids}   # keeps the id tensor alive: its id() is in the key
+            g = ent["g"]
             if g is not None and not g.valid(prefix):
-                g = None
-            if g is None:
+                g = ent["g"] = None
+            # a prompt that lives at a new address on every call (UPT: the coupled prompt is a fresh tensor each step)
+            # would be re-captured every time: after a few captures for the same ids the eager route is kept
+            if g is None and ent["captures"] < 5:
+                ent["captures"] += 1
                 try:
-                    if len(cache) >= 4:
-                        cache.pop(next(iter(cache)))
-                    g = cache[key] = _TextGraphs(engine, prefix, ids)
-                    g._ids_ref = ids      # keeps the id tensor alive: its id() is part of the key
+                    g = ent["g"] = _TextGraphs(engine, prefix, ids)
                 except Exception:
-                    cache.pop(key, None)
-                    g = None
+                    g, ent["captures"] = None, 5
             if g is not None and not g.busy:
                 return _TextPrefixGraphFn.apply(prefix, g)
         return _TextPrefixFn.apply(prefix, ids, engine)
