@@ -581,9 +581,12 @@ class _TextPrefixGraphFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dfeat):
         g = ctx.graphs
+        if g is None:
+            raise GripB200Error("backward through the text tower a second time: the tape of that forward has been released")
         g.dfeat.copy_(dfeat)
         g.bwd.replay()
         g._pending = None
+        ctx.graphs = None
         return g.dprefix.clone().reshape(g.shape).to(g.dtype), None
 
 
