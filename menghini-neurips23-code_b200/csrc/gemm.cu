@@ -47,8 +47,20 @@ static int launch_gemm_bn(gb_ctx* c, const CUtensorMap& tmA, const CUtensorMap& 
 
 template <int kMode>
 static int launch_gemm_2cta(gb_ctx* c, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                            const CUtensorMap& tmC, const GemmParams& p, cudaStream_t st) {
-  using Cfg = Gemm2Cfg;
+                            const CUtensorMap& tmC_in, const GemmParams& p, cudaStream_t st) {
+  using Cfg = Gemm2Cfg<kMode>;
+  // The flavours with a second operand of the output's shape (residual, saved pre-activation) fetch it through
+  // a tensor map of their own, in the 32 x 32 boxes their outputs are stored in (gemm_epilogue_tile_pre).
+  CUtensorMap tmC = tmC_in, tmR = tmC_in;
+  if (Cfg::kPreTma) {
+    const void* pre = kMode == kEpiAct2 ? (const void*)p.aux : (const void*)p.resid;
+    const int pre_ld = kMode == kEpiAct2 ? p.ldo : p.ldr;
+    if (!pre) return gb_fail(c, GB_ERR_ARG, "gemm: the second operand of this epilogue is missing");
+    int rc = gb_make_tmap_2d_f16(c, &tmC, p.out, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)p.ldo, 32, 32);
+    if (rc) return rc;
+    rc = gb_make_tmap_2d_f16(c, &tmR, pre, (uint64_t)p.M, (uint64_t)p.N, (uint64_t)pre_ld, 32, 32);
+    if (rc) return rc;
+  }
   // One pair per cluster.  (The kernel also supports two pairs sharing their W tile through TMA
   // multicast; measured on B200 at M = 51200, K = 768 / 3072 it gains nothing — the pair kernel is not
   // bound by L2 bandwidth — and four-CTA clusters strand 16 of the 148 SMs.)
@@ -77,7 +89,7 @@ static int launch_gemm_2cta(gb_ctx* c, const CUtensorMap& tmA, const CUtensorMap
   cfg.gridDim = dim3(kCluster * clusters);
   {
     gb_prof_scope prof(c, st, 0, 2.0 * p.M * p.N * p.K, p.M, p.N, p.K);
-    GB_CUDA(c, cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, tmC, p));
+    GB_CUDA(c, cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, tmC, tmR, p));
   }
   GB_LAUNCH_CHECK(c);
   return GB_OK;

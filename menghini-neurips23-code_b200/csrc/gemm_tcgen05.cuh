@@ -657,6 +657,141 @@ __device__ __forceinline__ void gemm_epilogue_tile_tma(const GemmParams& p, cons
   ln_st = ln_next;
 }
 
+// Epilogue of the flavours that combine the accumulator with a SECOND global operand of the output's shape
+// (kEpiResid: the residual stream; kEpiAct2: the saved pre-activation), GB_PRE_TMA build (default).
+// Read by the thread that owns the row (16-byte pieces of 32 different rows per instruction, as the first
+// version did) that operand cost the out-proj GEMM 23 % (B200, M = 94 700, N = K = 768: 95 µs plain / bias,
+// 117 µs with the residual).  Here it arrives the way the output leaves: a 32 x 32 box per chunk, fetched by the
+// TMA engine straight into the half-slab the chunk's output is then written to IN PLACE (each thread reads and
+// rewrites its own 64 bytes) and stored from.  Five half-slabs per warp rotate; the box of chunk g + 3 is requested
+// when chunk g starts — its slab was last read by the store of chunk g − 2, which wait_group.read<1> has seen off —
+// so a box has three chunks (¾ of a tile) to arrive.  One mbarrier per half-slab (the lane that arms it is the
+// lane that issues the load); no registers are spent on the operand.
+constexpr int kPreSlabs = 5;
+constexpr int kPreAhead = 3;
+constexpr int kPreSlabBytes = 32 * 64;  // 32 rows x 32 fp16 columns
+
+template <int kMode, typename WaitAcc, typename ReleaseAcc>
+__device__ __forceinline__ void gemm_epilogue_tile_pre(const GemmParams& p, const CUtensorMap* tmC,
+                                                       const CUtensorMap* tmR, uint8_t* slabs, uint64_t* pre_bar,
+                                                       uint32_t tmem_acc, int m0, int n_base, int warp, int lane,
+                                                       int next_m0, uint32_t consts_s, uint32_t consts_next_s,
+                                                       int next_n_base, int& ring_s, uint32_t& ring_par,
+                                                       WaitAcc&& wait_acc, ReleaseAcc&& release_acc) {
+  static_assert(kMode == kEpiResid || kMode == kEpiAct2, "second-operand flavours only");
+  constexpr int kCols = kEpiCols;
+  constexpr int kChunks = kCols / 32;
+  constexpr bool kAct2 = kMode == kEpiAct2;
+  const int q = warp & 3;
+  const int cg = (warp - 4) >> 2;
+  const int n0 = n_base + cg * kCols;
+  const int row0 = m0 + q * 32;
+  const int row = row0 + lane;
+  const bool row_ok = row < p.M;
+  constexpr int kCPL = kCols / 32;
+  float nb[kCPL];
+#pragma unroll
+  for (int i = 0; i < kCPL; ++i) nb[i] = 0.f;
+  if (!kAct2 && next_n_base >= 0 && p.bias != nullptr) {
+    const int nc = next_n_base + cg * kCols + kCPL * lane;
+#pragma unroll
+    for (int i = 0; i < kCPL; ++i) nb[i] = __ldg(p.bias + nc + i);
+  }
+  float st_sum = 0.f, st_sq = 0.f, st_x0 = 0.f;
+  wait_acc();
+  tc_fence_after();
+  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + cg * kCols;
+  uint32_t v[kCols];
+#pragma unroll
+  for (int i = 0; i < kCols / 64; ++i) tmem_ld_32x64(taddr + 64 * i, v + 64 * i);
+  tmem_ld_wait();
+  tc_fence_before();
+  __syncwarp();
+  release_acc();
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c) {
+    const int col0 = n0 + c * 32;
+    const int s = ring_s;
+    if (lane == 0) {
+      // the box of the chunk kPreAhead ahead → the slab the store of two chunks ago has finished reading
+      tma_store_wait_read<1>();
+      int sa = s + kPreAhead;
+      if (sa >= kPreSlabs) sa -= kPreSlabs;
+      const bool same_tile = c + kPreAhead < kChunks;
+      const int la_row = same_tile ? row0 : next_m0 + q * 32;
+      const int la_col = same_tile ? col0 + kPreAhead * 32 : next_n_base + cg * kCols + (c + kPreAhead - kChunks) * 32;
+      if (same_tile || next_m0 >= 0) {
+        mbar_expect_tx(&pre_bar[sa], kPreSlabBytes);
+        tma_load_2d(slabs + sa * kPreSlabBytes, tmR, &pre_bar[sa], la_col, la_row);
+      }
+    }
+    uint8_t* slab = slabs + s * kPreSlabBytes;
+    const uint32_t slab_s = smem_u32(slab);
+    mbar_wait(&pre_bar[s], (ring_par >> s) & 1u);
+    ring_par ^= 1u << s;
+    ring_s = s + 1 == kPreSlabs ? 0 : s + 1;
+    uint4 pre[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pre[j] = lds128u(slab_s + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[32 * c + j]);
+    if (!kAct2 && p.bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 bb = lds128f(consts_s + (c * 32 + 4 * j) * 4);
+        f[4 * j + 0] += bb.x; f[4 * j + 1] += bb.y; f[4 * j + 2] += bb.z; f[4 * j + 3] += bb.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __half2* h = reinterpret_cast<const __half2*>(&pre[j]);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 x = __half22float2(h[t]);
+        if constexpr (kAct2) {
+          f[8 * j + 2 * t] *= quick_gelu_grad(x.x);
+          f[8 * j + 2 * t + 1] *= quick_gelu_grad(x.y);
+        } else {
+          f[8 * j + 2 * t] += x.x;
+          f[8 * j + 2 * t + 1] += x.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 o;
+      __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        h[t] = __floats2half2_rn(f[8 * j + 2 * t], f[8 * j + 2 * t + 1]);
+        if (kMode == kEpiResid && p.stats_out != nullptr) {  // statistics of the values as stored (fp16-rounded)
+          const float2 r = __half22float2(h[t]);
+          if (c == 0 && j == 0 && t == 0) st_x0 = r.x;
+          const float d0 = r.x - st_x0, d1 = r.y - st_x0;
+          st_sum += d0 + d1;
+          st_sq = fmaf(d0, d0, fmaf(d1, d1, st_sq));
+        }
+      }
+      sts128(slab_s + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4), o);
+    }
+    fence_proxy_async();  // generic-proxy writes → visible to the TMA engine
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(tmC, slab, col0, row0);
+      tma_store_commit();
+    }
+  }
+  if (!kAct2 && next_n_base >= 0) {  // park the next tile's biases (all reads of this tile's are done)
+#pragma unroll
+    for (int i = 0; i < kCPL; ++i) sts32f(consts_next_s + (kCPL * lane + i) * 4, nb[i]);
+    __syncwarp();
+  }
+  if (kMode == kEpiResid && p.stats_out != nullptr && row_ok)
+    *reinterpret_cast<float4*>(p.stats_out + ((size_t)(n0 / kCols) * p.M + row) * 4) =
+        make_float4(st_x0, st_sum, st_sq, 0.f);
+}
+
 // -------------------------------------------------------------------------------------------------
 // CTA-pair variant (cta_group::2), N % 256 == 0: a CTA pair computes 256 x 256 output tiles.
 // CTA h of the pair stages rows [m0 + 128·h, +128) of A and rows [n0 + 128·h, +128) of W per
@@ -688,27 +823,37 @@ struct TileWalk {
   }
 };
 
+#ifndef GB_PRE_TMA
+#define GB_PRE_TMA 1  // residual / saved pre-activation through TMA into the output slabs (gemm_epilogue_tile_pre)
+#endif
+template <int kMode>
 struct Gemm2Cfg {
   static constexpr int BN = 256;
+  static constexpr bool kPreTma = GB_PRE_TMA && (kMode == kEpiResid || kMode == kEpiAct2);
 #ifndef GB_STAGES2
 #define GB_STAGES2 ((GB_EPI_WARPS == 8 && GB_SLAB_COLS == 32) ? 5 : 4)  // measured: 4, 5 and 6 stages perform alike; 16 warps need the smem
 #endif
-  static constexpr int kStages = GB_STAGES2;
-  static constexpr int kSlabBytes = kEpiWarps2 * 2 * 64 * GB_SLAB_COLS;  // two 32-row output (half-)slabs per epilogue warp
+  static constexpr int kStages = kPreTma ? 4 : GB_STAGES2;  // the five rotating half-slabs take a stage's room
+  static constexpr int kSlabBytes = kPreTma ? kEpiWarps2 * kPreSlabs * kPreSlabBytes
+                                            : kEpiWarps2 * 2 * 64 * GB_SLAB_COLS;  // two 32-row output (half-)slabs per epilogue warp
   static constexpr int kConstBytes = kEpiWarps2 * 2 * kEpiCols * 8;  // per warp, double-buffered: biases + column sums
+  static constexpr int kPreBarBytes = kPreTma ? 512 : 0;             // one mbarrier per rotating half-slab
   static constexpr int kABytes = kBM * kBK * 2;        // 16 KB: this CTA's 128 rows of A
   static constexpr int kBBytes = (BN / 2) * kBK * 2;   // 16 KB: this CTA's half of the W tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kSlabBytes + kConstBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kSlabBytes + kConstBytes + 1024 + 256 + kPreBarBytes;
+  static_assert(kSmemBytes <= 232448, "shared memory per CTA");
+  static_assert(!kPreTma || kEpiWarps2 * kPreSlabs * 8 <= kPreBarBytes, "mbarrier room");
 };
 
 template <int kPairs, int kMode>
 __global__ void __launch_bounds__(kGemm2Threads, 1)
 gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
                              const __grid_constant__ CUtensorMap tmB,
-                             const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
-  using Cfg = Gemm2Cfg;
+                             const __grid_constant__ CUtensorMap tmC,
+                             const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
+  using Cfg = Gemm2Cfg<kMode>;
   constexpr int kStages = Cfg::kStages;
   constexpr int BN = Cfg::BN;
 
@@ -725,6 +870,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
   uint64_t* tfull_bar = bars + 2 * kStages;       // [2]        (each CTA waits on its own)
   uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]        (used on the leader)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* pre_bars = reinterpret_cast<uint64_t*>(smem_consts + Cfg::kConstBytes + 256);  // [warps][kPreSlabs] (kPreTma)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -747,12 +893,15 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
+    if constexpr (Cfg::kPreTma) tma_prefetch_desc(&tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);   // leader's arrive.expect_tx covering both CTAs' loads
       mbar_init(&empty_bar[s], kPairs);  // every leader's multicast commit
     }
+    if constexpr (Cfg::kPreTma)
+      for (int s = 0; s < kEpiWarps2 * kPreSlabs; ++s) mbar_init(&pre_bars[s], 1);  // the arming lane's arrive.expect_tx
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);    // the leader's multicast commit
       mbar_init(&tempty_bar[s], 2 * kEpiWarps2);  // the epilogue warps of both CTAs
@@ -876,41 +1025,79 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA,
       }
       __syncwarp();
     }
-    float4 lp[kLnMaxParts];
-    bool lp_pending = false;
-    uint4 pre_lo[kEpiCols / 16];
-    if ((kMode == kEpiResid || kMode == kEpiAct2) && cluster_id < num_tiles) {  // first tile's columns 0-63
-      const __half* pre_base = kMode == kEpiAct2 ? p.aux : p.resid;
-      const int pre_ld = kMode == kEpiAct2 ? p.ldo : p.ldr;
-      const int r = (cluster_id / n_tiles) * kClusterRows + row_off + (warp & 3) * 32 + lane;
-      if (pre_base != nullptr && r < p.M) {
-        const uint4* r4 = reinterpret_cast<const uint4*>(
-            pre_base + (size_t)r * pre_ld + (cluster_id % n_tiles) * BN + ((warp - 4) >> 2) * kEpiCols);
+    if constexpr (Cfg::kPreTma) {
+      uint8_t* my_slabs = smem_slabs + (warp - 4) * (kPreSlabs * kPreSlabBytes);
+      uint64_t* my_bars = pre_bars + (warp - 4) * kPreSlabs;
+      int ring_s = 0;
+      uint32_t ring_par = 0;
+      if (lane == 0 && cluster_id < num_tiles) {  // the first kPreAhead boxes of the first tile
+        const int r0 = (cluster_id / n_tiles) * kClusterRows + row_off + (warp & 3) * 32;
+        const int c0 = (cluster_id % n_tiles) * BN + ((warp - 4) >> 2) * kEpiCols;
 #pragma unroll
-        for (int j = 0; j < kEpiCols / 16; ++j) pre_lo[j] = r4[j];
+        for (int g = 0; g < kPreAhead; ++g) {
+          mbar_expect_tx(&my_bars[g], kPreSlabBytes);
+          tma_load_2d(my_slabs + g * kPreSlabBytes, &tmR, &my_bars[g], c0 + 32 * g, r0);
+        }
       }
-    }
-    TileWalk tw(cluster_id, num_clusters, n_tiles);
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      const int m0 = tw.mi * kClusterRows + row_off;
-      const int n0 = tw.ni * BN;
-      tw.next();
-      const bool more = tile + num_clusters < num_tiles;
-      const int next_m0 = more ? tw.mi * kClusterRows + row_off : -1;
-      const int next_n0 = more ? tw.ni * BN : -1;
-      gemm_epilogue_tile_tma<kMode>(
-          p, &tmC, smem_slabs + (warp - 4) * (128 * GB_SLAB_COLS), tmem_base + as * BN, m0, n0, warp, lane, ln_st, next_m0,
-          consts_s + (it & 1) * kStrip, consts_s + ((it + 1) & 1) * kStrip, next_n0, pre_lo, lp, lp_pending,
-          [&]() {
-            GB_STALL_T(t_tf);
-            mbar_wait(&tfull_bar[as], aphase);
-            GB_STALL_ADD(w_tfull, t_tf);
-          },
-          [&]() {
-            if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], rank & ~1u);
-          });
+      TileWalk tw(cluster_id, num_clusters, n_tiles);
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        const int m0 = tw.mi * kClusterRows + row_off;
+        const int n0 = tw.ni * BN;
+        tw.next();
+        const bool more = tile + num_clusters < num_tiles;
+        const int next_m0 = more ? tw.mi * kClusterRows + row_off : -1;
+        const int next_n0 = more ? tw.ni * BN : -1;
+        gemm_epilogue_tile_pre<kMode>(
+            p, &tmC, &tmR, my_slabs, my_bars, tmem_base + as * BN, m0, n0, warp, lane, next_m0,
+            consts_s + (it & 1) * kStrip, consts_s + ((it + 1) & 1) * kStrip, next_n0, ring_s, ring_par,
+            [&]() {
+              GB_STALL_T(t_tf);
+              mbar_wait(&tfull_bar[as], aphase);
+              GB_STALL_ADD(w_tfull, t_tf);
+            },
+            [&]() {
+              if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], rank & ~1u);
+            });
+      }
+    } else {
+      float4 lp[kLnMaxParts];
+      bool lp_pending = false;
+      uint4 pre_lo[kEpiCols / 16];
+      if ((kMode == kEpiResid || kMode == kEpiAct2) && cluster_id < num_tiles) {  // first tile's columns 0-63
+        const __half* pre_base = kMode == kEpiAct2 ? p.aux : p.resid;
+        const int pre_ld = kMode == kEpiAct2 ? p.ldo : p.ldr;
+        const int r = (cluster_id / n_tiles) * kClusterRows + row_off + (warp & 3) * 32 + lane;
+        if (pre_base != nullptr && r < p.M) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(
+              pre_base + (size_t)r * pre_ld + (cluster_id % n_tiles) * BN + ((warp - 4) >> 2) * kEpiCols);
+#pragma unroll
+          for (int j = 0; j < kEpiCols / 16; ++j) pre_lo[j] = r4[j];
+        }
+      }
+      TileWalk tw(cluster_id, num_clusters, n_tiles);
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        const int m0 = tw.mi * kClusterRows + row_off;
+        const int n0 = tw.ni * BN;
+        tw.next();
+        const bool more = tile + num_clusters < num_tiles;
+        const int next_m0 = more ? tw.mi * kClusterRows + row_off : -1;
+        const int next_n0 = more ? tw.ni * BN : -1;
+        gemm_epilogue_tile_tma<kMode>(
+            p, &tmC, smem_slabs + (warp - 4) * (128 * GB_SLAB_COLS), tmem_base + as * BN, m0, n0, warp, lane, ln_st, next_m0,
+            consts_s + (it & 1) * kStrip, consts_s + ((it + 1) & 1) * kStrip, next_n0, pre_lo, lp, lp_pending,
+            [&]() {
+              GB_STALL_T(t_tf);
+              mbar_wait(&tfull_bar[as], aphase);
+              GB_STALL_ADD(w_tfull, t_tf);
+            },
+            [&]() {
+              if (lane == 0) mbar_arrive_cluster(&tempty_bar[as], rank & ~1u);
+            });
+      }
     }
 #ifdef GB_GEMM_STALLS
     if (leader && warp == 4 && lane == 0) {
