@@ -259,6 +259,7 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
   const int word_end = (p.row_end + 31) >> 5;
   int cursor = p.row_begin >> 5;  // uniform over the CTA
   long long t_ph = t_start, c_a = 0, c_c = 0, c_d = 0;
+  long long w_load = 0, w_poll = 0, w_offer = 0, w_own = 0;   // diag 3: where warp 0 spends the walk
   while (true) {
     // ---- lower bounds of this round from the live boards; is any board still filling? ----
     if (tid == 0) { s_bc[2] = 0; s_bc[3] = 0; }
@@ -363,6 +364,7 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
       const uint32_t m = rel[warp * kRelLd + wi];
       if (m == 0) continue;
       // lane e fetches what the warp needs of row slot 32·wi + e (one round of loads per 32 slots)
+      long long t_w = p.diag == 3 ? clock64() : 0;
       int row_e = 0, own_e = 0;
       float pown_e = 0.f, val_e[4] = {0.f, 0.f, 0.f, 0.f};
       if ((m >> lane) & 1u) {
@@ -374,27 +376,141 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
         for (int gq = 0; gq < 4; ++gq)
           if (gq < nb && warp + 32 * gq < C) val_e[gq] = prow[warp + 32 * gq];
       }
+      // Rows another warp owns matter here only if they were REJECTED by their own board (then they are offered
+      // to mine), and that is rare — walking them one by one (eight shuffles and a poll per row and warp) made the
+      // early part of a scan, where every row is relevant to every warp, issue-bound at ≈1000 clocks per row.  So the
+      // word is cut at the rows this warp owns: the verdicts of the foreign rows in between are read by all lanes
+      // at once (lane e polls the decision byte of slot e), and only the rejected ones are then walked, in order.
+      const bool bit_l = (m >> lane) & 1u;
+      if (p.diag == 3) { __syncwarp(); const long long t = clock64(); w_load += t - t_w; t_w = t; }
+      const uint32_t mine_mask = __ballot_sync(0xffffffffu, bit_l && (own_e & 31) == warp);
+      // at or below the bound of its own board: rejected whatever happened since (its owner does not publish)
+      const uint32_t krej_mask = __ballot_sync(0xffffffffu, bit_l && !(pown_e > s_lb[own_e]));
+
+      auto fetch = [&](int e, int& own, float& p_own, int& idx, float& v0, float& v1, float& v2, float& v3) {
+        own = __shfl_sync(0xffffffffu, own_e, e);
+        p_own = __shfl_sync(0xffffffffu, pown_e, e);
+        idx = __shfl_sync(0xffffffffu, row_e, e) + p.idx0;
+        v0 = __shfl_sync(0xffffffffu, val_e[0], e); v1 = __shfl_sync(0xffffffffu, val_e[1], e);
+        v2 = __shfl_sync(0xffffffffu, val_e[2], e); v3 = __shfl_sync(0xffffffffu, val_e[3], e);
+      };
+      // :83-101 — a row rejected by its own board is offered to every other board (here: to this warp's boards)
+      auto offer = [&](int own, int idx, float v0, float v1, float v2, float v3) -> bool {
+        const float p_mine = lane == 0 ? v0 : lane == 1 ? v1 : lane == 2 ? v2 : v3;
+        bool need = false;
+        if (have_board && my_board != own) {
+          const int cj = s_cnt[my_board];
+          if (cj < k) {
+            v.ep[(size_t)my_board * k + cj] = p_mine;
+            v.ei[(size_t)my_board * k + cj] = idx;
+            s_cnt[my_board] = cj + 1;
+            s_last[my_board] = p_mine;
+            if constexpr (kSet) {
+              s_min[my_board] = fminf(s_min[my_board], p_mine);
+              if (G > 0) s_gm[(size_t)my_board * G + (cj >> 5)] = fminf(s_gm[(size_t)my_board * G + (cj >> 5)], p_mine);
+            }
+          } else if (s_last[my_board] < p_mine) {
+            need = true;
+          }
+        }
+        uint32_t nm = __ballot_sync(0xffffffffu, need);
+        const bool admitted = nm != 0;
+        while (nm) {
+          const int l = __ffs(nm) - 1;
+          nm &= nm - 1;
+          const float pj = l == 0 ? v0 : l == 1 ? v1 : l == 2 ? v2 : v3;
+          if (p.diag == 1 && lane == 0) atomicAdd(&s_dbg[3], 1);
+          if constexpr (kSet) {
+            const int jb = warp + 32 * l;
+            if (G > 0) lb_admit_set_gm(v, jb, pj, idx, p.rank, s_last, s_gm + (size_t)jb * G, G, lane);
+            else lb_admit_set(v, jb, pj, idx, p.rank, s_last, lane);
+          } else {
+            lb_admit(v, warp + 32 * l, pj, idx, p.rank, s_last, lane);
+          }
+        }
+        __syncwarp();
+        return admitted;
+      };
+
       uint32_t mm = m;
       while (mm) {
-        const int e = __ffs(mm) - 1;
-        mm &= mm - 1;
-        const int s = wi * 32 + e;
-        const int own = __shfl_sync(0xffffffffu, own_e, e);
-        const float p_own = __shfl_sync(0xffffffffu, pown_e, e);
-        const int idx = __shfl_sync(0xffffffffu, row_e, e) + p.idx0;
-        const float v0 = __shfl_sync(0xffffffffu, val_e[0], e), v1 = __shfl_sync(0xffffffffu, val_e[1], e);
-        const float v2 = __shfl_sync(0xffffffffu, val_e[2], e), v3 = __shfl_sync(0xffffffffu, val_e[3], e);
-        const float p_mine = lane == 0 ? v0 : lane == 1 ? v1 : lane == 2 ? v2 : v3;
-        const bool known_rej = !(p_own > s_lb[own]);  // at or below the bound: rejected whatever happened since
-        bool rejected;
-        if (p.diag == 1 && lane == 0) atomicAdd(&s_dbg[0], 1);
-        if ((own & 31) == warp) {
+        const uint32_t mine_left = mm & mine_mask;
+        const int o = mine_left ? __ffs(mine_left) - 1 : 32;
+        const uint32_t seg = mm & ~mine_mask & (o >= 32 ? 0xffffffffu : ((1u << o) - 1u));  // foreign rows before my next one
+        // My next own row is fetched and provisionally decided BEFORE the foreign verdicts are waited for: the warps
+        // form a chain through the decision bytes (row s is decided once the rows before it are), and what sits
+        // between "the last foreign verdict is in" and "my verdict is out" is that chain's step — a poll, two votes
+        // and a store instead of the ≈100 dependent instructions of fetch + decide.
+        int own = 0, idx = 0, c_own = 0;
+        float p_own = 0.f, v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+        bool fill = false, acc = false;
+        if (o < 32) {
+          fetch(o, own, p_own, idx, v0, v1, v2, v3);
+          c_own = s_cnt[own];
+          fill = c_own < k;
+          acc = fill || s_last[own] < p_own;
+        }
+        if (seg) {
+          uint8_t d = 2;
+          const bool poll = ((seg & ~krej_mask) >> lane) & 1u;
+          if (p.diag == 1 && poll) atomicAdd(&s_dbg[1], 1);
+          while (true) {   // warp-uniform loop (a divergent per-lane spin was 5x slower): lane e looks at slot e's byte
+            if (poll) d = dec[wi * 32 + lane];
+            if (__all_sync(0xffffffffu, d != 0)) break;
+            if (p.spin_sleep) __nanosleep(p.spin_sleep);
+          }
+          if (p.diag == 3) { const long long t = clock64(); w_poll += t - t_w; t_w = t; }
+          // Rejected rows are offered to my boards — and nearly always declined: a board that is full but has not
+          // admitted anything yet keeps the p of its k-th ARRIVAL as threshold while the only bound that holds for the
+          // whole round is its smallest entry, so it finds every rejected row of the round relevant.  Lane e holds
+          // row e's probabilities for my boards: all 32 rows are screened at once against the LIVE thresholds (exact
+          // at this moment; thresholds change only through an admission, which can lower one — the first admission
+          // of a board sorts it — so the rows not yet walked are screened again after every admission), and only
+          // the rows that pass are walked, in order.
+          uint32_t todo = __ballot_sync(0xffffffffu, ((seg >> lane) & 1u) && d == 2);
+          bool offered = false;
+          while (todo) {
+            bool take = false;
+            if ((todo >> lane) & 1u) {
+#pragma unroll
+              for (int gq = 0; gq < 4; ++gq) {
+                const int b = warp + 32 * gq;
+                if (gq < nb && b < C && b != own_e)
+                  take = take || s_cnt[b] < k || s_last[b] < val_e[gq];
+              }
+            }
+            uint32_t rej = __ballot_sync(0xffffffffu, take);
+            if (rej == 0) break;
+            bool admitted = false;
+            while (rej && !admitted) {
+              const int e = __ffs(rej) - 1;
+              rej &= rej - 1;
+              todo &= ~((2u << e) - 1u);   // rows up to e are settled
+              int own_f, idx_f;
+              float p_f, f0, f1, f2, f3;
+              fetch(e, own_f, p_f, idx_f, f0, f1, f2, f3);
+              if (p.diag == 1 && lane == 0) atomicAdd(&s_dbg[0], 1);
+              admitted = offer(own_f, idx_f, f0, f1, f2, f3);
+              offered = true;
+            }
+            if (!admitted) break;   // every row that passed has been walked and nothing changed in between
+          }
+          mm &= ~seg;
+          if (offered && o < 32) {   // an offer may have gone into the board my own row is about to meet
+            c_own = s_cnt[own];
+            fill = c_own < k;
+            acc = fill || s_last[own] < p_own;
+          }
+          if (p.diag == 3) { const long long t = clock64(); w_offer += t - t_w; t_w = t; }
+        }
+        if (o < 32) {
           // this warp owns the arg-max board: utils/clip_pseudolabels.py:73-82
-          const int c_own = s_cnt[own];
-          const bool fill = c_own < k;
-          const bool acc = fill || s_last[own] < p_own;
+          mm &= ~(1u << o);
+          const int s = wi * 32 + o;
+          if (p.diag == 1 && lane == 0) atomicAdd(&s_dbg[0], 1);
           // the verdict first, the bookkeeping after: the warps that wait for it are the critical path
-          if (!known_rej && lane == 0) dec[s] = acc ? 1 : 2;
+          if (!((krej_mask >> o) & 1u) && lane == 0) dec[s] = acc ? 1 : 2;
+          if (p.diag == 5 && lane == 0 && idx < (1 << 21)) p.ts[idx] = clock64();
           if (fill) {
             __syncwarp();
             if (lane == 0) {
@@ -415,54 +531,10 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
             } else {
               lb_admit(v, own, p_own, idx, p.rank, s_last, lane);
             }
-          }
-          rejected = !acc;
-        } else {
-          // would any of my boards take this row if it is offered?  (live state: exact)
-          bool need = false;
-          if (have_board) need = s_cnt[my_board] < k || s_last[my_board] < p_mine;
-          if (!__any_sync(0xffffffffu, need)) continue;
-          if (known_rej) {
-            rejected = true;
           } else {
-            uint8_t d;
-            if (p.diag == 1 && lane == 0) atomicAdd(&s_dbg[1], 1);
-            while ((d = dec[s]) == 0) { if (p.spin_sleep) __nanosleep(p.spin_sleep); }
-            rejected = d == 2;
+            offer(own, idx, v0, v1, v2, v3);
           }
-        }
-        if (rejected) {  // :83-101 — offered to every other board
-          bool need = false;
-          if (have_board && my_board != own) {
-            const int cj = s_cnt[my_board];
-            if (cj < k) {
-              v.ep[(size_t)my_board * k + cj] = p_mine;
-              v.ei[(size_t)my_board * k + cj] = idx;
-              s_cnt[my_board] = cj + 1;
-              s_last[my_board] = p_mine;
-              if constexpr (kSet) {
-                s_min[my_board] = fminf(s_min[my_board], p_mine);
-                if (G > 0) s_gm[(size_t)my_board * G + (cj >> 5)] = fminf(s_gm[(size_t)my_board * G + (cj >> 5)], p_mine);
-              }
-            } else if (s_last[my_board] < p_mine) {
-              need = true;
-            }
-          }
-          uint32_t nm = __ballot_sync(0xffffffffu, need);
-          while (nm) {
-            const int l = __ffs(nm) - 1;
-            nm &= nm - 1;
-            const float pj = l == 0 ? v0 : l == 1 ? v1 : l == 2 ? v2 : v3;
-            if (p.diag == 1 && lane == 0) atomicAdd(&s_dbg[3], 1);
-            if constexpr (kSet) {
-              const int jb = warp + 32 * l;
-              if (G > 0) lb_admit_set_gm(v, jb, pj, idx, p.rank, s_last, s_gm + (size_t)jb * G, G, lane);
-              else lb_admit_set(v, jb, pj, idx, p.rank, s_last, lane);
-            } else {
-              lb_admit(v, warp + 32 * l, pj, idx, p.rank, s_last, lane);
-            }
-          }
-          __syncwarp();
+          if (p.diag == 3) { const long long t = clock64(); w_own += t - t_w; t_w = t; }
         }
       }
     }
@@ -472,6 +544,22 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
   __syncthreads();
   if (p.diag == 2 && tid == 0) {   // phase clocks / 1024 instead of the event counters: collect+bounds, relevance, walk, rounds
     s_dbg[0] = (int32_t)(c_a >> 10); s_dbg[1] = (int32_t)(c_c >> 10); s_dbg[3] = (int32_t)(c_d >> 10); s_dbg[2] = s_dbg[5];
+  }
+  if (p.diag == 3) {   // the busiest warp's walk: kilo-clocks loading / polling / offers (+ 1000·warp) / own rows
+    if (lane == 0) {
+      slots[warp * 4 + 0] = (int32_t)(w_load >> 10); slots[warp * 4 + 1] = (int32_t)(w_poll >> 10);
+      slots[warp * 4 + 2] = (int32_t)(w_offer >> 10); slots[warp * 4 + 3] = (int32_t)(w_own >> 10);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int best = 0, bw = 0;
+      for (int w = 0; w < kLbpWarps; ++w) {
+        const int t = slots[w * 4] + slots[w * 4 + 2] + slots[w * 4 + 3];   // busy time (polling is waiting)
+        if (t > best) { best = t; bw = w; }
+      }
+      s_dbg[0] = slots[bw * 4]; s_dbg[1] = slots[bw * 4 + 1]; s_dbg[2] = slots[bw * 4 + 2] + 100000 * bw;
+      s_dbg[3] = slots[bw * 4 + 3];
+    }
   }
   if (tid == 0) {  // diagnostics, accumulated over the launches of a scan: header words 3..7 =
                    // events walked, decisions waited for, flagged rows, spill admissions, kernel clocks / 1024

@@ -410,6 +410,7 @@ struct LbReplayParams {
   int idx0;               // global image index of local row 0 (boards and rank[] use global indices)
   int set_groups = 0;     // set-mode boards: group minima per board kept in shared memory (0: none)
   int diag = 0;           // count events / waits / spill admissions into the state header (GB_LB_DIAG=1)
+  long long* ts = nullptr;  // GB_LB_DIAG=5: clock of every published verdict, by row (gb_debug_lb_ts)
   int spin_sleep = 32;    // ns a warp sleeps between polls of another warp's decision (GB_LB_SPIN_NS; 0 = busy poll)
 };
 
@@ -593,18 +594,20 @@ __device__ void lb_admit(const LbView& v, int j, float pj, int idx, const int32_
   const int k = v.k;
   float* ep = v.ep + (size_t)j * k;
   int32_t* ei = v.ei + (size_t)j * k;
-  const int64_t rnew = rank ? (int64_t)rank[idx] : (int64_t)idx;
   __syncwarp();
   if (v.srt[j]) {
     // pos = number of entries that stay in front of the new one (entries ≥ new; equal keys keep
-    // the old entry first — Python's sort is stable)
+    // the old entry first — Python's sort is stable).  Path ranks decide only between EQUAL probabilities, so
+    // rank[] (global memory: an L2 round trip on the sequential critical path of the replay) is read only then.
     int pos = 0;
     for (int e0 = 0; e0 < k; e0 += 32) {
       const int e = e0 + lane;
-      bool front = false;
-      if (e < k) {
-        const float pe = ep[e];
-        front = pe > pj || (pe == pj && (rank ? (int64_t)rank[ei[e]] : (int64_t)ei[e]) >= rnew);
+      const float pe = e < k ? ep[e] : -INFINITY;
+      bool front = pe > pj;
+      const bool tie = e < k && pe == pj;
+      if (__any_sync(0xffffffffu, tie)) {
+        const int64_t rnew = rank ? (int64_t)rank[idx] : (int64_t)idx;
+        if (tie) front = (rank ? (int64_t)rank[ei[e]] : (int64_t)ei[e]) >= rnew;
       }
       pos += __popc(__ballot_sync(0xffffffffu, front));
     }
@@ -851,6 +854,7 @@ int lb_set_finalize(gb_ctx* c, void* state, int C, int k, const int32_t* rank, v
   return GB_OK;
 }
 
+static long long* g_lb_ts = nullptr;
 int launch_replay(gb_ctx* c, void* state, int C, int k, const float* rows, int rows_row0,
                   const int32_t* pred, const int32_t* rank, const uint32_t* flags, int row_begin,
                   int row_end, int idx0, cudaStream_t st) {
@@ -882,6 +886,10 @@ int launch_replay(gb_ctx* c, void* state, int C, int k, const float* rows, int r
       diag = e ? atoi(e) : 0;
     }
     q.diag = diag;
+    if (diag == 5) {
+      if (!g_lb_ts) cudaMalloc(&g_lb_ts, sizeof(long long) << 21);
+      q.ts = g_lb_ts;
+    }
     if (path == 1) lb_replay_par_kernel<false><<<1, kLbpThreads, lb_replay_par_smem_bytes(C, k), st>>>(q);
     else {
       // GB_LB_NO_GROUPS=1 (tests): the whole-board scan that boards beyond ≈1.4 M entries fall back to
@@ -1044,4 +1052,12 @@ extern "C" int gb_pseudolabel_scan(gb_ctx* c, void* state, const void* F, const 
     if (chunk < chunk_cap) chunk *= 2;
   }
   return lb_set_finalize(c, state, C, k, rank, sort_scratch, st);
+}
+
+// Debug hook (GB_LB_DIAG=5): SM clock at which the verdict of each row (index < n ≤ 2^21) was published by the
+// parallel replay; 0 for rows whose verdict was implied by the bounds.
+extern "C" int gb_debug_lb_ts(long long* out, int n) {
+  if (!out || n <= 0 || n > (1 << 21)) return GB_ERR_ARG;
+  if (!g_lb_ts || cudaDeviceSynchronize() != cudaSuccess) return GB_ERR_CUDA;
+  return cudaMemcpy(out, g_lb_ts, sizeof(long long) * n, cudaMemcpyDeviceToHost) == cudaSuccess ? GB_OK : GB_ERR_CUDA;
 }
