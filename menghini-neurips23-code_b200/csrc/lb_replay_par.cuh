@@ -58,10 +58,13 @@ __device__ __forceinline__ int lbp_block_excl_scan(int v, int32_t* s_warp, int& 
   return base + x - v;
 }
 
+// decision bytes | slots | relevance masks | scan scratch, broadcast words, diagnostics | phase clocks, 16-byte aligned
+constexpr size_t kLbpFixedBytes =
+    ((size_t)kLbpRound + (size_t)kLbpRound * 4 + (size_t)kLbpWarps * (kLbpRound / 32) * 4 + (size_t)(kLbpWarps + 4 + 8) * 4 + 32 + 15) &
+    ~size_t(15);
 inline size_t lb_replay_par_smem_bytes(int C, int k, bool set_mode = false) {
   const size_t boards = set_mode ? 0 : (size_t)C * k * 8 + (size_t)C * 4 + (size_t)kLbpWarps * 3 * (k + 1) * 4;
-  return (size_t)5 * C * 4 + boards + (size_t)kLbpRound * 4 + (size_t)kLbpWarps * (kLbpRound / 32) * 4 +
-         (size_t)(kLbpWarps + 4 + 8) * 4 + kLbpRound + 16;
+  return kLbpFixedBytes + (size_t)5 * C * 4 + boards + 16;
 }
 // kSet: minima of every group of 32 consecutive board slots, [C][ceil(k/32)] floats, when they fit beside the rest
 // (C·k ≲ 1.4 M entries): an admission then reads one or two 128-byte groups instead of the whole board.
@@ -69,6 +72,21 @@ constexpr size_t kLbpSmemMax = 200 * 1024;
 inline int lb_set_groups(int C, int k) {
   const int G = (k + 31) / 32;
   return lb_replay_par_smem_bytes(C, k, true) + (size_t)C * G * 4 <= kLbpSmemMax ? G : 0;
+}
+
+// decision bytes: volatile shared-space accesses through a 32-bit shared address
+__device__ __forceinline__ uint32_t lbp_lds_u8(uint32_t a) {
+  uint32_t x;
+  asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(x) : "r"(a) : "memory");
+  return x;
+}
+__device__ __forceinline__ uint32_t lbp_lds_u32(uint32_t a) {   // boards' counts / thresholds: written by the owner warp only
+  uint32_t x;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(a) : "memory");
+  return x;
+}
+__device__ __forceinline__ void lbp_sts_u8(uint32_t a, uint32_t x) {
+  asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(a), "r"(x) : "memory");
 }
 
 __device__ __forceinline__ float lbp_warp_min(float m) {
@@ -189,8 +207,24 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
   }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nb = (C + 31) >> 5;  // boards per warp (≤ 4): lane l < nb of warp w ↔ board w + 32·l
-  // ---- shared memory carve-up (every region is a multiple of 4 bytes) ----
-  float* s_last = reinterpret_cast<float*>(lb_smem);                 // [C] acceptance threshold: p of the last list entry
+  // ---- shared memory carve-up ----
+  // The regions the sequential walk touches on its critical path sit at FIXED offsets (decision bytes first): their
+  // addresses are constants instead of arithmetic on C and k that the compiler — capped at 64 registers by the 1024
+  // threads — re-did, with two special-register reads for the generic-to-shared conversion, in every iteration of the
+  // poll loop.
+  volatile uint8_t* dec = reinterpret_cast<volatile uint8_t*>(lb_smem);     // [kLbpRound] 0 pending, 1 accepted, 2 rejected
+  // (opaque moves: the compiler otherwise re-derives these addresses — a special-register read each — wherever it
+  // needs them instead of keeping them in a register)
+  uint32_t dec_s, last_s;
+  asm volatile("mov.u32 %0, %1;" : "=r"(dec_s) : "r"(smem_u32(lb_smem)));
+  asm volatile("mov.u32 %0, %1;" : "=r"(last_s) : "r"(smem_u32(lb_smem + kLbpFixedBytes)));   // s_last; s_cnt follows
+  int32_t* slots = reinterpret_cast<int32_t*>(lb_smem + kLbpRound);         // [kLbpRound]
+  uint32_t* rel = reinterpret_cast<uint32_t*>(slots + kLbpRound);           // [32][kLbpRound/32]
+  int32_t* s_warp = reinterpret_cast<int32_t*>(rel + kLbpWarps * (kLbpRound / 32));  // [32] scan scratch
+  int32_t* s_bc = s_warp + kLbpWarps;                                // [4] n, cursor, boards still filling, … nearly full
+  int32_t* s_dbg = s_bc + 4;                                         // [8] diagnostics (→ header words 3..7)
+  long long* s_clk = reinterpret_cast<long long*>(s_dbg + 8);        // [4] diag 2: last stamp, clocks of phases a / c / d
+  float* s_last = reinterpret_cast<float*>(lb_smem + kLbpFixedBytes);  // [C] acceptance threshold: p of the last list entry
   int32_t* s_cnt = reinterpret_cast<int32_t*>(s_last + C);           // [C]
   float* s_lb = reinterpret_cast<float*>(s_cnt + C);                 // [C] lower bounds of this round
   float* s_min = s_lb + C;                                           // [C] kSet: running minimum of a never-sorted board
@@ -208,16 +242,10 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
     v.sr = v.si + k + 1;
     carve = scratch + (size_t)kLbpWarps * 3 * (k + 1);
   }
-  int32_t* slots = reinterpret_cast<int32_t*>(carve);                // [kLbpRound]
-  uint32_t* rel = reinterpret_cast<uint32_t*>(slots + kLbpRound);    // [32][kLbpRound/32]
-  int32_t* s_warp = reinterpret_cast<int32_t*>(rel + kLbpWarps * (kLbpRound / 32));  // [32] scan scratch
-  int32_t* s_bc = s_warp + kLbpWarps;                                // [4] n, cursor, boards still filling, … nearly full
-  int32_t* s_dbg = s_bc + 4;                                         // [8] diagnostics (→ header words 3..7)
-  volatile uint8_t* dec = reinterpret_cast<volatile uint8_t*>(s_dbg + 8);  // [kLbpRound] 0 pending, 1 accepted, 2 rejected
   constexpr int kRelLd = kLbpRound / 32;
   const int G = kSet ? p.set_groups : 0;    // group minima of the set-mode boards ([C][G]; 0: not kept)
   float* s_gm = reinterpret_cast<float*>(
-      lb_smem + ((reinterpret_cast<uint8_t*>(s_dbg + 8) - lb_smem + kLbpRound + 15) & ~size_t(15)));
+      lb_smem + ((reinterpret_cast<uint8_t*>(carve) - lb_smem + 15) & ~size_t(15)));
 
   if (tid < 8) s_dbg[tid] = 0;
   const long long t_start = clock64();
@@ -258,8 +286,7 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
 
   const int word_end = (p.row_end + 31) >> 5;
   int cursor = p.row_begin >> 5;  // uniform over the CTA
-  long long t_ph = t_start, c_a = 0, c_c = 0, c_d = 0;
-  long long w_load = 0, w_poll = 0, w_offer = 0, w_own = 0;   // diag 3: where warp 0 spends the walk
+  if (tid == 0) { s_clk[0] = t_start; s_clk[1] = 0; s_clk[2] = 0; s_clk[3] = 0; }   // diag 2: last stamp, phases a / c / d
   while (true) {
     // ---- lower bounds of this round from the live boards; is any board still filling? ----
     if (tid == 0) { s_bc[2] = 0; s_bc[3] = 0; }
@@ -331,7 +358,7 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
     for (int i = tid; i < kLbpWarps * n_words; i += kLbpThreads) rel[(i / n_words) * kRelLd + (i % n_words)] = 0u;
     for (int i = tid; i < n; i += kLbpThreads) dec[i] = 0;
     __syncthreads();
-    if (p.diag == 2) { const long long t = clock64(); c_a += t - t_ph; t_ph = t; }
+    if (p.diag == 2 && tid == 0) { const long long t = clock64(); s_clk[1] += t - s_clk[0]; s_clk[0] = t; }
     // ---- (c) relevance: bit s of rel[w] ⇔ row slots[s] beats the bound of some board owned by warp w ----
     for (int s0 = warp * 32; s0 < n; s0 += kLbpWarps * 32) {
       const int s = s0 + lane;
@@ -356,7 +383,7 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
       }
     }
     __syncthreads();
-    if (p.diag == 2) { const long long t = clock64(); c_c += t - t_ph; t_ph = t; }
+    if (p.diag == 2 && tid == 0) { const long long t = clock64(); s_clk[2] += t - s_clk[0]; s_clk[0] = t; }
     // ---- (d) replay: every warp walks its relevant rows in index order ----
     const int my_board = warp + 32 * lane;            // meaningful for lane < nb
     const bool have_board = lane < nb && my_board < C;
@@ -364,7 +391,6 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
       const uint32_t m = rel[warp * kRelLd + wi];
       if (m == 0) continue;
       // lane e fetches what the warp needs of row slot 32·wi + e (one round of loads per 32 slots)
-      long long t_w = p.diag == 3 ? clock64() : 0;
       int row_e = 0, own_e = 0;
       float pown_e = 0.f, val_e[4] = {0.f, 0.f, 0.f, 0.f};
       if ((m >> lane) & 1u) {
@@ -382,7 +408,6 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
       // word is cut at the rows this warp owns: the verdicts of the foreign rows in between are read by all lanes
       // at once (lane e polls the decision byte of slot e), and only the rejected ones are then walked, in order.
       const bool bit_l = (m >> lane) & 1u;
-      if (p.diag == 3) { __syncwarp(); const long long t = clock64(); w_load += t - t_w; t_w = t; }
       const uint32_t mine_mask = __ballot_sync(0xffffffffu, bit_l && (own_e & 31) == warp);
       // at or below the bound of its own board: rejected whatever happened since (its owner does not publish)
       const uint32_t krej_mask = __ballot_sync(0xffffffffu, bit_l && !(pown_e > s_lb[own_e]));
@@ -446,20 +471,19 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
         bool fill = false, acc = false;
         if (o < 32) {
           fetch(o, own, p_own, idx, v0, v1, v2, v3);
-          c_own = s_cnt[own];
+          c_own = (int)lbp_lds_u32(last_s + 4u * (uint32_t)(C + own));
           fill = c_own < k;
-          acc = fill || s_last[own] < p_own;
+          acc = fill || __uint_as_float(lbp_lds_u32(last_s + 4u * (uint32_t)own)) < p_own;
         }
         if (seg) {
           uint8_t d = 2;
           const bool poll = ((seg & ~krej_mask) >> lane) & 1u;
           if (p.diag == 1 && poll) atomicAdd(&s_dbg[1], 1);
           while (true) {   // warp-uniform loop (a divergent per-lane spin was 5x slower): lane e looks at slot e's byte
-            if (poll) d = dec[wi * 32 + lane];
+            if (poll) d = (uint8_t)lbp_lds_u8(dec_s + wi * 32 + lane);
             if (__all_sync(0xffffffffu, d != 0)) break;
             if (p.spin_sleep) __nanosleep(p.spin_sleep);
           }
-          if (p.diag == 3) { const long long t = clock64(); w_poll += t - t_w; t_w = t; }
           // Rejected rows are offered to my boards — and nearly always declined: a board that is full but has not
           // admitted anything yet keeps the p of its k-th ARRIVAL as threshold while the only bound that holds for the
           // whole round is its smallest entry, so it finds every rejected row of the round relevant.  Lane e holds
@@ -497,11 +521,10 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
           }
           mm &= ~seg;
           if (offered && o < 32) {   // an offer may have gone into the board my own row is about to meet
-            c_own = s_cnt[own];
+            c_own = (int)lbp_lds_u32(last_s + 4u * (uint32_t)(C + own));
             fill = c_own < k;
-            acc = fill || s_last[own] < p_own;
+            acc = fill || __uint_as_float(lbp_lds_u32(last_s + 4u * (uint32_t)own)) < p_own;
           }
-          if (p.diag == 3) { const long long t = clock64(); w_offer += t - t_w; t_w = t; }
         }
         if (o < 32) {
           // this warp owns the arg-max board: utils/clip_pseudolabels.py:73-82
@@ -509,7 +532,7 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
           const int s = wi * 32 + o;
           if (p.diag == 1 && lane == 0) atomicAdd(&s_dbg[0], 1);
           // the verdict first, the bookkeeping after: the warps that wait for it are the critical path
-          if (!((krej_mask >> o) & 1u) && lane == 0) dec[s] = acc ? 1 : 2;
+          if (!((krej_mask >> o) & 1u) && lane == 0) lbp_sts_u8(dec_s + s, acc ? 1u : 2u);
           if (p.diag == 5 && lane == 0 && idx < (1 << 21)) p.ts[idx] = clock64();
           if (fill) {
             __syncwarp();
@@ -534,32 +557,15 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
           } else {
             offer(own, idx, v0, v1, v2, v3);
           }
-          if (p.diag == 3) { const long long t = clock64(); w_own += t - t_w; t_w = t; }
         }
       }
     }
     __syncthreads();
-    if (p.diag == 2) { const long long t = clock64(); c_d += t - t_ph; t_ph = t; }
+    if (p.diag == 2 && tid == 0) { const long long t = clock64(); s_clk[3] += t - s_clk[0]; s_clk[0] = t; }
   }
   __syncthreads();
   if (p.diag == 2 && tid == 0) {   // phase clocks / 1024 instead of the event counters: collect+bounds, relevance, walk, rounds
-    s_dbg[0] = (int32_t)(c_a >> 10); s_dbg[1] = (int32_t)(c_c >> 10); s_dbg[3] = (int32_t)(c_d >> 10); s_dbg[2] = s_dbg[5];
-  }
-  if (p.diag == 3) {   // the busiest warp's walk: kilo-clocks loading / polling / offers (+ 1000·warp) / own rows
-    if (lane == 0) {
-      slots[warp * 4 + 0] = (int32_t)(w_load >> 10); slots[warp * 4 + 1] = (int32_t)(w_poll >> 10);
-      slots[warp * 4 + 2] = (int32_t)(w_offer >> 10); slots[warp * 4 + 3] = (int32_t)(w_own >> 10);
-    }
-    __syncthreads();
-    if (tid == 0) {
-      int best = 0, bw = 0;
-      for (int w = 0; w < kLbpWarps; ++w) {
-        const int t = slots[w * 4] + slots[w * 4 + 2] + slots[w * 4 + 3];   // busy time (polling is waiting)
-        if (t > best) { best = t; bw = w; }
-      }
-      s_dbg[0] = slots[bw * 4]; s_dbg[1] = slots[bw * 4 + 1]; s_dbg[2] = slots[bw * 4 + 2] + 100000 * bw;
-      s_dbg[3] = slots[bw * 4 + 3];
-    }
+    s_dbg[0] = (int32_t)(s_clk[1] >> 10); s_dbg[1] = (int32_t)(s_clk[2] >> 10); s_dbg[3] = (int32_t)(s_clk[3] >> 10); s_dbg[2] = s_dbg[5];
   }
   if (tid == 0) {  // diagnostics, accumulated over the launches of a scan: header words 3..7 =
                    // events walked, decisions waited for, flagged rows, spill admissions, kernel clocks / 1024
