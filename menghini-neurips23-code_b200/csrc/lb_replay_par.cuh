@@ -360,27 +360,37 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
     __syncthreads();
     if (p.diag == 2 && tid == 0) { const long long t = clock64(); s_clk[1] += t - s_clk[0]; s_clk[0] = t; }
     // ---- (c) relevance: bit s of rel[w] ⇔ row slots[s] beats the bound of some board owned by warp w ----
+    // A warp takes 32 slots at a time; lane l tests the boards l, l + 32, … (the boards of WARP l) of every slot and
+    // collects warp l's 32 relevance bits in a register: word (l, group) has this one writer, so the slot loop holds
+    // no atomics and the loads of several slots are in flight together (one atomicOr per load, each waiting for its
+    // L2 round trip, made this phase a quarter of a scan).
+    float lbv[4];
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq) lbv[gq] = (gq < nb && lane + 32 * gq < C) ? s_lb[lane + 32 * gq] : INFINITY;
     for (int s0 = warp * 32; s0 < n; s0 += kLbpWarps * 32) {
       const int s = s0 + lane;
-      int row_s = 0;
+      int row_s = 0, own_s = 0;
       bool ka = false;
       if (s < n) {
         row_s = slots[s];
-        const int own_s = p.pred[row_s];
+        own_s = p.pred[row_s];
         ka = s_ka[own_s] != 0;   // sure to be appended to its own board: nobody else is offered this row
-        if (ka) atomicOr(&rel[(own_s & 31) * kRelLd + (s >> 5)], 1u << (s & 31));
       }
-      uint32_t todo = __ballot_sync(0xffffffffu, s < n && !ka);
-      while (todo) {
-        const int e = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int ss = s0 + e;
+      const uint32_t todo = __ballot_sync(0xffffffffu, s < n && !ka);
+      uint32_t bits = 0;
+#pragma unroll 4
+      for (int e = 0; e < 32; ++e) {
+        if (!((todo >> e) & 1u)) continue;
         const float* prow = p.rows + (size_t)(__shfl_sync(0xffffffffu, row_s, e) - p.rows_row0) * C;
-        for (int gq = 0; gq < nb; ++gq) {
-          const int j = lane + 32 * gq;      // the owner warp of board j is j % 32 == lane
-          if (j < C && prow[j] > s_lb[j]) atomicOr(&rel[lane * kRelLd + (ss >> 5)], 1u << (ss & 31));
-        }
+        bool hit = false;
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq)
+          if (gq < nb && lane + 32 * gq < C) hit = hit || prow[lane + 32 * gq] > lbv[gq];
+        if (hit) bits |= 1u << e;
       }
+      rel[lane * kRelLd + (s0 >> 5)] = bits;
+      __syncwarp();
+      if (ka) atomicOr(&rel[(own_s & 31) * kRelLd + (s >> 5)], 1u << (s & 31));
     }
     __syncthreads();
     if (p.diag == 2 && tid == 0) { const long long t = clock64(); s_clk[2] += t - s_clk[0]; s_clk[0] = t; }
