@@ -5,14 +5,15 @@
 //
 // Boards evolve independently of one another except for ONE bit per image: "was it rejected by the board of
 // its own arg-max class" (only then is it offered to the other boards, :83-101).  So board j is owned by warp
-// j % 32 (lane l of warp w looks after board w + 32·l); every warp walks the flagged rows in index order but
-// stops only at the rows that can matter to one of ITS boards (p_j > lower bound of board j at the start of
-// the round — a full board's minimum never decreases), and the owner of the arg-max board publishes its
-// accept / reject decision in a shared-memory byte that the other warps wait for only when (a) one of their
-// boards would really take the row and (b) the decision is not already implied by the lower bound
-// (p_own ≤ bound ⇒ rejected).  A warp waits only on rows ≤ the one it is at, whose owner never waits at that
-// row: no cycle, and all 32 warps are resident (one CTA).  Every board sees exactly the operation sequence of
-// the single-warp replay, so the result is bit-identical to it.
+// j % 32 (lane l of warp w looks after board w + 32·l); every warp goes through the flagged rows in index order,
+// 32 at a time, but looks only at the rows that can matter to one of ITS boards (p_j > lower bound of board j at
+// the start of the round — a full board's minimum never decreases).  The owner of a row's arg-max board decides it
+// from the live board and publishes accept / reject in a shared-memory byte; the other warps read the bytes of the
+// rows between two rows of their own all at once (lane e polls slot e; a verdict implied by the lower bound —
+// p_own ≤ bound ⇒ rejected — is not waited for), screen the rejected ones against the live thresholds of their
+// boards and walk only those a board would take.  A warp waits only on rows before the own row it is about to
+// decide, whose owners never wait at or beyond their row: no cycle, and all 32 warps are resident (one CTA).
+// Every board sees exactly the operation sequence of the single-warp replay, so the result is bit-identical to it.
 //
 // kSet = true is the same walk for boards too large for shared memory (GRIP grows k to N/C,
 // methods/semi_supervised_learning/pseudo_iterative.py:62-75): the boards stay in the caller's state (global
