@@ -106,3 +106,35 @@ def test_install_without_the_reference_tree_patches_nothing():
     if importlib.util.find_spec("methods") is not None:
         pytest.skip("a `methods` package is importable here")
     assert PL.install() == []
+
+
+def test_prob_dtype_reads_and_validates_the_environment(monkeypatch):
+    CP = importlib.import_module("menghini-neurips23-code_b200.utils.clip_pseudolabels")
+    monkeypatch.delenv("GRIPB200_PROB_DTYPE", raising=False)
+    assert CP.prob_dtype() == "fp32"                          # the reference's CPU arithmetic is the default
+    monkeypatch.setenv("GRIPB200_PROB_DTYPE", "FP16")
+    assert CP.prob_dtype() == "fp16"                          # the reference's CUDA arithmetic, on request
+    monkeypatch.setenv("GRIPB200_PROB_DTYPE", "bf16")
+    with pytest.raises(ValueError):
+        CP.prob_dtype()
+
+
+def test_pool_cache_key_follows_the_files(tmp_path, monkeypatch):
+    """The pool-feature cache (GRIP re-encodes the same pool every iteration under the frozen tower,
+    methods/semi_supervised_learning/pseudo_iterative.py:62-75) is keyed by path, mtime and size of EVERY file."""
+    import os
+    CP = importlib.import_module("menghini-neurips23-code_b200.utils.clip_pseudolabels")
+    monkeypatch.delenv("GRIPB200_POOL_CACHE", raising=False)
+    files = []
+    for i in range(3):
+        f = tmp_path / f"{i}.png"
+        f.write_bytes(b"x" * (10 + i))
+        files.append(str(f))
+    k0 = CP._pool_cache_key(files)
+    assert k0 is not None and k0[0] == 3 and CP._pool_cache_key(list(files)) == k0
+    assert CP._pool_cache_key(files[::-1]) != k0              # the order of the pool is part of the result
+    (tmp_path / "1.png").write_bytes(b"y" * 40)               # a file rewritten → another pool
+    assert CP._pool_cache_key(files) != k0
+    assert CP._pool_cache_key(files + [str(tmp_path / "missing.png")]) is None   # unreadable → no caching, no error here
+    monkeypatch.setenv("GRIPB200_POOL_CACHE", "0")
+    assert CP._pool_cache_key(files) is None
