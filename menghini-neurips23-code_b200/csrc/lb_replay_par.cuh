@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
     }
     __syncthreads();
     if (p.diag == 2 && tid == 0) { const long long t = clock64(); s_clk[2] += t - s_clk[0]; s_clk[0] = t; }
-    // ---- (d) replay: every warp walks its relevant rows in index order ----
+    // ---- (d) replay: every warp goes through the words of its relevant rows in index order ----
     const int my_board = warp + 32 * lane;            // meaningful for lane < nb
     const bool have_board = lane < nb && my_board < C;
     for (int wi = 0; wi < n_words; ++wi) {
