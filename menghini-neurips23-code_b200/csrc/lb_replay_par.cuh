@@ -379,15 +379,26 @@ __global__ void __launch_bounds__(kLbpThreads, 1) lb_replay_par_kernel(const LbR
       }
       const uint32_t todo = __ballot_sync(0xffffffffu, s < n && !ka);
       uint32_t bits = 0;
-#pragma unroll 4
-      for (int e = 0; e < 32; ++e) {
-        if (!((todo >> e) & 1u)) continue;
-        const float* prow = p.rows + (size_t)(__shfl_sync(0xffffffffu, row_s, e) - p.rows_row0) * C;
-        bool hit = false;
+      // two slots per step, their (up to) eight loads issued together and unconditionally: a short-circuit `||` over
+      // the column groups made each load wait for the comparison of the one before — four L2 round trips in a row
+#pragma unroll 1
+      for (int e0 = 0; e0 < 32; e0 += 2) {
+        if (!((todo >> e0) & 3u)) continue;
+        float val[2][4];
 #pragma unroll
-        for (int gq = 0; gq < 4; ++gq)
-          if (gq < nb && lane + 32 * gq < C) hit = hit || prow[lane + 32 * gq] > lbv[gq];
-        if (hit) bits |= 1u << e;
+        for (int u = 0; u < 2; ++u) {
+          const bool on = (todo >> (e0 + u)) & 1u;
+          const int r = __shfl_sync(0xffffffffu, row_s, e0 + u);
+          const float* prow = p.rows + (size_t)((on ? r : p.rows_row0) - p.rows_row0) * C;
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq)
+            val[u][gq] = (on && gq < nb && lane + 32 * gq < C) ? prow[lane + 32 * gq] : -INFINITY;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const bool hit = (val[u][0] > lbv[0]) | (val[u][1] > lbv[1]) | (val[u][2] > lbv[2]) | (val[u][3] > lbv[3]);
+          if (hit) bits |= 1u << (e0 + u);
+        }
       }
       rel[lane * kRelLd + (s0 >> 5)] = bits;
       __syncwarp();
